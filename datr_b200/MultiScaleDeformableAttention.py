@@ -1,0 +1,122 @@
+"""Drop-in for the reference's native extension module `MultiScaleDeformableAttention`.
+
+Same two callables, argument order and error behaviour as the pybind module built from
+models/dino/ops/src/vision.cpp:13-16 (dispatch ms_deform_attn.h:21-60, host code
+cuda/ms_deform_attn_cuda.cu:20-153), implemented as a thin ctypes shim over the C ABI in
+include/datr_msda.h.  `install()` registers it under the reference's import name so that
+`import MultiScaleDeformableAttention as MSDA` (ms_deform_attn_func.py:18) resolves to it.
+
+Thread-safety: no Python-side state; forward runs on the caller's thread, backward on autograd's
+worker thread, both on the *current* torch CUDA stream of the tensors' device.
+"""
+from __future__ import annotations
+
+import sys
+
+import torch
+
+from . import native
+
+_DTYPES = {torch.float32: 0, torch.float64: 1}
+
+# Optional launch timers: bench.py sets this to a list and each launch appends
+# (kind, shape_key, start_event, end_event) recorded on the launching stream.
+_timers = None
+
+
+def _check(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, extra=()):
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), *extra]
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")           # ms_deform_attn.h:38,60
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")  # cu:28-32, :93-98
+    for name, t in named:
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor")        # cu:34-38, :100-105
+        if t.device != value.device:
+            raise RuntimeError(f"{name} must be on the same device as value")
+    if value.dtype not in _DTYPES:
+        # AT_DISPATCH_FLOATING_TYPES (cu:64,134): float and double only
+        raise RuntimeError(f'"ms_deform_attn_cuda" not implemented for \'{value.dtype}\'')
+    for name, t in named[3:]:
+        if t.dtype != value.dtype:
+            raise RuntimeError(f"{name} must have the dtype of value ({value.dtype}), got {t.dtype}")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes and level_start_index must be int64")
+    if value.dim() != 4 or sampling_loc.dim() != 6 or attn_weight.dim() != 5:
+        raise RuntimeError("expected value[N,S,M,D], sampling_loc[N,Lq,M,L,P,2], attn_weight[N,Lq,M,L,P]")
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    if tuple(sampling_loc.shape) != (N, Lq, M, L, P, 2) or tuple(attn_weight.shape) != (N, Lq, M, L, P) \
+            or level_start_index.numel() != L or tuple(spatial_shapes.shape) != (L, 2):
+        raise RuntimeError("inconsistent MSDeformAttn argument shapes")
+    return N, S, M, D, L, Lq, P
+
+
+def _check_step(batch, im2col_step):
+    step = min(batch, int(im2col_step))
+    if step <= 0 or batch % step != 0:
+        raise RuntimeError(f"batch({batch}) must divide im2col_step({step})")  # cu:52, :119
+
+
+def _raise(rc, what):
+    raise RuntimeError(f"{what} failed (code {rc}): {native.lib().datr_last_error().decode()}")
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step):
+    N, S, M, D, L, Lq, P = _check(value, spatial_shapes, level_start_index, sampling_loc, attn_weight)
+    _check_step(N, im2col_step)
+    lib = native.lib()
+    with torch.cuda.device(value.device):
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        stream = torch.cuda.current_stream()
+        if _timers is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        rc = lib.datr_msda_forward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                   sampling_loc.data_ptr(), attn_weight.data_ptr(), N, S, M, D, L, Lq, P,
+                                   _DTYPES[value.dtype], out.data_ptr(), stream.cuda_stream)
+        if _timers is not None:
+            e1.record(stream)
+            _timers.append(("fwd", (N, S, M, D, L, Lq, P, value.element_size()), e0, e1))
+    if rc != 0:
+        _raise(rc, "ms_deform_attn_forward")
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step):
+    N, S, M, D, L, Lq, P = _check(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                  extra=(("grad_output", grad_output),))
+    _check_step(N, im2col_step)
+    if grad_output.numel() != N * Lq * M * D:
+        raise RuntimeError("grad_output has the wrong number of elements")
+    lib = native.lib()
+    with torch.cuda.device(value.device):
+        grad_value = torch.empty_like(value)            # zero-filled by the library on the stream
+        grad_loc = torch.empty_like(sampling_loc)
+        grad_attn = torch.empty_like(attn_weight)
+        stream = torch.cuda.current_stream()
+        if _timers is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        rc = lib.datr_msda_backward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                    sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
+                                    N, S, M, D, L, Lq, P, _DTYPES[value.dtype],
+                                    grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
+                                    stream.cuda_stream)
+        if _timers is not None:
+            e1.record(stream)
+            _timers.append(("bwd", (N, S, M, D, L, Lq, P, value.element_size()), e0, e1))
+    if rc != 0:
+        _raise(rc, "ms_deform_attn_backward")
+    return [grad_value, grad_loc, grad_attn]
+
+
+def install(name: str = "MultiScaleDeformableAttention"):
+    """Register this module under the reference's extension name."""
+    sys.modules[name] = sys.modules[__name__]
+    return sys.modules[__name__]

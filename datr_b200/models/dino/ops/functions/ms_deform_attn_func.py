@@ -1,0 +1,34 @@
+"""Autograd binding of the native op -- mirror of the reference's
+models/dino/ops/functions/ms_deform_attn_func.py:21-38 (same class name, argument order, saved
+tensors, `once_differentiable`, and the (grad_value, None, None, grad_loc, grad_attn, None) return).
+
+The reference file also carries a pure-PyTorch implementation for debugging
+(ms_deform_attn_core_pytorch, :41-61).  This package deliberately has none: the product path is the
+CUDA library only and raises when it is unavailable; the CPU restatement lives under oracle/ and is
+test infrastructure.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from datr_b200 import MultiScaleDeformableAttention as MSDA
+
+
+class MSDeformAttnFunction(Function):
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        output = MSDA.ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
+                                             sampling_locations, attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index,
+                              sampling_locations, attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, loc, attn = ctx.saved_tensors
+        grad_value, grad_loc, grad_attn = MSDA.ms_deform_attn_backward(
+            value, shapes, level_start, loc, attn, grad_output.contiguous(), ctx.im2col_step)
+        return grad_value, None, None, grad_loc, grad_attn, None

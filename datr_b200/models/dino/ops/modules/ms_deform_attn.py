@@ -1,0 +1,94 @@
+"""MSDeformAttn module -- host-side mirror of the reference's
+models/dino/ops/modules/ms_deform_attn.py:30-126.
+
+Kept identical on purpose (drop-in / checkpoint compatibility): constructor signature, the
+attributes `im2col_step, d_model, n_levels, n_heads, n_points`, the four sub-modules named
+`sampling_offsets, attention_weights, value_proj, output_proj` (state_dict keys), the
+initialisation of `_reset_parameters` (:62-76) and the forward argument order (:78).
+"""
+import math
+import warnings
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from ..functions import MSDeformAttnFunction
+
+
+def _is_power_of_2(n):
+    if not isinstance(n, int) or n < 0:
+        raise ValueError(f"invalid input for _is_power_of_2: {n} (type: {type(n)})")
+    return n != 0 and (n & (n - 1)) == 0
+
+
+class MSDeformAttn(nn.Module):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
+        super().__init__()
+        if d_model % n_heads:
+            raise ValueError(f"d_model must be divisible by n_heads, but got {d_model} and {n_heads}")
+        if not _is_power_of_2(d_model // n_heads):
+            warnings.warn("MSDeformAttn: a power-of-two head dimension (32 in DINO) takes the vectorised "
+                          "CUDA path; other sizes run the generic kernels.")
+        self.im2col_step = 64
+        self.d_model, self.n_levels, self.n_heads, self.n_points = d_model, n_levels, n_heads, n_points
+        taps = n_heads * n_levels * n_points
+        self.sampling_offsets = nn.Linear(d_model, taps * 2)
+        self.attention_weights = nn.Linear(d_model, taps)
+        self.value_proj = nn.Linear(d_model, d_model)
+        self.output_proj = nn.Linear(d_model, d_model)
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        """Offsets start as a per-head compass direction scaled by the point index (1..P); attention
+        logits start at zero (uniform softmax); projections are Xavier-uniform with zero bias."""
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        angle = torch.arange(M, dtype=torch.float32) * (2.0 * math.pi / M)
+        direction = torch.stack([angle.cos(), angle.sin()], -1)
+        direction = direction / direction.abs().max(-1, keepdim=True)[0]          # on the unit square
+        steps = torch.arange(1, P + 1, dtype=torch.float32).view(1, 1, P, 1)
+        bias = direction.view(M, 1, 1, 2).repeat(1, L, P, 1) * steps
+        nn.init.constant_(self.sampling_offsets.weight.data, 0.0)
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(bias.reshape(-1))
+        nn.init.constant_(self.attention_weights.weight.data, 0.0)
+        nn.init.constant_(self.attention_weights.bias.data, 0.0)
+        for proj in (self.value_proj, self.output_proj):
+            nn.init.xavier_uniform_(proj.weight.data)
+            nn.init.constant_(proj.bias.data, 0.0)
+
+    def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
+                input_level_start_index, input_padding_mask=None):
+        """query [N,Lq,C]; reference_points [N,Lq,L,2] (centres) or [N,Lq,L,4] (cx,cy,w,h boxes), in [0,1];
+        input_flatten [N,S,C]; input_spatial_shapes [L,2]=(H,W); input_level_start_index [L];
+        input_padding_mask [N,S] bool, True on padding.  Returns [N,Lq,C]."""
+        N, Lq, _ = query.shape
+        S = input_flatten.shape[1]
+        M, L, P = self.n_heads, self.n_levels, self.n_points
+        assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == S
+
+        value = self.value_proj(input_flatten)
+        if input_padding_mask is not None:
+            value = value.masked_fill(input_padding_mask[..., None], 0.0)
+        value = value.view(N, S, M, self.d_model // M)
+
+        offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
+        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+
+        ref_dim = reference_points.shape[-1]
+        if ref_dim == 2:      # offsets are in pixels of each level: normalise by (W_l, H_l)
+            wh = input_spatial_shapes.flip(-1)
+            locations = reference_points[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]
+        elif ref_dim == 4:    # offsets are fractions of half the reference box, split over P points
+            locations = reference_points[:, :, None, :, None, :2] \
+                + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5
+        else:
+            raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {ref_dim} instead.")
+
+        if value.dtype == torch.float16:   # AMP: the op itself runs in fp32 (reference :114-121)
+            sampled = MSDeformAttnFunction.apply(value.float(), input_spatial_shapes, input_level_start_index,
+                                                 locations.float(), weights.float(), self.im2col_step)
+            return self.output_proj(sampled.to(torch.float16))
+        sampled = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                             locations, weights, self.im2col_step)
+        return self.output_proj(sampled)

@@ -1,0 +1,89 @@
+"""Loader/builder of the C-ABI CUDA library (include/datr_msda.h).
+
+The library is plain CUDA C++ (no torch headers) compiled in-tree for sm_100a:
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared ...
+There is NO fallback: if the library cannot be built or loaded, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import threading
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+SOURCES = [os.path.join(_PKG, "csrc", "msda.cu")]
+INCLUDE_DIR = os.path.join(_ROOT, "include")
+LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_last_error", "datr_abi_version",
+           "datr_launch_count")
+
+_lock = threading.Lock()
+_lib = None
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = SOURCES + [os.path.join(INCLUDE_DIR, f) for f in os.listdir(INCLUDE_DIR)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile libdatr_b200.so in-tree (cross-compiles without a GPU)."""
+    if force or _stale():
+        cmd = ["nvcc", *NVCC_FLAGS, f"-I{INCLUDE_DIR}", "-o", LIB_PATH, *SOURCES]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise NativeLibraryError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
+    return LIB_PATH
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library; builds it first if the sources are newer.  Raises on any failure."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        try:
+            path = build()
+        except FileNotFoundError as e:  # nvcc missing: accept a prebuilt library, else fail loudly
+            if not os.path.exists(LIB_PATH):
+                raise NativeLibraryError(f"libdatr_b200.so is missing and nvcc is unavailable: {e}") from e
+            path = LIB_PATH
+        try:
+            L = ctypes.CDLL(path)
+        except OSError as e:
+            raise NativeLibraryError(f"cannot load {path}: {e}") from e
+        vp, i, i64p = ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p
+        L.datr_msda_forward.restype = i
+        L.datr_msda_forward.argtypes = [vp, i64p, i64p, vp, vp, i, i, i, i, i, i, i, i, vp, vp]
+        L.datr_msda_backward.restype = i
+        L.datr_msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp]
+        L.datr_last_error.restype = ctypes.c_char_p
+        L.datr_last_error.argtypes = []
+        L.datr_abi_version.restype = i
+        L.datr_launch_count.restype = ctypes.c_uint64
+        if L.datr_abi_version() != 1:
+            raise NativeLibraryError("libdatr_b200.so ABI version mismatch; rebuild")
+        _lib = L
+    return _lib
+
+
+def launch_count() -> int:
+    return int(lib().datr_launch_count())

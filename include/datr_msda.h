@@ -1,0 +1,86 @@
+/*
+ * datr_msda.h -- C ABI of the B200 (sm_100a) multi-scale deformable attention
+ * library (libdatr_b200.so).  Plain pointers and sizes only; no torch types.
+ *
+ * Each entry point replaces one function of the reference's native extension
+ * `MultiScaleDeformableAttention` (paths relative to the reference repo):
+ *
+ *   datr_msda_forward   <- ms_deform_attn_forward   models/dino/ops/src/vision.cpp:14,
+ *                          ms_deform_attn.h:21-39 (dispatch),
+ *                          cuda/ms_deform_attn_cuda.cu:20-80 (host),
+ *                          cuda/ms_deform_im2col_cuda.cuh:237-299, :924-954 (kernel + launcher)
+ *   datr_msda_backward  <- ms_deform_attn_backward  vision.cpp:15, ms_deform_attn.h:41-60,
+ *                          ms_deform_attn_cuda.cu:83-153, ms_deform_im2col_cuda.cuh:87-159,
+ *                          :301-920 (6 kernel variants), :957-1327 (launcher)
+ *
+ * Contract (differences from the reference are deliberate and listed):
+ *   - The CALLER owns every buffer (device memory, contiguous, row-major).  The
+ *     library allocates nothing and keeps no global mutable state; calls are
+ *     re-entrant across host threads and streams.
+ *   - All work is enqueued on `stream` (a cudaStream_t passed as void*; NULL =
+ *     legacy default stream) and the call returns without host synchronisation,
+ *     like the reference (cu:65,135 use the current torch stream).
+ *   - forward: every element of `output` is written (no pre-zeroing needed; the
+ *     reference pre-zeroes with at::zeros, cu:54).
+ *   - backward: `grad_value` is zero-filled BY THE LIBRARY on `stream` before the
+ *     scatter; `grad_sampling_loc` and `grad_attn_weight` are fully overwritten
+ *     (the reference allocates the three with zeros, cu:121-123).
+ *   - spatial_shapes / level_start_index are int64 arrays IN DEVICE MEMORY, as in
+ *     the reference (cuh:240-241).
+ *   - Errors are returned as negative codes (the reference only printf()s launch
+ *     errors, cuh:948-952); datr_last_error() gives the message for the calling
+ *     thread.  The im2col_step batch chunking of the reference host code
+ *     (cu:50-75) has no numerical effect and is validated by the Python shim.
+ *   - There is no CPU implementation (the reference's CPU entry points throw,
+ *     cpu/ms_deform_attn_cpu.cpp:26,39).
+ *
+ * Shapes:  value [batch, spatial_size, num_heads, channels]
+ *          spatial_shapes int64 [num_levels, 2] = (H_l, W_l); level_start_index int64 [num_levels]
+ *          sampling_loc [batch, num_query, num_heads, num_levels, num_point, 2] = (x, y) in [0,1]
+ *          attn_weight  [batch, num_query, num_heads, num_levels, num_point]
+ *          output / grad_output [batch, num_query, num_heads * channels]
+ */
+#ifndef DATR_MSDA_H_
+#define DATR_MSDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element type of value / sampling_loc / attn_weight / output (all the same, as cu:64 dispatches) */
+enum { DATR_DTYPE_F32 = 0, DATR_DTYPE_F64 = 1 };
+
+enum {
+  DATR_OK = 0,
+  DATR_ERR_BAD_ARGUMENT = -1, /* null pointer, non-positive dimension, unknown dtype */
+  DATR_ERR_ALIGNMENT = -2,    /* a buffer is not aligned to its element type */
+  DATR_ERR_CUDA = -3          /* memset / kernel launch failed; see datr_last_error() */
+};
+
+int datr_msda_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                      const void* sampling_loc, const void* attn_weight,
+                      int batch, int spatial_size, int num_heads, int channels,
+                      int num_levels, int num_query, int num_point, int dtype,
+                      void* output, void* stream);
+
+int datr_msda_backward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                       const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                       int batch, int spatial_size, int num_heads, int channels,
+                       int num_levels, int num_query, int num_point, int dtype,
+                       void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* stream);
+
+/* Message of the last failing call made by the calling thread ("" if none). */
+const char* datr_last_error(void);
+
+/* ABI version of this header (bumped on any signature change). */
+int datr_abi_version(void);
+
+/* Number of kernel launches issued by this process through the library (for bench accounting). */
+uint64_t datr_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DATR_MSDA_H_ */

@@ -1,0 +1,83 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/*.h declares.
+No compute calls here (no GPU); argument validation paths return before touching CUDA."""
+import ctypes
+import glob
+import os
+import re
+
+import pytest
+import torch
+
+from datr_b200 import native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    names = []
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        src = re.sub(r"/\*.*?\*/", "", open(h).read(), flags=re.S)
+        names += re.findall(r"\b(datr_\w+)\s*\(", src)
+    return sorted(set(names))
+
+
+def test_header_declares_the_reference_entry_points():
+    names = declared_functions()
+    assert "datr_msda_forward" in names and "datr_msda_backward" in names
+
+
+def test_library_builds_loads_and_exports_all_declared_symbols():
+    lib = native.lib()
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/ but not exported"
+    assert set(native.EXPORTS) <= set(declared_functions())
+    assert lib.datr_abi_version() == 1
+
+
+def test_library_is_sm100a_only():
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-lelf", native.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_bad_arguments_return_error_codes_without_touching_the_gpu():
+    lib = native.lib()
+    rc = lib.datr_msda_forward(None, None, None, None, None, 1, 1, 1, 1, 1, 1, 1, 0, None, None)
+    assert rc == -1 and b"null" in lib.datr_last_error()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    rc = lib.datr_msda_forward(p, p, p, p, p, 0, 1, 1, 1, 1, 1, 1, 0, p, None)
+    assert rc == -1 and b"positive" in lib.datr_last_error()
+    rc = lib.datr_msda_forward(p, p, p, p, p, 1, 1, 1, 1, 1, 1, 1, 7, p, None)
+    assert rc == -1 and b"dtype" in lib.datr_last_error()
+    rc = lib.datr_msda_backward(p, p, p, p, p, None, 1, 1, 1, 1, 1, 1, 1, 0, p, p, p, None)
+    assert rc == -1
+    rc = lib.datr_msda_forward(p + 2, p, p, p, p, 1, 1, 1, 1, 1, 1, 1, 0, p, None)
+    assert rc == -2
+
+
+def test_shim_refuses_cpu_tensors_like_the_reference():
+    """ms_deform_attn.h:38,60 -> 'Not implemented on the CPU'; there is no CPU fallback."""
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    from datr_b200.models.dino.ops.functions import MSDeformAttnFunction
+    v = torch.zeros(1, 5, 2, 4)
+    shapes = torch.tensor([[1, 5]])
+    start = torch.tensor([0])
+    loc = torch.zeros(1, 3, 2, 1, 2, 2)
+    attn = torch.zeros(1, 3, 2, 1, 2)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        MSDA.ms_deform_attn_forward(v, shapes, start, loc, attn, 64)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        MSDA.ms_deform_attn_backward(v, shapes, start, loc, attn, torch.zeros(1, 3, 8), 64)
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        MSDeformAttnFunction.apply(v, shapes, start, loc, attn, 64)
+
+
+def test_dropin_module_name():
+    import sys
+    from datr_b200 import MultiScaleDeformableAttention as shim
+    shim.install()
+    import MultiScaleDeformableAttention as MSDA
+    assert MSDA.ms_deform_attn_forward is shim.ms_deform_attn_forward
+    assert MSDA.ms_deform_attn_backward is shim.ms_deform_attn_backward
+    del sys.modules["MultiScaleDeformableAttention"]

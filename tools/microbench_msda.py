@@ -1,0 +1,56 @@
+"""Micro-benchmark of the MSDeformAttn kernels at the BASELINE.json shapes (GPU box only).
+Times ours and, when oracle/_ref is built, the reference's own CUDA kernels, with an L2 flush
+between iterations.  Prints one line per (shape, direction)."""
+import os, sys, json
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+import msda_cases as mc
+from datr_b200 import MultiScaleDeformableAttention as MSDA
+from oracle import build_ref
+
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def algo_bytes(N, S, M, D, L, Lq, P, es=4):
+    fwd = es * (N * S * M * D + 3 * N * Lq * M * L * P + N * Lq * M * D)
+    return fwd, fwd + es * (N * S * M * D + 3 * N * Lq * M * L * P)
+
+
+def timeit(fn, iters=20, flush=None):
+    for _ in range(3):
+        fn()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    ref = build_ref.load()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    cases = [("cfg2_enc", 2, mc.CFG2_LEVELS, -1, "encoder"), ("cfg2_enc_uniform", 2, mc.CFG2_LEVELS, -1, "uniform"),
+             ("cfg2_dec1100", 2, mc.CFG2_LEVELS, 1100, "uniform"), ("cfg1_enc", 1, mc.CFG1_LEVELS, -1, "encoder"),
+             ("cfg4_enc", 1, mc.CFG4_LEVELS, -1, "encoder")]
+    for name, N, levels, Lq, mode in cases:
+        inp = mc.make_inputs(N, 8, 32, Lq, 4, levels, mode, 1, np.float32)
+        d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+        args = (d["value"], d["shapes"], d["level_start"], d["loc"], d["attn"])
+        S = d["value"].shape[1]; LQ = d["loc"].shape[1]
+        fb, bb = algo_bytes(N, S, 8, 32, len(levels), LQ, 4)
+        for impl, mod in (("ours", MSDA), ("ref", ref)):
+            if mod is None:
+                continue
+            for flushed, fl in (("cold", flush), ("warm", None)):
+                tf, tfm = timeit(lambda: mod.ms_deform_attn_forward(*args, 64), flush=fl)
+                tb, tbm = timeit(lambda: mod.ms_deform_attn_backward(*args, d["grad_out"], 64), flush=fl)
+                print(f"{name:18s} {impl:5s} {flushed} fwd {tf*1e3:8.1f} us ({fb/tf/1e6:7.1f} GB/s, {fb/tf/1e6/PEAK:5.3f}) "
+                      f"bwd {tb*1e3:8.1f} us ({bb/tb/1e6:7.1f} GB/s, {bb/tb/1e6/PEAK:5.3f})", flush=True)
+
+
+if __name__ == "__main__":
+    main()
