@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the DATR/DINO data-parallel hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload msda|dino]
+
+Metric (BASELINE.json): images/sec at 1333x800, batch_size 2 per GPU (a DA training step consumes
+2 source + 2 target images per GPU), plus the MSDeformAttn HBM roofline.  One JSON
+line on stdout (rank 0).  Workloads:
+
+  msda  the MultiScaleDeformableAttention calls of one DINO-4scale DA training step at
+        BASELINE.json configs[1] shapes: two transformer passes, each 6 encoder calls
+        (N=2, Lq=S=22223) and 6 decoder calls (Lq=1100 with denoising queries in the source
+        pass, 900 in the target pass), forward AND backward: 24 + 24 launches.
+  dino  the full DINO-4scale ResNet-50 forward+backward step (datr_b200.models), same shapes.
+
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
+Every call of a step reads its own buffers (the step cycles > 3 GB, far larger than the 126 MB L2).
+The oracle (oracle/) is used here only as `cpu_baseline` / `--impl reference`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CFG2_LEVELS = [(100, 167), (50, 84), (25, 42), (13, 21)]   # 1333x800 through ResNet-50 C3..C5 + extra
+M_HEADS, D_HEAD, N_POINTS = 8, 32, 4
+IMAGES_PER_STEP_PER_GPU = 4        # batch_size 2 -> 2 source + 2 target images (util/misc.py:291-300)
+MSDA_WORKLOAD = ("MSDeformAttn calls of one DINO-4scale DA training step, 1333x800, batch_size 2/GPU: "
+                 "12 encoder (N=2,Lq=S=22223) + 6 decoder Lq=1100 + 6 decoder Lq=900, forward+backward, fp32")
+FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            for k in ("hbm_gbs", "hbm_gb_s", "hbm"):
+                if k in d:
+                    return float(d[k]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def msda_algo_bytes(N, S, M, D, L, Lq, P, es=4):
+    """compulsory bytes of one call (gather re-reads, zero-fill and atomic RMW not credited)."""
+    fwd = es * (N * S * M * D + 3 * N * Lq * M * L * P + N * Lq * M * D)
+    bwd = fwd + es * (N * S * M * D + 3 * N * Lq * M * L * P)
+    return fwd, bwd
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100", "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# workload: the MSDeformAttn calls of one DA training step
+# ----------------------------------------------------------------------------------------------
+def step_plan():
+    """(kind, Lq) for every MSDeformAttn module invocation of one DA training step, forward order.
+    Source pass: encoder x6 then decoder x6 with 900+200 denoising queries; target pass: 900."""
+    S = sum(h * w for h, w in CFG2_LEVELS)
+    plan = []
+    for dec_q in (1100, 900):
+        plan += [("enc", S)] * 6 + [("dec", dec_q)] * 6
+    return S, plan
+
+
+def synth_call(N, S, Lq, kind, seed, device, pinned=False):
+    """Synthetic inputs of one call: value ~ N(0,1); encoder calls sample around each
+    token's own reference point (offsets ~ N(0, (2 px)^2)); decoder calls around random box centres;
+    attention = softmax(N(0,1)) over L*P."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    L = len(CFG2_LEVELS)
+    value = torch.randn((N, S, M_HEADS, D_HEAD), generator=g)
+    wh = torch.tensor([[w, h] for h, w in CFG2_LEVELS], dtype=torch.float32)
+    if kind == "enc":
+        refs = []
+        for h, w in CFG2_LEVELS:
+            ys, xs = torch.meshgrid((torch.arange(h) + 0.5) / h, (torch.arange(w) + 0.5) / w, indexing="ij")
+            refs.append(torch.stack([xs.reshape(-1), ys.reshape(-1)], -1))
+        ref = torch.cat(refs)[None, :, None, None, None, :]
+        loc = ref + torch.randn((N, Lq, M_HEADS, L, N_POINTS, 2), generator=g) * 2.0 / wh[None, None, None, :, None, :]
+    else:
+        ctr = torch.rand((N, Lq, 1, 1, 1, 2), generator=g)
+        box = torch.rand((N, Lq, 1, 1, 1, 2), generator=g) * 0.3 + 0.02
+        loc = ctr + torch.randn((N, Lq, M_HEADS, L, N_POINTS, 2), generator=g) * 0.25 * box
+    attn = torch.softmax(torch.randn((N, Lq, M_HEADS, L * N_POINTS), generator=g), -1).view(N, Lq, M_HEADS, L, N_POINTS)
+    gout = torch.randn((N, Lq, M_HEADS * D_HEAD), generator=g)
+    t = dict(value=value, loc=loc.contiguous(), attn=attn.contiguous(), grad_out=gout)
+    if pinned:
+        return {k: v.pin_memory() for k, v in t.items()}
+    return {k: v.to(device) for k, v in t.items()}
+
+
+class MsdaStep:
+    name = "msda"
+
+    def __init__(self, device, rank):
+        from datr_b200 import MultiScaleDeformableAttention as MSDA
+        from datr_b200 import native
+        self.MSDA, self.native, self.device = MSDA, native, device
+        self.S, self.plan = step_plan()
+        self.N = 2
+        L = len(CFG2_LEVELS)
+        self.shapes = torch.tensor(CFG2_LEVELS, dtype=torch.int64, device=device)
+        hw = self.shapes[:, 0] * self.shapes[:, 1]
+        self.lstart = torch.cat([hw.new_zeros(1), hw.cumsum(0)[:-1]])
+        # one private buffer set per call of the step => nothing is L2-resident from a previous call
+        self.calls = [synth_call(self.N, self.S, Lq, kind, 1000 * rank + i, device) for i, (kind, Lq) in enumerate(self.plan)]
+        self.bytes = [msda_algo_bytes(self.N, self.S, M_HEADS, D_HEAD, L, Lq, N_POINTS) for _, Lq in self.plan]
+        # host copies for the end-to-end leg: one encoder set and one set per decoder length
+        self.host = {}
+        for i, (kind, Lq) in enumerate(self.plan):
+            if (kind, Lq) not in self.host:
+                self.host[(kind, Lq)] = synth_call(self.N, self.S, Lq, kind, 77 + i, device, pinned=True)
+        self.host_out = {k: dict(out=torch.empty_like(v["grad_out"]).pin_memory(), gv=torch.empty_like(v["value"]).pin_memory(),
+                                 gl=torch.empty_like(v["loc"]).pin_memory(), ga=torch.empty_like(v["attn"]).pin_memory())
+                         for k, v in self.host.items()}
+        self.launches_per_step = 2 * len(self.plan)
+        self.workload = MSDA_WORKLOAD
+
+    def step(self):
+        F, B = self.MSDA.ms_deform_attn_forward, self.MSDA.ms_deform_attn_backward
+        for c in self.calls:
+            F(c["value"], self.shapes, self.lstart, c["loc"], c["attn"], 64)
+        for c in reversed(self.calls):
+            B(c["value"], self.shapes, self.lstart, c["loc"], c["attn"], c["grad_out"], 64)
+
+    def e2e_step(self):
+        """Same calls through the public op with HOST buffers: H2D of the inputs and D2H of the results
+        of every call are inside the timed region."""
+        F, B = self.MSDA.ms_deform_attn_forward, self.MSDA.ms_deform_attn_backward
+        h2d = d2h = 0
+        for kind, Lq in self.plan:
+            h, o = self.host[(kind, Lq)], self.host_out[(kind, Lq)]
+            v, l, a = (h[k].to(self.device, non_blocking=True) for k in ("value", "loc", "attn"))
+            out = F(v, self.shapes, self.lstart, l, a, 64)
+            o["out"].copy_(out, non_blocking=True)
+            h2d += sum(h[k].numel() * 4 for k in ("value", "loc", "attn")); d2h += out.numel() * 4
+        for kind, Lq in reversed(self.plan):
+            h, o = self.host[(kind, Lq)], self.host_out[(kind, Lq)]
+            v, l, a, g = (h[k].to(self.device, non_blocking=True) for k in ("value", "loc", "attn", "grad_out"))
+            gv, gl, ga = B(v, self.shapes, self.lstart, l, a, g, 64)
+            o["gv"].copy_(gv, non_blocking=True); o["gl"].copy_(gl, non_blocking=True); o["ga"].copy_(ga, non_blocking=True)
+            h2d += sum(h[k].numel() * 4 for k in ("value", "loc", "attn", "grad_out"))
+            d2h += (gv.numel() + gl.numel() + ga.numel()) * 4
+        return h2d, d2h
+
+    def roofline(self, timers, peak, peak_src):
+        """Dominant kernel = the one with the largest share of the timed region; achieved = algorithmic
+        bytes of its launches / their event-timed duration."""
+        groups = {}
+        for kind, key, e0, e1 in timers:
+            N, S, M, D, L, Lq, P, es = key
+            name = f"msda_{kind}_f32_d32<{P}> " + ("encoder" if Lq == S else "decoder")
+            fb, bb = msda_algo_bytes(N, S, M, D, L, Lq, P, es)
+            g = groups.setdefault(name, [0.0, 0, 0])
+            g[0] += e0.elapsed_time(e1) * 1e-3; g[1] += fb if kind == "fwd" else bb; g[2] += 1
+        total = sum(g[0] for g in groups.values())
+        top = max(groups, key=lambda k: groups[k][0])
+        t, b, n = groups[top]
+        per_kernel = {k: {"launches": v[2], "avg_us": v[0] / v[2] * 1e6, "gbs": v[1] / v[0] / 1e9,
+                          "frac": v[1] / v[0] / 1e9 / peak, "share": v[0] / total} for k, v in groups.items()}
+        return {"bound": "hbm", "kernel": top, "achieved": b / t / 1e9, "peak": peak, "peak_source": peak_src,
+                "unit": "GB/s", "frac": b / t / 1e9 / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": b / n, "avg_launch_us": t / n * 1e6, "share_of_step": t / total,
+                "per_kernel": per_kernel}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the reference's CPU MSDeformAttn path (grid_sample formulation), port in oracle/msda.py
+# ----------------------------------------------------------------------------------------------
+def cpu_port_images_per_s(threads, repeats=1):
+    """Times one encoder, one Lq=1100 and one Lq=900 decoder call (forward + autograd backward) of the
+    step on the host and extrapolates to the 12/6/6 calls of the step."""
+    from oracle import msda as om
+    torch.set_num_threads(threads)
+    S, plan = step_plan()
+    shapes = np.array(CFG2_LEVELS, dtype=np.int64)
+    t_call = {}
+    for kind, Lq in (("enc", S), ("dec", 1100), ("dec", 900)):
+        c = synth_call(2, S, Lq, kind, 5, "cpu")
+        best = None
+        for _ in range(repeats + 1):          # first pass = warm-up
+            v, l, a = (c[k].clone().requires_grad_(True) for k in ("value", "loc", "attn"))
+            t0 = time.perf_counter()
+            out = om.core_torch(v, shapes, l, a)
+            out.backward(c["grad_out"].view_as(out))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        t_call[(kind, Lq)] = best
+    step_s = sum(t_call[k] for k in plan)
+    return IMAGES_PER_STEP_PER_GPU / step_s, step_s, t_call
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("DATR_BENCH_WORKLOAD", "auto"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    threads = os.cpu_count() or 1
+
+    if args.workload == "auto":
+        try:
+            import datr_b200.bench_dino  # noqa: F401
+            args.workload = "dino"
+        except ImportError:
+            args.workload = "msda"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        if args.workload == "dino":
+            from datr_b200 import bench_dino
+            print(json.dumps(bench_dino.reference_arm(args, threads)), flush=True)
+            return
+        vals = []
+        for _ in range(max(1, min(args.steps, 3))):
+            ips, step_s, t_call = cpu_port_images_per_s(threads, repeats=1)
+            vals.append((ips, step_s))
+        ips, step_s = max(vals)
+        sample = ("1 encoder + 1 decoder(1100) + 1 decoder(900) call, forward + autograd backward, of the "
+                  "reference's grid_sample CPU path (func.py:41-61, port in oracle/msda.py), extrapolated x12/x6/x6")
+        print(json.dumps({
+            "impl": "reference", "metric": "images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": MSDA_WORKLOAD, "l2": "n/a (CPU)"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }), flush=True)
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    if args.workload == "dino":
+        from datr_b200 import bench_dino
+        wl = bench_dino.DinoStep(device, rank, world)
+    else:
+        wl = MsdaStep(device, rank)
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    from datr_b200 import native
+    peak, peak_src = hbm_peak()
+
+    for _ in range(args.warmup):
+        wl.step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    MSDA._timers = []
+    n0 = native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        wl.step()
+    e1.record()
+    barrier()
+    launches = native.launch_count() - n0
+    timers, MSDA._timers = MSDA._timers, None
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end leg: host buffers in, host results out, through the public op / model API
+    for _ in range(2):
+        wl.e2e_step()
+    barrier()
+    k2 = max(2, min(args.steps, 5))
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(k2):
+        h2d, d2h = wl.e2e_step()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    images = IMAGES_PER_STEP_PER_GPU * world
+    value = images * args.steps / (ms * 1e-3)
+    e2e = images * k2 / (ms_e2e * 1e-3)
+    roof = wl.roofline(timers, peak, peak_src)
+    line = {
+        "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl.workload, "images_per_step_per_gpu": IMAGES_PER_STEP_PER_GPU,
+                   "l2": "every call of a step reads its own buffers; the step cycles >3 GB (L2 is 126 MB)",
+                   "parallelism": f"dp{world}"},
+        "roofline": roof,
+        "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": k2, "ms_per_step": ms_e2e / k2},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        ips, step_s, t_call = cpu_port_images_per_s(threads, repeats=1)
+        line["cpu_baseline"] = {
+            "value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": "1 encoder + 1 decoder(1100) + 1 decoder(900) call fwd+bwd of the grid_sample CPU path "
+                      "(oracle/msda.py core_torch), extrapolated x12/x6/x6 to the step; %.2f s per step" % step_s}
+    extra = getattr(wl, "extra", None)
+    if extra:
+        line.update(extra() if callable(extra) else extra)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
