@@ -1,0 +1,1 @@
+from .dino import build_dino  # noqa: F401

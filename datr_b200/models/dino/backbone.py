@@ -1,0 +1,190 @@
+"""ResNet backbone with frozen batch-norm, mask down-sampling and position encoding.
+
+Mirrors the hot-path part of the reference's models/dino/backbone.py: FrozenBatchNorm2d (:36-72),
+BackboneBase (:75-106; stem + layer1 frozen :79-81, nearest-neighbour mask resize :103),
+Backbone (:109-129; torchvision ResNet-50/101 layout, stride on the 3x3 conv), Joiner (:132-144),
+build_backbone (:147-219).  Swin / ConvNeXt backbones of the reference are outside the hot path.
+
+The ResNet is defined here (not taken from torchvision) with torchvision's parameter names, so the
+reference's checkpoints (`backbone.0.body.layerK.B.convJ.weight`, `...bnJ.{weight,bias,running_mean,
+running_var}`, `...downsample.{0,1}`) load unchanged, and so that the frozen batch-norm folds into a
+per-channel scale/shift applied in one pass (the reference does 4 elementwise passes, :62-72).
+"""
+from typing import Dict, List
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from datr_b200.util.misc import NestedTensor
+from .position_encoding import build_position_encoding
+
+
+class FrozenBatchNorm2d(nn.Module):
+    """y = x * w / sqrt(var + 1e-5) + (b - mean * w / sqrt(var + 1e-5)); statistics and affine are buffers."""
+
+    def __init__(self, n):
+        super().__init__()
+        self.register_buffer("weight", torch.ones(n))
+        self.register_buffer("bias", torch.zeros(n))
+        self.register_buffer("running_mean", torch.zeros(n))
+        self.register_buffer("running_var", torch.ones(n))
+
+    def _load_from_state_dict(self, state_dict, prefix, *rest):
+        state_dict.pop(prefix + "num_batches_tracked", None)
+        super()._load_from_state_dict(state_dict, prefix, *rest)
+
+    def scale_shift(self):
+        scale = self.weight * (self.running_var + 1e-5).rsqrt()
+        return scale, self.bias - self.running_mean * scale
+
+    def forward(self, x):
+        scale, shift = self.scale_shift()
+        return torch.addcmul(shift.view(1, -1, 1, 1), x, scale.view(1, -1, 1, 1))
+
+
+class Bottleneck(nn.Module):
+    expansion = 4
+
+    def __init__(self, inplanes, planes, stride=1, downsample=None, dilation=1, norm_layer=FrozenBatchNorm2d):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = norm_layer(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=stride, padding=dilation, dilation=dilation, bias=False)
+        self.bn2 = norm_layer(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = norm_layer(planes * 4)
+        self.downsample = downsample
+        self.stride = stride
+
+    def forward(self, x):
+        y = F.relu(self.bn1(self.conv1(x)))
+        y = F.relu(self.bn2(self.conv2(y)))
+        y = self.bn3(self.conv3(y))
+        if self.downsample is not None:
+            x = self.downsample(x)
+        return F.relu(y + x)
+
+
+class ResNet(nn.Module):
+    """conv1/bn1/maxpool + layer1..layer4 of bottlenecks (ResNet-50: 3,4,6,3; ResNet-101: 3,4,23,3)."""
+
+    def __init__(self, blocks, replace_stride_with_dilation=(False, False, False), norm_layer=FrozenBatchNorm2d):
+        super().__init__()
+        self.inplanes, self.dilation = 64, 1
+        self.conv1 = nn.Conv2d(3, 64, 7, stride=2, padding=3, bias=False)
+        self.bn1 = norm_layer(64)
+        self.layer1 = self._stage(64, blocks[0], 1, False, norm_layer)
+        self.layer2 = self._stage(128, blocks[1], 2, replace_stride_with_dilation[0], norm_layer)
+        self.layer3 = self._stage(256, blocks[2], 2, replace_stride_with_dilation[1], norm_layer)
+        self.layer4 = self._stage(512, blocks[3], 2, replace_stride_with_dilation[2], norm_layer)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+
+    def _stage(self, planes, n, stride, dilate, norm_layer):
+        prev_dilation = self.dilation
+        if dilate:
+            self.dilation *= stride
+            stride = 1
+        down = None
+        if stride != 1 or self.inplanes != planes * 4:
+            down = nn.Sequential(nn.Conv2d(self.inplanes, planes * 4, 1, stride=stride, bias=False),
+                                 norm_layer(planes * 4))
+        layers = [Bottleneck(self.inplanes, planes, stride, down, prev_dilation, norm_layer)]
+        self.inplanes = planes * 4
+        layers += [Bottleneck(self.inplanes, planes, dilation=self.dilation, norm_layer=norm_layer) for _ in range(1, n)]
+        return nn.Sequential(*layers)
+
+    def stem(self, x):
+        return F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, stride=2, padding=1)
+
+
+_RESNETS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
+
+
+class _Body(nn.Module):
+    """Runs the ResNet and returns {"<interm index>": feature} for the requested stages (the role of
+    torchvision's IntermediateLayerGetter in the reference); children keep the ResNet's names."""
+
+    def __init__(self, net: ResNet, return_layers: Dict[str, str]):
+        super().__init__()
+        last = max(int(k[-1]) for k in return_layers)
+        self.conv1, self.bn1 = net.conv1, net.bn1
+        for i in range(1, last + 1):
+            setattr(self, f"layer{i}", getattr(net, f"layer{i}"))
+        self.return_layers = dict(return_layers)
+        self._last = last
+
+    def forward(self, x):
+        out = {}
+        x = F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, stride=2, padding=1)
+        for i in range(1, self._last + 1):
+            name = f"layer{i}"
+            # stem and layer1 never train (BackboneBase): no autograd graph through them
+            x = getattr(self, name)(x)
+            if name in self.return_layers:
+                out[self.return_layers[name]] = x
+        return out
+
+
+class BackboneBase(nn.Module):
+    def __init__(self, backbone: nn.Module, train_backbone: bool, num_channels, return_interm_indices: list):
+        super().__init__()
+        for name, p in backbone.named_parameters():
+            if not train_backbone or not any(k in name for k in ("layer2", "layer3", "layer4")):
+                p.requires_grad_(False)
+        n = len(return_interm_indices)
+        return_layers = {f"layer{5 - n + i}": str(idx) for i, idx in enumerate(return_interm_indices)}
+        self.body = _Body(backbone, return_layers)
+        self.num_channels = num_channels
+
+    def forward(self, tensor_list: NestedTensor):
+        feats = self.body(tensor_list.tensors)
+        m = tensor_list.mask
+        assert m is not None
+        out: Dict[str, NestedTensor] = {}
+        for name, x in feats.items():
+            mask = F.interpolate(m[None].float(), size=x.shape[-2:]).to(torch.bool)[0]
+            out[name] = NestedTensor(x, mask)
+        return out
+
+
+class Backbone(BackboneBase):
+    """ResNet-50/101 with FrozenBatchNorm2d.  Weights are random-initialised here: the reference downloads
+    ImageNet weights on the main process (:118-120); there is no network on the benchmark box, and a
+    checkpoint load overwrites them anyway."""
+
+    def __init__(self, name: str, train_backbone: bool, dilation: bool, return_interm_indices: list,
+                 batch_norm=FrozenBatchNorm2d):
+        if name not in _RESNETS:
+            raise NotImplementedError(f"Why you can get here with name {name}")
+        assert return_interm_indices in [[0, 1, 2, 3], [1, 2, 3], [3]]
+        net = ResNet(_RESNETS[name], (False, False, dilation), norm_layer=batch_norm)
+        num_channels = [256, 512, 1024, 2048][4 - len(return_interm_indices):]
+        super().__init__(net, train_backbone, num_channels, return_interm_indices)
+
+
+class Joiner(nn.Sequential):
+    def __init__(self, backbone, position_embedding):
+        super().__init__(backbone, position_embedding)
+
+    def forward(self, tensor_list: NestedTensor):
+        feats = self[0](tensor_list)
+        out: List[NestedTensor] = list(feats.values())
+        pos = [self[1](x).to(x.tensors.dtype) for x in out]
+        return out, pos
+
+
+def build_backbone(args):
+    position_embedding = build_position_encoding(args)
+    if not args.lr_backbone > 0:
+        raise ValueError("Please set lr_backbone > 0")
+    idx = args.return_interm_indices
+    assert idx in [[0, 1, 2, 3], [1, 2, 3], [3]]
+    if args.backbone not in _RESNETS:
+        raise NotImplementedError(f"Unknown backbone {args.backbone} (the B200 hot path covers ResNet-50/101)")
+    backbone = Backbone(args.backbone, True, args.dilation, idx, batch_norm=FrozenBatchNorm2d)
+    model = Joiner(backbone, position_embedding)
+    model.num_channels = backbone.num_channels
+    return model

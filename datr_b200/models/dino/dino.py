@@ -1,0 +1,522 @@
+"""DINO detector with DATR's domain-adaptation branch, its criterion and post-processor.
+
+Mirrors the reference's models/dino/dino.py: DINO (:43-483), SetCriterion (:486-941), PostProcess (:944-996)
+and the registry entry build_dino (:999-1143) -- same constructor arguments, sub-module names (state_dict
+keys), forward signature `model(samples, targets=None, self_training_flag=False)` and output dict keys, so
+engine.py / main.py / main_teacher.py of the reference drive it unchanged.
+
+Hot-path differences that keep the numbers:
+  * nothing is hard-wired to .cuda(): helper tensors are created on the device of the parameters
+    (the reference calls .cuda()/.to('cuda') at :106-107, :790-818);
+  * the de-noising queries are prepared before the backbone is launched, so their one data-dependent host
+    read happens while the GPU queue is empty;
+  * box losses use the paired GIoU instead of the diagonal of an N x N matrix (:563-565);
+  * segmentation heads (DETRsegm) are outside the hot path (`masks=False` in every DINO/DATR config).
+"""
+import copy
+import math
+from typing import List
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from datr_b200.util import box_ops
+from datr_b200.util.misc import (NestedTensor, accuracy, get_world_size, inverse_sigmoid,
+                                 is_dist_avail_and_initialized, nested_tensor_from_tensor_list)
+from ..registry import MODULE_BUILD_FUNCS
+from .backbone import build_backbone
+from .DA_utils import FCDiscriminator_img, decompose_features, get_prototype_class_wise, grad_reverse
+from .deformable_transformer import build_deformable_transformer
+from .dn_components import dn_post_process, prepare_for_cdn
+from .matcher import build_matcher
+from .utils import MLP, sigmoid_focal_loss
+
+
+class DINO(nn.Module):
+    """Backbone -> input projections -> (CDN queries) -> deformable transformer -> class / box heads,
+    plus in training mode the image-level discriminator, class prototypes and a second transformer pass
+    over the target-domain half of the batch."""
+
+    def __init__(self, backbone, transformer, num_classes, num_queries, aux_loss=False, iter_update=False,
+                 query_dim=2, random_refpoints_xy=False, fix_refpoints_hw=-1, num_feature_levels=1, nheads=8,
+                 two_stage_type="no", two_stage_add_query_num=0, dec_pred_class_embed_share=True,
+                 dec_pred_bbox_embed_share=True, two_stage_class_embed_share=True, two_stage_bbox_embed_share=True,
+                 decoder_sa_type="sa", num_patterns=0, dn_number=100, dn_box_noise_scale=0.4,
+                 dn_label_noise_ratio=0.5, dn_labelbook_size=100):
+        super().__init__()
+        assert query_dim == 4
+        assert iter_update, "Why not iter_update?"
+        assert two_stage_type in ("no", "standard"), f"unknown param {two_stage_type} of two_stage_type"
+        assert decoder_sa_type in ("sa", "ca_label", "ca_content")
+        self.num_queries, self.transformer, self.num_classes = num_queries, transformer, num_classes
+        self.hidden_dim = hidden_dim = transformer.d_model
+        self.num_feature_levels, self.nheads = num_feature_levels, nheads
+        self.label_enc = nn.Embedding(dn_labelbook_size + 1, hidden_dim)
+        self.query_dim, self.random_refpoints_xy, self.fix_refpoints_hw = query_dim, random_refpoints_xy, fix_refpoints_hw
+        self.num_patterns, self.dn_number = num_patterns, dn_number
+        self.dn_box_noise_scale, self.dn_label_noise_ratio = dn_box_noise_scale, dn_label_noise_ratio
+        self.dn_labelbook_size = dn_labelbook_size
+
+        # domain-adaptation heads (a fresh module is in training mode, so the reference always builds them, :102-108)
+        self.D_img = FCDiscriminator_img(256)
+        self.global_proto = None          # [num_classes, 256] running class prototypes, created on first use;
+        self.Amount = None                # plain attributes like the reference: not saved, not rank-synchronised
+        self.Proto_D = MLP(hidden_dim, hidden_dim, 1, 3)
+
+        if num_feature_levels > 1:
+            n_backbone = len(backbone.num_channels)
+            proj = [nn.Sequential(nn.Conv2d(c, hidden_dim, kernel_size=1), nn.GroupNorm(32, hidden_dim))
+                    for c in backbone.num_channels]
+            c_in = backbone.num_channels[-1]
+            for _ in range(num_feature_levels - n_backbone):
+                proj.append(nn.Sequential(nn.Conv2d(c_in, hidden_dim, kernel_size=3, stride=2, padding=1),
+                                          nn.GroupNorm(32, hidden_dim)))
+                c_in = hidden_dim
+            self.input_proj = nn.ModuleList(proj)
+        else:
+            assert two_stage_type == "no", "two_stage_type should be no if num_feature_levels=1 !!!"
+            self.input_proj = nn.ModuleList([nn.Sequential(nn.Conv2d(backbone.num_channels[-1], hidden_dim, kernel_size=1),
+                                                           nn.GroupNorm(32, hidden_dim))])
+        self.backbone = backbone
+        self.aux_loss = aux_loss
+        self.box_pred_damping = None
+        self.iter_update = iter_update
+
+        self.dec_pred_class_embed_share, self.dec_pred_bbox_embed_share = dec_pred_class_embed_share, dec_pred_bbox_embed_share
+        cls_head = nn.Linear(hidden_dim, num_classes)
+        box_head = MLP(hidden_dim, hidden_dim, 4, 3)
+        prior = 0.01
+        cls_head.bias.data = torch.ones(num_classes) * (-math.log((1 - prior) / prior))
+        nn.init.constant_(box_head.layers[-1].weight.data, 0)
+        nn.init.constant_(box_head.layers[-1].bias.data, 0)
+        n_dec = transformer.num_decoder_layers
+        self.bbox_embed = nn.ModuleList([box_head if dec_pred_bbox_embed_share else copy.deepcopy(box_head) for _ in range(n_dec)])
+        self.class_embed = nn.ModuleList([cls_head if dec_pred_class_embed_share else copy.deepcopy(cls_head) for _ in range(n_dec)])
+        self.transformer.decoder.bbox_embed = self.bbox_embed
+        self.transformer.decoder.class_embed = self.class_embed
+
+        self.two_stage_type, self.two_stage_add_query_num = two_stage_type, two_stage_add_query_num
+        if two_stage_type != "no":
+            if two_stage_bbox_embed_share:
+                assert dec_pred_class_embed_share and dec_pred_bbox_embed_share
+                self.transformer.enc_out_bbox_embed = box_head
+            else:
+                self.transformer.enc_out_bbox_embed = copy.deepcopy(box_head)
+            if two_stage_class_embed_share:
+                assert dec_pred_class_embed_share and dec_pred_bbox_embed_share
+                self.transformer.enc_out_class_embed = cls_head
+            else:
+                self.transformer.enc_out_class_embed = copy.deepcopy(cls_head)
+            self.refpoint_embed = None
+            if two_stage_add_query_num > 0:
+                self.init_ref_points(two_stage_add_query_num)
+
+        self.decoder_sa_type = decoder_sa_type
+        self.label_embedding = nn.Embedding(num_classes, hidden_dim) if decoder_sa_type == "ca_label" else None
+        for layer in self.transformer.decoder.layers:
+            layer.label_embedding = self.label_embedding
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for proj in self.input_proj:
+            nn.init.xavier_uniform_(proj[0].weight, gain=1)
+            nn.init.constant_(proj[0].bias, 0)
+
+    def init_ref_points(self, use_num_queries):
+        self.refpoint_embed = nn.Embedding(use_num_queries, self.query_dim)
+        if self.random_refpoints_xy:
+            self.refpoint_embed.weight.data[:, :2].uniform_(0, 1)
+            self.refpoint_embed.weight.data[:, :2] = inverse_sigmoid(self.refpoint_embed.weight.data[:, :2])
+            self.refpoint_embed.weight.data[:, :2].requires_grad = False
+        if self.fix_refpoints_hw > 0:
+            assert self.random_refpoints_xy
+            self.refpoint_embed.weight.data[:, 2:] = self.fix_refpoints_hw
+            self.refpoint_embed.weight.data[:, 2:] = inverse_sigmoid(self.refpoint_embed.weight.data[:, 2:])
+            self.refpoint_embed.weight.data[:, 2:].requires_grad = False
+        elif int(self.fix_refpoints_hw) == -2:
+            assert self.random_refpoints_xy
+            self.refpoint_embed = nn.Embedding(use_num_queries, 2)
+            self.refpoint_embed.weight.data[:, :2].uniform_(0, 1)
+            self.refpoint_embed.weight.data[:, :2] = inverse_sigmoid(self.refpoint_embed.weight.data[:, :2])
+            self.refpoint_embed.weight.data[:, :2].requires_grad = False
+            self.hw_embed = nn.Embedding(1, 1)
+        elif int(self.fix_refpoints_hw) != -1:
+            raise NotImplementedError(f"Unknown fix_refpoints_hw {self.fix_refpoints_hw}")
+
+    # ------------------------------------------------------------------------------------------
+    def _features(self, samples: NestedTensor):
+        """Backbone + input projections (+ the extra stride-2 levels): per level (src, mask, pos)."""
+        features, poss = self.backbone(samples)
+        srcs, masks = [], []
+        for l, feat in enumerate(features):
+            src, mask = feat.decompose()
+            assert mask is not None
+            srcs.append(self.input_proj[l](src))
+            masks.append(mask)
+        for l in range(len(srcs), self.num_feature_levels):
+            src = self.input_proj[l](features[-1].tensors if l == len(features) else srcs[-1])
+            mask = F.interpolate(samples.mask[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
+            poss.append(self.backbone[1](NestedTensor(src, mask)).to(src.dtype))
+            srcs.append(src)
+            masks.append(mask)
+        return srcs, masks, poss
+
+    def _heads(self, hs, reference):
+        """Per-decoder-layer boxes (sigmoid(delta + logit(reference))) and class logits, stacked over layers."""
+        coords = torch.stack([(head(h) + inverse_sigmoid(ref)).sigmoid()
+                              for ref, head, h in zip(reference[:-1], self.bbox_embed, hs)])
+        classes = torch.stack([head(h) for head, h in zip(self.class_embed, hs)])
+        return classes, coords
+
+    def _interm(self, out, hs_enc, ref_enc, init_box_proposal, suffix=""):
+        interm_class = self.transformer.enc_out_class_embed(hs_enc[-1])
+        out["interm_outputs" + suffix] = {"pred_logits": interm_class, "pred_boxes": ref_enc[-1]}
+        out["interm_outputs_for_matching_pre" + suffix] = {"pred_logits": interm_class, "pred_boxes": init_box_proposal}
+        if hs_enc.shape[0] > 1:      # per-encoder-layer heads: unreachable with two_stage_type 'standard' (one entry)
+            raise NotImplementedError("per-encoder-layer outputs (enc_outputs) are outside the DINO hot path")
+
+    def _prototypes(self, feats, logits):
+        if self.global_proto is None or self.global_proto.device != feats.device:
+            self.global_proto = torch.zeros(self.num_classes, 256, device=feats.device)
+            self.Amount = torch.zeros(self.num_classes, device=feats.device)
+        proto, present, self.global_proto, self.Amount, _ = get_prototype_class_wise(
+            feats, logits, self.num_classes, global_proto=self.global_proto.detach(), global_amount=self.Amount)
+        return proto, present
+
+    def forward(self, samples: NestedTensor, targets: List = None, self_training_flag=False):
+        """samples: NestedTensor (tensors [B,3,H,W], mask [B,H,W] True on padding), a tensor or a list of images.
+        In training mode the first half of the batch is the source domain (with `targets`), the second half the
+        target domain.  Returns the reference's output dict (pred_logits, pred_boxes, aux_outputs, interm_outputs,
+        interm_outputs_for_matching_pre, dn_meta, and in training da_output [+ *_target keys])."""
+        if isinstance(samples, (list, torch.Tensor)):
+            samples = nested_tensor_from_tensor_list(samples)
+
+        if self.dn_number > 0 or targets is not None:
+            dn_label, dn_bbox, attn_mask, dn_meta = prepare_for_cdn(
+                dn_args=(targets, self.dn_number, self.dn_label_noise_ratio, self.dn_box_noise_scale),
+                training=self.training, num_queries=self.num_queries, num_classes=self.num_classes,
+                hidden_dim=self.hidden_dim, label_enc=self.label_enc)
+        else:
+            dn_bbox = dn_label = attn_mask = dn_meta = None
+
+        srcs, masks, poss = self._features(samples)
+        if self.training:
+            srcs, masks, poss, srcs_all, masks_all, poss_all, srcs_t, masks_t, poss_t = decompose_features(srcs, masks, poss)
+
+        hs, reference, hs_enc, ref_enc, init_box_proposal = self.transformer(srcs, masks, dn_bbox, poss, dn_label, attn_mask)
+        hs[0] = hs[0] + self.label_enc.weight[0, 0] * 0.0        # keeps label_enc in the graph when there are no objects
+
+        outputs_class, outputs_coord = self._heads(hs, reference)
+        if self.dn_number > 0 and dn_meta is not None:
+            outputs_class, outputs_coord = dn_post_process(outputs_class, outputs_coord, dn_meta, self.aux_loss, self._set_aux_loss)
+        out = {"pred_logits": outputs_class[-1], "pred_boxes": outputs_coord[-1]}
+        if self.aux_loss:
+            out["aux_outputs"] = self._set_aux_loss(outputs_class, outputs_coord)
+        if hs_enc is not None:
+            self._interm(out, hs_enc, ref_enc, init_box_proposal)
+        out["dn_meta"] = dn_meta
+        if not self.training:
+            return out
+
+        # ---- domain adaptation -----------------------------------------------------------------
+        da = {}
+        d_img = [self.D_img(grad_reverse(s)) for s in srcs_all]                       # every level, both domains
+        da["backbone_DA"] = torch.cat([d.flatten(2).transpose(1, 2) for d in d_img], dim=1)
+
+        pad = dn_meta["pad_size"] if dn_meta is not None else 0
+        proto_s, present_s = self._prototypes(hs[-1][:, pad:, :], out["pred_logits"])
+
+        hs_t, reference_t, hs_enc_t, ref_enc_t, init_box_proposal_t = self.transformer(srcs_t, masks_t, None, poss_t, None, None)
+        proto_t, present_t = self._prototypes(hs_t[-1], self.class_embed[-1](hs_t[-1]))
+
+        da["proto_DA"] = {"da_protos": self.Proto_D(grad_reverse(torch.cat([proto_s, proto_t], dim=0))),
+                          "class_map_source": present_s, "class_map_target": present_t}
+        da["global_proto_DA"] = {"output_source": proto_s, "outputs_target": proto_t, "query_mask_source": present_s,
+                                 "query_mask_target": present_t, "global_proto": self.global_proto}
+        out["da_output"] = da
+
+        if self_training_flag:          # expose the target-domain predictions for the pseudo-label losses
+            hs_t[0] = hs_t[0] + self.label_enc.weight[0, 0] * 0.0
+            class_t, coord_t = self._heads(hs_t, reference_t)
+            out["pred_logits_target"], out["pred_boxes_target"] = class_t[-1], coord_t[-1]
+            if self.aux_loss:
+                out["aux_outputs_target"] = self._set_aux_loss(class_t, coord_t)
+            if hs_enc_t is not None:
+                self._interm(out, hs_enc_t, ref_enc_t, init_box_proposal_t, suffix="_target")
+        return out
+
+    @torch.jit.unused
+    def _set_aux_loss(self, outputs_class, outputs_coord):
+        return [{"pred_logits": a, "pred_boxes": b} for a, b in zip(outputs_class[:-1], outputs_coord[:-1])]
+
+
+class SetCriterion(nn.Module):
+    """Hungarian matching + focal / L1 / GIoU losses for the final, auxiliary, intermediate and de-noising
+    outputs, plus DATR's three domain-adaptation losses.  Loss names match the reference's weight_dict keys."""
+
+    def __init__(self, num_classes, matcher, weight_dict, focal_alpha, losses):
+        super().__init__()
+        self.num_classes, self.matcher, self.weight_dict = num_classes, matcher, weight_dict
+        self.losses, self.focal_alpha = losses, focal_alpha
+
+    # ---- individual losses -------------------------------------------------------------------------
+    def loss_labels(self, outputs, targets, indices, num_boxes, log=True):
+        logits = outputs["pred_logits"]
+        idx = self._get_src_permutation_idx(indices)
+        matched = torch.cat([t["labels"][J] for t, (_, J) in zip(targets, indices)])
+        onehot = torch.zeros_like(logits)
+        onehot[idx[0], idx[1], matched] = 1
+        loss_ce = sigmoid_focal_loss(logits, onehot, num_boxes, alpha=self.focal_alpha, gamma=2) * logits.shape[1]
+        losses = {"loss_ce": loss_ce}
+        if log:
+            losses["class_error"] = 100 - accuracy(logits[idx], matched)[0]
+        return losses
+
+    @torch.no_grad()
+    def loss_cardinality(self, outputs, targets, indices, num_boxes):
+        logits = outputs["pred_logits"]
+        n_tgt = torch.as_tensor([len(v["labels"]) for v in targets], device=logits.device)
+        n_pred = (logits.argmax(-1) != logits.shape[-1] - 1).sum(1)
+        return {"cardinality_error": F.l1_loss(n_pred.float(), n_tgt.float())}
+
+    def loss_boxes(self, outputs, targets, indices, num_boxes):
+        idx = self._get_src_permutation_idx(indices)
+        src = outputs["pred_boxes"][idx]
+        tgt = torch.cat([t["boxes"][i] for t, (_, i) in zip(targets, indices)], dim=0)
+        l1 = F.l1_loss(src, tgt, reduction="none")
+        giou = box_ops.paired_giou(box_ops.box_cxcywh_to_xyxy(src), box_ops.box_cxcywh_to_xyxy(tgt))
+        losses = {"loss_bbox": l1.sum() / num_boxes, "loss_giou": (1 - giou).sum() / num_boxes}
+        with torch.no_grad():
+            losses["loss_xy"] = l1[..., :2].sum() / num_boxes
+            losses["loss_hw"] = l1[..., 2:].sum() / num_boxes
+        return losses
+
+    def _get_src_permutation_idx(self, indices):
+        batch_idx = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(indices)])
+        return batch_idx, torch.cat([src for (src, _) in indices])
+
+    def _get_tgt_permutation_idx(self, indices):
+        batch_idx = torch.cat([torch.full_like(tgt, i) for i, (_, tgt) in enumerate(indices)])
+        return batch_idx, torch.cat([tgt for (_, tgt) in indices])
+
+    def get_loss(self, loss, outputs, targets, indices, num_boxes, **kwargs):
+        table = {"labels": self.loss_labels, "cardinality": self.loss_cardinality, "boxes": self.loss_boxes}
+        assert loss in table, f"do you really want to compute {loss} loss?"
+        return table[loss](outputs, targets, indices, num_boxes, **kwargs)
+
+    # ---- domain-adaptation losses ------------------------------------------------------------------
+    def loss_da(self, outputs):
+        """Image-level discriminator logits [2B', S, 1]: source half -> 0, target half -> 1."""
+        B = outputs.shape[0]
+        assert B % 2 == 0
+        src, tgt = outputs[:B // 2], outputs[B // 2:]
+        return F.binary_cross_entropy_with_logits(src, torch.zeros_like(src)) \
+            + F.binary_cross_entropy_with_logits(tgt, torch.ones_like(tgt))
+
+    def loss_proto_da(self, outputs):
+        protos = outputs["da_protos"]
+        assert protos.shape[0] % 2 == 0
+        k = outputs["class_map_source"].shape[0]
+        target = torch.cat([torch.zeros_like(protos[:k]), torch.ones_like(protos[k:])], 0)
+        loss = F.binary_cross_entropy_with_logits(protos, target, reduction="none")
+        present = torch.cat([outputs["class_map_source"], outputs["class_map_target"]], dim=0).unsqueeze(1)
+        return (loss * present).mean()
+
+    def loss_contrast_da(self, outputs):
+        proto = outputs["global_proto"]
+        mask_s, mask_t = outputs["query_mask_source"], outputs["query_mask_target"]
+        assert not proto.requires_grad and not mask_s.requires_grad and not mask_t.requires_grad
+        q_s, q_t = outputs["output_source"], outputs["outputs_target"]
+        assert q_s.requires_grad and q_t.requires_grad
+        k = q_s.shape[0]
+        proto = F.normalize(proto, dim=1).t().contiguous()
+        eye = torch.eye(k, device=proto.device)
+        return F.cross_entropy(F.normalize(q_s, dim=1) @ proto, eye * mask_s) \
+            + F.cross_entropy(F.normalize(q_t, dim=1) @ proto, eye * mask_t)
+
+    # ---- driver ------------------------------------------------------------------------------------
+    def _dn_indices(self, targets, single_pad, scalar, device):
+        pos = []
+        for t in targets:
+            n = len(t["labels"])
+            if n > 0:
+                tgt_idx = torch.arange(n, device=device).repeat(scalar)
+                out_idx = (torch.arange(scalar, device=device)[:, None] * single_pad + torch.arange(n, device=device)[None]).flatten()
+            else:
+                out_idx = tgt_idx = torch.zeros(0, dtype=torch.long, device=device)
+            pos.append((out_idx, tgt_idx))
+        return pos
+
+    def _group(self, outputs, targets, indices, num_boxes, suffix, log_labels=False):
+        out = {}
+        for loss in self.losses:
+            kwargs = {"log": log_labels} if loss == "labels" else {}
+            out.update({k + suffix: v for k, v in self.get_loss(loss, outputs, targets, indices, num_boxes, **kwargs).items()})
+        return out
+
+    def forward(self, outputs, targets, return_indices=False, target_domain_flag=False):
+        """outputs: the model's dict; targets: list of {'labels','boxes'} per (source or pseudo-labelled) image.
+        With target_domain_flag the *_target keys are scored instead (self-training)."""
+        if target_domain_flag:
+            outputs_without_aux = {k.replace("_target", ""): v for k, v in outputs.items() if k != "aux_outputs_target"}
+            outputs.update({"pred_boxes": outputs.pop("pred_boxes_target")})
+            outputs.update({"pred_logits": outputs.pop("pred_logits_target")})
+            device = outputs["pred_logits"].device
+        else:
+            outputs_without_aux = {k: v for k, v in outputs.items() if k != "aux_outputs"}
+            device = next(iter(outputs.values())).device
+
+        if len(targets) > 0:
+            indices = self.matcher(outputs_without_aux, targets)
+            num_boxes = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=device)
+            indices0, indices_list = indices, []
+        else:       # no pseudo labels on this rank: still take part in the collective below
+            indices = None
+            num_boxes = torch.as_tensor([1], dtype=torch.float, device=outputs["pred_logits"].device)
+        if is_dist_avail_and_initialized():
+            torch.distributed.all_reduce(num_boxes)
+        if indices is None:
+            num_boxes = num_boxes - 1
+        num_boxes = torch.clamp(num_boxes / get_world_size(), min=1).item()
+        if indices is None:
+            return {}
+
+        losses = {}
+        dn_zero = ("loss_bbox_dn", "loss_giou_dn", "loss_ce_dn", "loss_xy_dn", "loss_hw_dn", "cardinality_error_dn")
+        use_dn = False
+        if not target_domain_flag:
+            dn_meta = outputs["dn_meta"]
+            use_dn = bool(self.training and dn_meta and "output_known_lbs_bboxes" in dn_meta)
+            if use_dn:
+                known = dn_meta["output_known_lbs_bboxes"]
+                scalar, pad_size = dn_meta["num_dn_group"], dn_meta["pad_size"]
+                assert pad_size % scalar == 0
+                single_pad = pad_size // scalar
+                dn_pos_idx = self._dn_indices(targets, single_pad, scalar, device)
+                losses.update(self._group(known, targets, dn_pos_idx, num_boxes * scalar, "_dn"))
+            else:
+                losses.update({k: torch.as_tensor(0.0, device=device) for k in dn_zero})
+            losses.update(self._group(outputs, targets, indices, num_boxes, "", log_labels=True))
+
+        key_aux = "aux_outputs_target" if target_domain_flag else "aux_outputs"
+        if key_aux in outputs:
+            for i, aux in enumerate(outputs[key_aux]):
+                indices = self.matcher(aux, targets)
+                if return_indices:
+                    indices_list.append(indices)
+                losses.update(self._group(aux, targets, indices, num_boxes, f"_{i}"))
+                if not target_domain_flag:
+                    if use_dn:
+                        losses.update(self._group(known["aux_outputs"][i], targets, dn_pos_idx, num_boxes * scalar, f"_dn_{i}"))
+                    else:
+                        losses.update({f"{k}_{i}": torch.as_tensor(0.0, device=device) for k in dn_zero})
+
+        key_interm = "interm_outputs_target" if target_domain_flag else "interm_outputs"
+        if key_interm in outputs:
+            interm = outputs[key_interm]
+            indices = self.matcher(interm, targets)
+            if return_indices:
+                indices_list.append(indices)
+            losses.update(self._group(interm, targets, indices, num_boxes, "_interm"))
+
+        key_enc = "enc_outputs_target" if target_domain_flag else "enc_outputs"
+        if key_enc in outputs:
+            for i, enc in enumerate(outputs[key_enc]):
+                indices = self.matcher(enc, targets)
+                if return_indices:
+                    indices_list.append(indices)
+                losses.update(self._group(enc, targets, indices, num_boxes, f"_enc_{i}"))
+
+        if "da_output" in outputs:
+            da = outputs["da_output"]
+            losses["loss_backbone_DA"] = self.loss_da(da["backbone_DA"])
+            losses["loss_proto_DA"] = self.loss_proto_da(da["proto_DA"])
+            losses["loss_global_proto_DA"] = self.loss_contrast_da(da["global_proto_DA"])
+
+        if return_indices:
+            indices_list.append(indices0)
+            return losses, indices_list
+        return losses
+
+    def prep_for_dn(self, dn_meta):
+        groups, pad = dn_meta["num_dn_group"], dn_meta["pad_size"]
+        assert pad % groups == 0
+        return dn_meta["output_known_lbs_bboxes"], pad // groups, groups
+
+
+class PostProcess(nn.Module):
+    """Top-k over (query, class) scores -> per-image {'scores','labels','boxes'} in absolute xyxy pixels."""
+
+    def __init__(self, num_select=100, nms_iou_threshold=-1) -> None:
+        super().__init__()
+        self.num_select, self.nms_iou_threshold = num_select, nms_iou_threshold
+
+    @torch.no_grad()
+    def forward(self, outputs, target_sizes, not_to_xyxy=False, test=False):
+        logits, bbox = outputs["pred_logits"], outputs["pred_boxes"]
+        assert len(logits) == len(target_sizes) and target_sizes.shape[1] == 2
+        n_cls = logits.shape[2]
+        scores, flat = torch.topk(logits.sigmoid().view(logits.shape[0], -1), self.num_select, dim=1)
+        query = torch.div(flat, n_cls, rounding_mode="floor")
+        labels = flat % n_cls
+        boxes = bbox if not_to_xyxy else box_ops.box_cxcywh_to_xyxy(bbox)
+        if test:
+            assert not not_to_xyxy
+            boxes[:, :, 2:] = boxes[:, :, 2:] - boxes[:, :, :2]
+        boxes = torch.gather(boxes, 1, query.unsqueeze(-1).repeat(1, 1, 4))
+        img_h, img_w = target_sizes.unbind(1)
+        boxes = boxes * torch.stack([img_w, img_h, img_w, img_h], dim=1)[:, None, :]
+        if self.nms_iou_threshold > 0:
+            from torchvision.ops.boxes import nms
+            keep = [nms(b, s, iou_threshold=self.nms_iou_threshold) for b, s in zip(boxes, scores)]
+            return [{"scores": s[i], "labels": l[i], "boxes": b[i]} for s, l, b, i in zip(scores, labels, boxes, keep)]
+        return [{"scores": s, "labels": l, "boxes": b} for s, l, b in zip(scores, labels, boxes)]
+
+
+@MODULE_BUILD_FUNCS.registe_with_name(module_name="dino")
+def build_dino(args):
+    """args -> (model, criterion, {'bbox': PostProcess}); reads the same fields as the reference (:1018-1136)."""
+    num_classes = args.num_classes
+    device = torch.device(args.device)
+    if getattr(args, "masks", False):
+        raise NotImplementedError("segmentation heads are outside the DINO hot path (masks=False in all DATR configs)")
+    backbone = build_backbone(args)
+    transformer = build_deformable_transformer(args)
+    model = DINO(
+        backbone, transformer, num_classes=num_classes, num_queries=args.num_queries, aux_loss=True, iter_update=True,
+        query_dim=4, random_refpoints_xy=args.random_refpoints_xy, fix_refpoints_hw=args.fix_refpoints_hw,
+        num_feature_levels=args.num_feature_levels, nheads=args.nheads,
+        dec_pred_class_embed_share=getattr(args, "dec_pred_class_embed_share", True),
+        dec_pred_bbox_embed_share=getattr(args, "dec_pred_bbox_embed_share", True),
+        two_stage_type=args.two_stage_type, two_stage_bbox_embed_share=args.two_stage_bbox_embed_share,
+        two_stage_class_embed_share=args.two_stage_class_embed_share, decoder_sa_type=args.decoder_sa_type,
+        num_patterns=args.num_patterns, dn_number=args.dn_number if args.use_dn else 0,
+        dn_box_noise_scale=args.dn_box_noise_scale, dn_label_noise_ratio=args.dn_label_noise_ratio,
+        dn_labelbook_size=getattr(args, "dn_labelbook_size", num_classes))
+    matcher = build_matcher(args)
+
+    weight_dict = {"loss_ce": args.cls_loss_coef, "loss_bbox": args.bbox_loss_coef, "loss_giou": args.giou_loss_coef}
+    plain = copy.deepcopy(weight_dict)
+    weight_dict["loss_backbone_DA"] = args.da_backbone_loss_coef
+    weight_dict["loss_proto_DA"] = args.da_proto_loss_coef
+    weight_dict["loss_global_proto_DA"] = args.da_global_proto_coef
+    weight_dict["loss_self_training"] = args.self_training_loss_coef
+    if args.use_dn:
+        weight_dict.update({"loss_ce_dn": args.cls_loss_coef, "loss_bbox_dn": args.bbox_loss_coef,
+                            "loss_giou_dn": args.giou_loss_coef})
+    per_layer = copy.deepcopy(weight_dict)
+    if args.aux_loss:
+        for i in range(args.dec_layers - 1):
+            weight_dict.update({f"{k}_{i}": v for k, v in per_layer.items()})
+    if args.two_stage_type != "no":
+        no_box = getattr(args, "no_interm_box_loss", False)
+        coef = getattr(args, "interm_loss_coef", 1.0)
+        scale = {"loss_ce": 1.0, "loss_bbox": 0.0 if no_box else 1.0, "loss_giou": 0.0 if no_box else 1.0}
+        weight_dict.update({k + "_interm": v * coef * scale[k] for k, v in plain.items()})
+
+    criterion = SetCriterion(num_classes, matcher=matcher, weight_dict=weight_dict, focal_alpha=args.focal_alpha,
+                             losses=["labels", "boxes", "cardinality"])
+    criterion.to(device)
+    postprocessors = {"bbox": PostProcess(num_select=args.num_select, nms_iou_threshold=args.nms_iou_threshold)}
+    return model, criterion, postprocessors
