@@ -35,6 +35,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "datr_msda.h"
@@ -79,6 +80,13 @@ __device__ __forceinline__ Tap<T> locate(T locx, T locy, int H, int W) {
 }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// ordered (volatile) variant: keeps a batch of loads ahead of the arithmetic that consumes them
+__device__ __forceinline__ float4 ldg4_ordered(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
 
 __device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -423,6 +431,200 @@ msda_bwd_f32_d32_p4(const float* __restrict__ value, const int64_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------
+// Compact geometry table (16 bytes per sample): {pixel index | flags << 26, lx, ly, attn}.
+// flags: bits 0-3 corner (y0x0, y0x1, y1x0, y1x1) contributes; bit 4: x1 is a distinct pixel
+// (x1c = x0c + 1); bit 5: y1 is a distinct row.  Lane `sub` prepares samples sub and sub + 8 of the
+// chunk, so the table writes are conflict-free; rows of a warp are 17 slots apart (bank offset 4).
+// ------------------------------------------------------------------------------------------------
+constexpr int kCRow = kChunk + 1;
+
+__device__ __forceinline__ uint4 pack_tap(float locx, float locy, float a, const LevelGeom& g, bool live) {
+  const Tap<float> t = locate<float>(locx, locy, g.H, g.W);
+  unsigned flags = (t.in[0] ? 1u : 0u) | (t.in[1] ? 2u : 0u) | (t.in[2] ? 4u : 0u) | (t.in[3] ? 8u : 0u);
+  if (!live) flags = 0u;
+  flags |= (t.o[1] != t.o[0]) ? 16u : 0u;
+  flags |= (t.o[2] != t.o[0]) ? 32u : 0u;
+  uint4 q;
+  q.x = unsigned(g.start + t.o[0]) | (flags << 26);
+  q.y = __float_as_uint(t.lx); q.z = __float_as_uint(t.ly); q.w = __float_as_uint(a);
+  return q;
+}
+
+template <int kBatch>
+__global__ void __launch_bounds__(256)
+msda_fwd_f32_d32_p4c(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
+                     const float* __restrict__ attn, int N, int S, int M, int L, int Lq,
+                     float* __restrict__ out) {
+  __shared__ __align__(16) uint4 taps[8][4][kCRow];
+  __shared__ LevelGeom geom[kMaxLevels];
+  load_levels(geom, shapes, lstart, L);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 3, sub = lane & 7;
+  const int m = blockIdx.x % M;
+  long long bq = (long long)(blockIdx.x / M) * kRowsPerCta + warp * 4 + r;
+  const bool live = bq < (long long)N * Lq;
+  if (!live) bq = (long long)N * Lq - 1;
+  const int b = int(bq / Lq);
+  const long long row = bq * M + m;
+  const int rs = M * 32;
+  const int LP = L * 4;
+  const float* vb = value + (long long)b * S * rs + m * 32 + sub * 4;
+  uint4* mytaps = &taps[warp][r][0];
+
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s0 = 0; s0 < LP; s0 += kChunk) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int s = s0 + sub + 8 * k;
+      if (s < LP) {
+        const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
+        const float a = __ldg(attn + row * LP + s);
+        mytaps[sub + 8 * k] = pack_tap(xy.x, xy.y, a, geom[s >> 2], true);
+      }
+    }
+    __syncwarp();
+    const int n = min(kChunk, LP - s0);
+    for (int j0 = 0; j0 < n; j0 += 4) {
+      const int W = geom[(s0 + j0) >> 2].W;
+#pragma unroll
+      for (int jb = 0; jb < 4; jb += kBatch) {
+        float4 v[kBatch][4];
+        float w[kBatch][4];
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j) {
+          const uint4 q = mytaps[j0 + jb + j];
+          const unsigned flags = q.x >> 26;
+          const int base = int(q.x & 0x03ffffffu);
+          const int dx = (flags >> 4) & 1, dy = (flags & 32u) ? W : 0;
+          const float lx = __uint_as_float(q.y), ly = __uint_as_float(q.z), a = __uint_as_float(q.w);
+          const float wy0 = (1.f - ly) * a, wy1 = ly * a, hx = 1.f - lx;
+          w[j][0] = (flags & 1u) ? wy0 * hx : 0.f;
+          w[j][1] = (flags & 2u) ? wy0 * lx : 0.f;
+          w[j][2] = (flags & 4u) ? wy1 * hx : 0.f;
+          w[j][3] = (flags & 8u) ? wy1 * lx : 0.f;
+          const float* p00 = vb + (long long)base * rs;
+          v[j][0] = ldg4_ordered(p00);
+          v[j][1] = ldg4_ordered(p00 + dx * rs);
+          v[j][2] = ldg4_ordered(p00 + (long long)dy * rs);
+          v[j][3] = ldg4_ordered(p00 + (long long)(dy + dx) * rs);
+        }
+#pragma unroll
+        for (int j = 0; j < kBatch; ++j)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc.x = fmaf(w[j][i], v[j][i].x, acc.x);
+            acc.y = fmaf(w[j][i], v[j][i].y, acc.y);
+            acc.z = fmaf(w[j][i], v[j][i].z, acc.z);
+            acc.w = fmaf(w[j][i], v[j][i].w, acc.w);
+          }
+      }
+    }
+    __syncwarp();
+  }
+  if (live) *reinterpret_cast<float4*>(out + row * 32 + sub * 4) = acc;
+}
+
+template <int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
+msda_bwd_f32_d32_p4c(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
+                     const float* __restrict__ attn, const float* __restrict__ grad_out,
+                     int N, int S, int M, int L, int Lq,
+                     float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
+  __shared__ __align__(16) uint4 taps[8][4][kCRow];
+  __shared__ LevelGeom geom[kMaxLevels];
+  load_levels(geom, shapes, lstart, L);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 3, sub = lane & 7;
+  const int m = blockIdx.x % M;
+  long long bq = (long long)(blockIdx.x / M) * kRowsPerCta + warp * 4 + r;
+  const bool live = bq < (long long)N * Lq;
+  if (!live) bq = (long long)N * Lq - 1;
+  const int b = int(bq / Lq);
+  const long long row = bq * M + m;
+  const int rs = M * 32;
+  const int LP = L * 4;
+  const long long voff = (long long)b * S * rs + m * 32 + sub * 4;
+  const float* vb = value + voff;
+  float* gvb = grad_value + voff;
+  uint4* mytaps = &taps[warp][r][0];
+  const float4 g = ldg4(grad_out + row * 32 + sub * 4);
+  const bool hi4 = (sub & 4) != 0, hi2 = (sub & 2) != 0;
+
+  for (int s0 = 0; s0 < LP; s0 += kChunk) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int s = s0 + sub + 8 * k;
+      if (s < LP) {
+        const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
+        const float a = __ldg(attn + row * LP + s);
+        mytaps[sub + 8 * k] = pack_tap(xy.x, xy.y, a, geom[s >> 2], live);
+      }
+    }
+    __syncwarp();
+    const int n = min(kChunk, LP - s0);
+    for (int j0 = 0; j0 < n; j0 += 4) {
+      const LevelGeom gm = geom[(s0 + j0) >> 2];
+      float d[4][4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const uint4 q = mytaps[j0 + p];
+        const unsigned flags = q.x >> 26;
+        const int base = int(q.x & 0x03ffffffu);
+        const int dx = (flags >> 4) & 1, dy = (flags & 32u) ? gm.W : 0;
+        const float lx = __uint_as_float(q.y), ly = __uint_as_float(q.z), a = __uint_as_float(q.w);
+        const float hx = 1.f - lx, hy = 1.f - ly;
+        const float cw[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+        const long long oo[4] = {(long long)base * rs, (long long)(base + dx) * rs, (long long)(base + dy) * rs,
+                                 (long long)(base + dy + dx) * rs};
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = ldg4(vb + oo[i]);
+        const float4 tv = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const bool on = (flags >> i) & 1u;
+          if (on) red_add4(gvb + oo[i], cw[i] * tv.x, cw[i] * tv.y, cw[i] * tv.z, cw[i] * tv.w);
+          d[p][i] = on ? dot4(g, v[i]) : 0.f;
+        }
+      }
+      float e[2][4], f[4];
+#pragma unroll
+      for (int k = 0; k < 2; ++k)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float send = hi4 ? d[k][i] : d[k + 2][i];
+          const float keep = hi4 ? d[k + 2][i] : d[k][i];
+          e[k][i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float send = hi2 ? e[0][i] : e[1][i];
+        const float keep = hi2 ? e[1][i] : e[0][i];
+        f[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+        f[i] += __shfl_xor_sync(0xffffffffu, f[i], 1);
+      }
+      const int p = sub >> 1;
+      const uint4 q = mytaps[j0 + p];
+      const float lx = __uint_as_float(q.y), ly = __uint_as_float(q.z), a = __uint_as_float(q.w);
+      const float hx = 1.f - lx, hy = 1.f - ly;
+      const long long k = row * LP + s0 + j0 + p;
+      if (live) {
+        if (sub & 1) {
+          const float gx = a * float(gm.W) * (hy * (f[1] - f[0]) + ly * (f[3] - f[2]));
+          const float gy = a * float(gm.H) * (hx * (f[2] - f[0]) + lx * (f[3] - f[1]));
+          reinterpret_cast<float2*>(grad_loc)[k] = make_float2(gx, gy);
+        } else {
+          grad_attn[k] = hy * hx * f[0] + hy * lx * f[1] + ly * hx * f[2] + ly * lx * f[3];
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Generic kernels: any channel count / point count, float or double.  One warp per (b,q,m) row,
 // lanes stride over channels.
 // ------------------------------------------------------------------------------------------------
@@ -516,6 +718,11 @@ msda_bwd_generic(const T* __restrict__ value, const int64_t* __restrict__ shapes
 // ------------------------------------------------------------------------------------------------
 // Host side.
 // ------------------------------------------------------------------------------------------------
+int tuning_variant() {   // DATR_MSDA_VARIANT: kernel selection for tuning runs (default = production choice)
+  static const int v = [] { const char* e = getenv("DATR_MSDA_VARIANT"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 int check_common(const void* value, const int64_t* shapes, const int64_t* lstart, const void* loc,
@@ -565,8 +772,14 @@ int datr_msda_forward(const void* value, const int64_t* shapes, const int64_t* l
     const float* at = static_cast<const float*>(attn);
     float* o = static_cast<float*>(out);
 #define DATR_FWD(PP) msda_fwd_f32_d32<PP><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o)
-    if (P == 4 && L <= kMaxLevels) {
-      msda_fwd_f32_d32_p4<<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o);
+    if (P == 4 && L <= kMaxLevels && tuning_variant() != 9) {
+      const bool small_s = (long long)S < (1LL << 26);
+      switch (small_s ? tuning_variant() : 1) {
+        case 1: msda_fwd_f32_d32_p4<<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o); break;
+        case 2: msda_fwd_f32_d32_p4c<1><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o); break;
+        case 3: msda_fwd_f32_d32_p4c<2><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o); break;
+        default: msda_fwd_f32_d32_p4c<4><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o); break;
+      }
       return after_launch("msda_fwd_f32_d32_p4");
     }
     switch (P) {
@@ -614,8 +827,14 @@ int datr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
     float* ga = static_cast<float*>(grad_attn);
 #define DATR_BWD(PP) \
   msda_bwd_f32_d32<PP><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga)
-    if (P == 4 && L <= kMaxLevels) {
-      msda_bwd_f32_d32_p4<<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga);
+    if (P == 4 && L <= kMaxLevels && tuning_variant() != 9) {
+      const bool small_s = (long long)S < (1LL << 26);
+      switch (small_s ? tuning_variant() : 1) {
+        case 1: msda_bwd_f32_d32_p4<<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga); break;
+        case 2: msda_bwd_f32_d32_p4c<1><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga); break;
+        case 3: msda_bwd_f32_d32_p4c<3><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga); break;
+        default: msda_bwd_f32_d32_p4c<4><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga); break;
+      }
       return after_launch("msda_bwd_f32_d32_p4");
     }
     switch (P) {
