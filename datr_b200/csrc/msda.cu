@@ -20,15 +20,15 @@
 //     reference stages them in shared memory and sums serially on thread 0, cuh:377-393);
 //     grad_value uses 16-byte vector reductions (red.global.add.v4.f32), one per corner per lane,
 //     instead of 4 scalar atomics.
-//   * the P = 4 kernels (the DINO configuration; `_p4` below) additionally remove the per-lane
-//     redundancy of the sample geometry: the 8 lanes of a row split its L*P samples between them
-//     (one coalesced 16-byte loc load + one 8-byte attn load per lane), compute offsets and weights
-//     once, and publish them to the other lanes through a conflict-free per-warp shared-memory
-//     table.  The gather loop is then 2 LDS + 4 LDG.128 + 16 FFMA per sample for four rows at once,
-//     which leaves the kernel bound by L1 line throughput (one 128-byte line per corner per row)
-//     instead of instruction issue.  The backward kernel reduces four corner dot-products per
-//     sample with a transposing butterfly (16 shuffles per 4 samples instead of 36) and derives
-//     grad_loc / grad_attn from those four scalars.
+//   * the P = 4 forward kernel (the DINO configuration; `_p4c` below) additionally removes the
+//     per-lane redundancy of the sample geometry: the 8 lanes of a row split its L*P samples between
+//     them (coalesced loc / attn loads), compute the geometry once and publish it to the other lanes
+//     as 16-byte records in a conflict-free per-warp shared-memory table.  Measured on B200 at the
+//     DINO-4scale encoder shape this halves the issued instructions (158 M -> 82 M warp
+//     instructions) and leaves the kernel bound by L1 line throughput: one 128-byte wavefront per
+//     (row, corner), 22.8 M per call, ~68 % of the l1tex data-pipe peak (profiles/).  For the
+//     backward kernel the same restructuring measured slower (the kernel is bound by L2 vector
+//     reductions: 82.5 M red sectors per call), so it keeps the direct per-lane geometry.
 //   * any other channel count, and fp64, run the generic warp-per-row kernels below.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -227,12 +227,11 @@ msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
 }
 
 // ------------------------------------------------------------------------------------------------
-// fp32, D = 32, P = 4: shared geometry table.  One warp = 4 rows x 8 lanes; per row a chunk holds up
-// to 16 samples (4 levels), 32 bytes each: {int4 corner pixel indices, float4 payload}.  Row stride
-// 34 x 16 B = 544 B puts the four rows of a warp on disjoint banks for the broadcast LDS.128.
+// fp32, D = 32, P = 4 forward: the 8 lanes of a row split its L*P samples between them, compute the
+// sample geometry once and publish it through a per-warp shared-memory table (a chunk = 16 samples
+// = 4 levels).
 // ------------------------------------------------------------------------------------------------
 constexpr int kChunk = 16;                    // samples per chunk
-constexpr int kTapRow = 2 * kChunk + 2;       // uint4 slots per row (2 per sample + 2 padding)
 
 struct LevelGeom { int H, W, start; };
 
@@ -247,188 +246,6 @@ __device__ __forceinline__ void load_levels(LevelGeom* sh, const int64_t* __rest
 }
 
 constexpr int kMaxLevels = 32;
-
-__global__ void __launch_bounds__(256)
-msda_fwd_f32_d32_p4(const float* __restrict__ value, const int64_t* __restrict__ shapes,
-                    const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                    const float* __restrict__ attn, int N, int S, int M, int L, int Lq,
-                    float* __restrict__ out) {
-  __shared__ __align__(16) uint4 taps[8][4][kTapRow];
-  __shared__ LevelGeom geom[kMaxLevels];
-  load_levels(geom, shapes, lstart, L);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 3, sub = lane & 7;
-  const int m = blockIdx.x % M;
-  long long bq = (long long)(blockIdx.x / M) * kRowsPerCta + warp * 4 + r;
-  const bool live = bq < (long long)N * Lq;
-  if (!live) bq = (long long)N * Lq - 1;
-  const int b = int(bq / Lq);
-  const long long row = bq * M + m;
-  const int rs = M * 32;
-  const int LP = L * 4;
-  const float* vb = value + (long long)b * S * rs + m * 32 + sub * 4;
-  uint4* mytaps = &taps[warp][r][0];
-
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s0 = 0; s0 < LP; s0 += kChunk) {
-    const int s = s0 + 2 * sub;                      // this lane prepares samples s and s+1 (same level)
-    if (s < LP) {
-      const LevelGeom g = geom[s >> 2];
-      const float4 xy = ldg4(loc + (row * LP + s) * 2);
-      const float2 a2 = __ldg(reinterpret_cast<const float2*>(attn + row * LP + s));
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const Tap<float> t = locate<float>(k ? xy.z : xy.x, k ? xy.w : xy.y, g.H, g.W);
-        const float a = k ? a2.y : a2.x;
-        const float wy0 = t.hy * a, wy1 = t.ly * a;
-        uint4 o;
-        float4 w;
-        o.x = g.start + t.o[0]; o.y = g.start + t.o[1]; o.z = g.start + t.o[2]; o.w = g.start + t.o[3];
-        w.x = t.in[0] ? wy0 * t.hx : 0.f;
-        w.y = t.in[1] ? wy0 * t.lx : 0.f;
-        w.z = t.in[2] ? wy1 * t.hx : 0.f;
-        w.w = t.in[3] ? wy1 * t.lx : 0.f;
-        mytaps[2 * (2 * sub + k)] = o;
-        mytaps[2 * (2 * sub + k) + 1] = *reinterpret_cast<uint4*>(&w);
-      }
-    }
-    __syncwarp();
-    const int n = min(kChunk, LP - s0);              // multiple of 4
-    for (int j0 = 0; j0 < n; j0 += 4) {
-      float4 v[4][4];
-      float4 w[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint4 o = mytaps[2 * (j0 + j)];
-        const uint4 wb = mytaps[2 * (j0 + j) + 1];
-        w[j] = *reinterpret_cast<const float4*>(&wb);
-        v[j][0] = ldg4(vb + (long long)o.x * rs);
-        v[j][1] = ldg4(vb + (long long)o.y * rs);
-        v[j][2] = ldg4(vb + (long long)o.z * rs);
-        v[j][3] = ldg4(vb + (long long)o.w * rs);
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float ww[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc.x = fmaf(ww[i], v[j][i].x, acc.x);
-          acc.y = fmaf(ww[i], v[j][i].y, acc.y);
-          acc.z = fmaf(ww[i], v[j][i].z, acc.z);
-          acc.w = fmaf(ww[i], v[j][i].w, acc.w);
-        }
-      }
-    }
-    __syncwarp();
-  }
-  if (live) *reinterpret_cast<float4*>(out + row * 32 + sub * 4) = acc;
-}
-
-__global__ void __launch_bounds__(256)
-msda_bwd_f32_d32_p4(const float* __restrict__ value, const int64_t* __restrict__ shapes,
-                    const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                    const float* __restrict__ attn, const float* __restrict__ grad_out,
-                    int N, int S, int M, int L, int Lq,
-                    float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
-  __shared__ __align__(16) uint4 taps[8][4][kTapRow];
-  __shared__ LevelGeom geom[kMaxLevels];
-  load_levels(geom, shapes, lstart, L);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 3, sub = lane & 7;
-  const int m = blockIdx.x % M;
-  long long bq = (long long)(blockIdx.x / M) * kRowsPerCta + warp * 4 + r;
-  const bool live = bq < (long long)N * Lq;
-  if (!live) bq = (long long)N * Lq - 1;
-  const int b = int(bq / Lq);
-  const long long row = bq * M + m;
-  const int rs = M * 32;
-  const int LP = L * 4;
-  const long long voff = (long long)b * S * rs + m * 32 + sub * 4;
-  const float* vb = value + voff;
-  float* gvb = grad_value + voff;
-  uint4* mytaps = &taps[warp][r][0];
-  const float4 g = ldg4(grad_out + row * 32 + sub * 4);
-  const bool hi4 = (sub & 4) != 0, hi2 = (sub & 2) != 0;
-
-  for (int s0 = 0; s0 < LP; s0 += kChunk) {
-    const int s = s0 + 2 * sub;
-    if (s < LP) {
-      const LevelGeom gm = geom[s >> 2];
-      const float4 xy = ldg4(loc + (row * LP + s) * 2);
-      const float2 a2 = __ldg(reinterpret_cast<const float2*>(attn + row * LP + s));
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const Tap<float> t = locate<float>(k ? xy.z : xy.x, k ? xy.w : xy.y, gm.H, gm.W);
-        uint4 o;
-        o.x = gm.start + t.o[0]; o.y = gm.start + t.o[1]; o.z = gm.start + t.o[2]; o.w = gm.start + t.o[3];
-        const unsigned flags = (t.in[0] ? 1u : 0u) | (t.in[1] ? 2u : 0u) | (t.in[2] ? 4u : 0u) | (t.in[3] ? 8u : 0u);
-        uint4 q;
-        q.x = __float_as_uint(t.lx); q.y = __float_as_uint(t.ly);
-        q.z = __float_as_uint(k ? a2.y : a2.x); q.w = live ? flags : 0u;   // dead rows contribute nothing
-        mytaps[2 * (2 * sub + k)] = o;
-        mytaps[2 * (2 * sub + k) + 1] = q;
-      }
-    }
-    __syncwarp();
-    const int n = min(kChunk, LP - s0);
-    for (int j0 = 0; j0 < n; j0 += 4) {              // one level: its 4 points
-      float d[4][4];                                  // <grad_out, corner value> per point and corner
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const uint4 o = mytaps[2 * (j0 + p)];
-        const uint4 q = mytaps[2 * (j0 + p) + 1];
-        const float lx = __uint_as_float(q.x), ly = __uint_as_float(q.y), a = __uint_as_float(q.z);
-        const unsigned flags = q.w;
-        const float hx = 1.f - lx, hy = 1.f - ly;
-        const float cw[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
-        const unsigned oo[4] = {o.x, o.y, o.z, o.w};
-        float4 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = ldg4(vb + (long long)oo[i] * rs);
-        const float4 tv = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool on = (flags >> i) & 1u;
-          if (on) red_add4(gvb + (long long)oo[i] * rs, cw[i] * tv.x, cw[i] * tv.y, cw[i] * tv.z, cw[i] * tv.w);
-          d[p][i] = on ? dot4(g, v[i]) : 0.f;
-        }
-      }
-      // transposing butterfly over the 8 lanes of the row: lanes (2p, 2p+1) end with the totals of point p
-      float e[2][4], f[4];
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float send = hi4 ? d[k][i] : d[k + 2][i];
-          const float keep = hi4 ? d[k + 2][i] : d[k][i];
-          e[k][i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float send = hi2 ? e[0][i] : e[1][i];
-        const float keep = hi2 ? e[1][i] : e[0][i];
-        f[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        f[i] += __shfl_xor_sync(0xffffffffu, f[i], 1);
-      }
-      const int p = sub >> 1;
-      const uint4 q = mytaps[2 * (j0 + p) + 1];
-      const float lx = __uint_as_float(q.x), ly = __uint_as_float(q.y), a = __uint_as_float(q.z);
-      const float hx = 1.f - lx, hy = 1.f - ly;
-      const long long k = row * LP + s0 + j0 + p;
-      if (live) {
-        if (sub & 1) {
-          const LevelGeom gm = geom[(s0 + j0) >> 2];
-          const float gx = a * float(gm.W) * (hy * (f[1] - f[0]) + ly * (f[3] - f[2]));
-          const float gy = a * float(gm.H) * (hx * (f[2] - f[0]) + lx * (f[3] - f[1]));
-          reinterpret_cast<float2*>(grad_loc)[k] = make_float2(gx, gy);
-        } else {
-          grad_attn[k] = hy * hx * f[0] + hy * lx * f[1] + ly * hx * f[2] + ly * lx * f[3];
-        }
-      }
-    }
-    __syncwarp();
-  }
-}
 
 // ------------------------------------------------------------------------------------------------
 // Compact geometry table (16 bytes per sample): {pixel index | flags << 26, lx, ly, attn}.
@@ -525,105 +342,6 @@ msda_fwd_f32_d32_p4c(const float* __restrict__ value, const int64_t* __restrict_
   if (live) *reinterpret_cast<float4*>(out + row * 32 + sub * 4) = acc;
 }
 
-template <int kMinBlocks>
-__global__ void __launch_bounds__(256, kMinBlocks)
-msda_bwd_f32_d32_p4c(const float* __restrict__ value, const int64_t* __restrict__ shapes,
-                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                     const float* __restrict__ attn, const float* __restrict__ grad_out,
-                     int N, int S, int M, int L, int Lq,
-                     float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
-  __shared__ __align__(16) uint4 taps[8][4][kCRow];
-  __shared__ LevelGeom geom[kMaxLevels];
-  load_levels(geom, shapes, lstart, L);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 3, sub = lane & 7;
-  const int m = blockIdx.x % M;
-  long long bq = (long long)(blockIdx.x / M) * kRowsPerCta + warp * 4 + r;
-  const bool live = bq < (long long)N * Lq;
-  if (!live) bq = (long long)N * Lq - 1;
-  const int b = int(bq / Lq);
-  const long long row = bq * M + m;
-  const int rs = M * 32;
-  const int LP = L * 4;
-  const long long voff = (long long)b * S * rs + m * 32 + sub * 4;
-  const float* vb = value + voff;
-  float* gvb = grad_value + voff;
-  uint4* mytaps = &taps[warp][r][0];
-  const float4 g = ldg4(grad_out + row * 32 + sub * 4);
-  const bool hi4 = (sub & 4) != 0, hi2 = (sub & 2) != 0;
-
-  for (int s0 = 0; s0 < LP; s0 += kChunk) {
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int s = s0 + sub + 8 * k;
-      if (s < LP) {
-        const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
-        const float a = __ldg(attn + row * LP + s);
-        mytaps[sub + 8 * k] = pack_tap(xy.x, xy.y, a, geom[s >> 2], live);
-      }
-    }
-    __syncwarp();
-    const int n = min(kChunk, LP - s0);
-    for (int j0 = 0; j0 < n; j0 += 4) {
-      const LevelGeom gm = geom[(s0 + j0) >> 2];
-      float d[4][4];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const uint4 q = mytaps[j0 + p];
-        const unsigned flags = q.x >> 26;
-        const int base = int(q.x & 0x03ffffffu);
-        const int dx = (flags >> 4) & 1, dy = (flags & 32u) ? gm.W : 0;
-        const float lx = __uint_as_float(q.y), ly = __uint_as_float(q.z), a = __uint_as_float(q.w);
-        const float hx = 1.f - lx, hy = 1.f - ly;
-        const float cw[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
-        const long long oo[4] = {(long long)base * rs, (long long)(base + dx) * rs, (long long)(base + dy) * rs,
-                                 (long long)(base + dy + dx) * rs};
-        float4 v[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = ldg4(vb + oo[i]);
-        const float4 tv = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const bool on = (flags >> i) & 1u;
-          if (on) red_add4(gvb + oo[i], cw[i] * tv.x, cw[i] * tv.y, cw[i] * tv.z, cw[i] * tv.w);
-          d[p][i] = on ? dot4(g, v[i]) : 0.f;
-        }
-      }
-      float e[2][4], f[4];
-#pragma unroll
-      for (int k = 0; k < 2; ++k)
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float send = hi4 ? d[k][i] : d[k + 2][i];
-          const float keep = hi4 ? d[k + 2][i] : d[k][i];
-          e[k][i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float send = hi2 ? e[0][i] : e[1][i];
-        const float keep = hi2 ? e[1][i] : e[0][i];
-        f[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-        f[i] += __shfl_xor_sync(0xffffffffu, f[i], 1);
-      }
-      const int p = sub >> 1;
-      const uint4 q = mytaps[j0 + p];
-      const float lx = __uint_as_float(q.y), ly = __uint_as_float(q.z), a = __uint_as_float(q.w);
-      const float hx = 1.f - lx, hy = 1.f - ly;
-      const long long k = row * LP + s0 + j0 + p;
-      if (live) {
-        if (sub & 1) {
-          const float gx = a * float(gm.W) * (hy * (f[1] - f[0]) + ly * (f[3] - f[2]));
-          const float gy = a * float(gm.H) * (hx * (f[2] - f[0]) + lx * (f[3] - f[1]));
-          reinterpret_cast<float2*>(grad_loc)[k] = make_float2(gx, gy);
-        } else {
-          grad_attn[k] = hy * hx * f[0] + hy * lx * f[1] + ly * hx * f[2] + ly * lx * f[3];
-        }
-      }
-    }
-    __syncwarp();
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Generic kernels: any channel count / point count, float or double.  One warp per (b,q,m) row,
 // lanes stride over channels.
@@ -718,11 +436,6 @@ msda_bwd_generic(const T* __restrict__ value, const int64_t* __restrict__ shapes
 // ------------------------------------------------------------------------------------------------
 // Host side.
 // ------------------------------------------------------------------------------------------------
-int tuning_variant() {   // DATR_MSDA_VARIANT: kernel selection for tuning runs (default = production choice)
-  static const int v = [] { const char* e = getenv("DATR_MSDA_VARIANT"); return e ? atoi(e) : 0; }();
-  return v;
-}
-
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 int check_common(const void* value, const int64_t* shapes, const int64_t* lstart, const void* loc,
@@ -772,15 +485,9 @@ int datr_msda_forward(const void* value, const int64_t* shapes, const int64_t* l
     const float* at = static_cast<const float*>(attn);
     float* o = static_cast<float*>(out);
 #define DATR_FWD(PP) msda_fwd_f32_d32<PP><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o)
-    if (P == 4 && L <= kMaxLevels && tuning_variant() != 9) {
-      const bool small_s = (long long)S < (1LL << 26);
-      switch (small_s ? tuning_variant() : 1) {
-        case 1: msda_fwd_f32_d32_p4<<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o); break;
-        case 2: msda_fwd_f32_d32_p4c<1><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o); break;
-        case 3: msda_fwd_f32_d32_p4c<2><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o); break;
-        default: msda_fwd_f32_d32_p4c<4><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o); break;
-      }
-      return after_launch("msda_fwd_f32_d32_p4");
+    if (P == 4 && L <= kMaxLevels && (long long)S < (1LL << 26)) {
+      msda_fwd_f32_d32_p4c<2><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o);
+      return after_launch("msda_fwd_f32_d32_p4c");
     }
     switch (P) {
       case 1: DATR_FWD(1); break;
@@ -827,16 +534,6 @@ int datr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
     float* ga = static_cast<float*>(grad_attn);
 #define DATR_BWD(PP) \
   msda_bwd_f32_d32<PP><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga)
-    if (P == 4 && L <= kMaxLevels && tuning_variant() != 9) {
-      const bool small_s = (long long)S < (1LL << 26);
-      switch (small_s ? tuning_variant() : 1) {
-        case 1: msda_bwd_f32_d32_p4<<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga); break;
-        case 2: msda_bwd_f32_d32_p4c<1><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga); break;
-        case 3: msda_bwd_f32_d32_p4c<3><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga); break;
-        default: msda_bwd_f32_d32_p4c<4><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga); break;
-      }
-      return after_launch("msda_bwd_f32_d32_p4");
-    }
     switch (P) {
       case 1: DATR_BWD(1); break;
       case 2: DATR_BWD(2); break;

@@ -11,6 +11,10 @@ import torch
 
 from datr_b200.util.misc import inverse_sigmoid
 
+# random sources (module-level so a test can feed a CPU-generated stream to a CUDA run)
+_rand_like = torch.rand_like
+_randint_like = torch.randint_like
+
 
 def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, label_enc):
     """-> (input_query_label [B,pad,C], input_query_bbox [B,pad,4] (logits), attn_mask [pad+nq,pad+nq] bool
@@ -44,8 +48,8 @@ def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, lab
     noisy_boxes = gt_boxes.clone()
 
     if label_noise_ratio > 0:
-        flip = torch.nonzero(torch.rand_like(noisy_labels.float()) < label_noise_ratio * 0.5).view(-1)
-        noisy_labels.scatter_(0, flip, torch.randint_like(flip, 0, num_classes))
+        flip = torch.nonzero(_rand_like(noisy_labels.float()) < label_noise_ratio * 0.5).view(-1)
+        noisy_labels.scatter_(0, flip, _randint_like(flip, 0, num_classes))
 
     pad_size = most * reps
     # rows [g*2T, g*2T+T) of the repeated set are positives of group g, the next T rows negatives
@@ -54,8 +58,8 @@ def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, lab
     if box_noise_scale > 0:
         corners = torch.cat([gt_boxes[:, :2] - gt_boxes[:, 2:] / 2, gt_boxes[:, :2] + gt_boxes[:, 2:] / 2], 1)
         half = (gt_boxes[:, 2:] / 2).repeat(1, 2)
-        sign = torch.randint_like(gt_boxes, low=0, high=2, dtype=torch.float32) * 2.0 - 1.0
-        mag = torch.rand_like(gt_boxes)
+        sign = _randint_like(gt_boxes, low=0, high=2, dtype=torch.float32) * 2.0 - 1.0
+        mag = _rand_like(gt_boxes)
         mag = (mag + is_negative[:, None].to(mag.dtype)) * sign
         corners = (corners + mag * half * box_noise_scale).clamp(min=0.0, max=1.0)
         noisy_boxes = torch.cat([(corners[:, :2] + corners[:, 2:]) / 2, corners[:, 2:] - corners[:, :2]], 1)

@@ -1,0 +1,71 @@
+"""Data parallelism for the DINO hot path: one process per GPU, one flat fp32 gradient buffer, ONE NCCL
+all-reduce per step.
+
+Replaces the reference's `DistributedDataParallel(model, find_unused_parameters=True)` (main.py:156) for the
+training step: every trainable parameter's .grad is a view into one contiguous buffer, so
+  * zeroing the gradients is one memset,
+  * parameters that did not take part in the step contribute zeros (what find_unused_parameters achieves),
+  * the gradient exchange is a single 191 MB (DINO-4scale) sum-all-reduce over NVLink followed by a scale by
+    1/world_size -- DDP's averaging semantics,
+  * gradient clipping (engine.py:110, max_norm 0.1) is one norm + one scale over the flat buffer.
+Works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)."""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+class FlatGradients:
+    def __init__(self, model: torch.nn.Module, process_group=None):
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        assert self.params, "model has no trainable parameters"
+        dev, dt = self.params[0].device, self.params[0].dtype
+        assert all(p.device == dev and p.dtype == dt for p in self.params)
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.group = process_group
+
+    @property
+    def world_size(self):
+        return dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+
+    def zero(self):
+        self.flat.zero_()
+
+    def check_views(self):
+        """True while every .grad still aliases the flat buffer (an optimizer.zero_grad(set_to_none=True) breaks it)."""
+        base = self.flat.data_ptr()
+        return all(p.grad is not None and base <= p.grad.data_ptr() < base + self.numel * self.flat.element_size()
+                   for p in self.params)
+
+    def all_reduce(self):
+        """Average the gradients over the ranks: one collective on the flat buffer."""
+        ws = self.world_size
+        if ws > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+            self.flat.mul_(1.0 / ws)
+
+    def clip_(self, max_norm: float):
+        """torch.nn.utils.clip_grad_norm_ on the flat buffer; returns the total norm (0-dim tensor, no host sync)."""
+        norm = torch.linalg.vector_norm(self.flat)
+        self.flat.mul_(torch.clamp(max_norm / (norm + 1e-6), max=1.0))
+        return norm
+
+
+def broadcast_parameters(model: torch.nn.Module, src: int = 0, group=None):
+    """Initial parameter/buffer sync (the broadcast DDP does at construction)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src=src, group=group)
+
+
+def param_groups(model, lr=1e-4, lr_backbone=1e-5):
+    """The two parameter groups of the reference (util/get_param_dicts.py:23-31): 'backbone' in the name -> lr_backbone."""
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    return [{"params": [p for n, p in named if "backbone" not in n], "lr": lr},
+            {"params": [p for n, p in named if "backbone" in n], "lr": lr_backbone}]

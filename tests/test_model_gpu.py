@@ -1,0 +1,140 @@
+"""GPU: the models/dino package running on the CUDA kernels (MSDeformAttn through the C ABI) against the golden
+vectors produced by the reference's own model code on CPU (tests/golden/make_model_golden.py).
+
+Bar (BASELINE.json north_star): outputs within 1e-3 relative (max|a-b| / max|b| per tensor) in fp32, index work
+(two-stage top-k, Hungarian assignment, PostProcess top-k labels) bit-exact.  TF32 is switched off for these
+tests so the library GEMMs / convolutions are true fp32 like the CPU reference run."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import model_cases as mcase
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REL = 1e-3
+
+
+@pytest.fixture(scope="module")
+def G():
+    return np.load(os.path.join(ROOT, "tests", "golden", "model_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def small():
+    assert torch.cuda.is_available()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    from datr_b200.models.dino.dino import build_dino
+    torch.manual_seed(0)
+    model, crit, post = build_dino(mcase.small_args(device="cuda"))
+    model.load_state_dict(mcase.seeded_state_dict(model), strict=True)
+    return model.cuda(), crit, post
+
+
+@pytest.fixture()
+def cpu_noise(monkeypatch):
+    """Feed the de-noising query generator the CPU random stream the golden run used."""
+    from datr_b200.models.dino import dn_components as dn
+    monkeypatch.setattr(dn, "_rand_like", lambda t, **k: torch.rand(t.shape, dtype=k.get("dtype", t.dtype)).to(t.device))
+    monkeypatch.setattr(dn, "_randint_like", lambda t, *a, **k: torch.randint_like(t.cpu(), *a, **k).to(t.device))
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+def finite_rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert np.array_equal(np.isinf(a), np.isinf(b))
+    m = np.isfinite(b)
+    return rel(a[m], b[m]) if m.any() else 0.0
+
+
+def test_cuda_kernels_are_on_the_path(small):
+    from datr_b200 import native
+    model, _, _ = small
+    model.eval()
+    n0 = native.launch_count()
+    with torch.no_grad():
+        model([i.cuda() for i in mcase.images()])
+    torch.cuda.synchronize()
+    assert native.launch_count() - n0 == 4      # 2 encoder + 2 decoder MSDeformAttn forward launches
+
+
+def test_eval_forward_and_postprocess_match_reference(G, small):
+    model, _, post = small
+    model.eval()
+    with torch.no_grad():
+        out = model([i.cuda() for i in mcase.images()])
+        res = post["bbox"](out, torch.tensor([[h, w] for h, w in mcase.IMAGE_SIZES], dtype=torch.float32, device="cuda"))
+    flat = mcase.flatten(out)
+    for k in [k[5:] for k in G.files if k.startswith("eval.")]:
+        assert rel(flat[k].cpu().numpy(), G["eval." + k]) < REL, k
+    for i, r in enumerate(res):
+        assert np.array_equal(r["labels"].cpu().numpy(), G[f"post[{i}].labels"])
+        assert rel(r["boxes"].cpu().numpy(), G[f"post[{i}].boxes"]) < REL
+
+
+@pytest.mark.parametrize("flag", [False, True])
+def test_train_step_matches_reference(G, small, cpu_noise, flag):
+    model, crit, _ = small
+    tag = "train_st" if flag else "train"
+    model.train(); crit.train()
+    model.global_proto = None
+    torch.manual_seed(7)
+    tg = mcase.targets(device="cuda")
+    out = model([i.cuda() for i in mcase.images()], tg, self_training_flag=flag)
+    losses = crit(out, tg)
+    flat = mcase.flatten(out)
+    skip = tuple(f"{tag}.{s}" for s in ("loss.", "grad_", "total", "global_proto", "Amount", "match["))
+    for k in [k[len(tag) + 1:] for k in G.files if k.startswith(tag + ".") and not k.startswith(skip)]:
+        assert finite_rel(flat[k].detach().cpu().numpy(), G[f"{tag}.{k}"]) < REL, k
+    for k in [k.split(".loss.")[1] for k in G.files if k.startswith(tag + ".loss.")]:
+        want = float(G[f"{tag}.loss.{k}"])
+        assert abs(float(losses[k]) - want) < REL * max(1.0, abs(want)), k
+    total = mcase.total_loss(losses, crit.weight_dict)
+    assert abs(float(total) - float(G[f"{tag}.total"])) < REL * abs(float(G[f"{tag}.total"]))
+    with torch.no_grad():
+        idx = crit.matcher({"pred_logits": out["pred_logits"], "pred_boxes": out["pred_boxes"]}, tg)
+    for i, (a, b) in enumerate(idx):        # assignment: bit-exact
+        assert np.array_equal(a.numpy(), G[f"{tag}.match[{i}].src"]) and np.array_equal(b.numpy(), G[f"{tag}.match[{i}].tgt"])
+    model.zero_grad()
+    total.backward()
+    for k, p in model.named_parameters():
+        key = f"{tag}.grad_sub.{k}"
+        if key in G.files:
+            assert p.grad is not None, k
+            sub = G[key]
+            got = p.grad.reshape(-1)[::101].cpu().numpy()
+            assert np.abs(got - sub).max() / max(np.abs(sub).max(), 1e-6) < 5e-3, k
+        else:
+            assert p.grad is None, k
+    assert np.array_equal(model.Amount.cpu().numpy(), G[f"{tag}.Amount"])
+
+
+def test_module_level_msdeformattn_matches_reference(G, small):
+    from datr_b200.models.dino.deformable_transformer import TransformerEncoder
+    model, _, _ = small
+    model.eval()
+    levels = [(8, 10), (4, 5), (2, 3), (1, 2)]
+    S = sum(h * w for h, w in levels)
+    rng = np.random.default_rng(11)
+    src = torch.from_numpy(rng.standard_normal((2, S, 256)).astype(np.float32)).cuda()
+    pos = torch.from_numpy(rng.standard_normal((2, S, 256)).astype(np.float32)).cuda()
+    shapes = torch.tensor(levels, device="cuda")
+    lstart = torch.cat((shapes.new_zeros(1), shapes.prod(1).cumsum(0)[:-1]))
+    vr = torch.from_numpy(rng.uniform(0.7, 1.0, (2, 4, 2)).astype(np.float32)).cuda()
+    mask = torch.zeros(2, S, dtype=torch.bool, device="cuda"); mask[1, -3:] = True
+    with torch.no_grad():
+        ref2 = TransformerEncoder.get_reference_points(levels, vr, device="cuda")
+        enc0 = model.transformer.encoder.layers[0]
+        assert rel(enc0(src, pos, ref2, shapes, lstart, mask).cpu().numpy(), G["mod.enc_layer"]) < REL
+        assert rel(enc0.self_attn(src + pos, ref2, src, shapes, lstart, mask).cpu().numpy(), G["mod.msda_2d"]) < REL
+        q = torch.from_numpy(rng.standard_normal((2, 7, 256)).astype(np.float32)).cuda()
+        ref4 = torch.from_numpy(rng.uniform(0.1, 0.9, (2, 7, 4, 4)).astype(np.float32)).cuda()
+        got = model.transformer.decoder.layers[0].cross_attn(q, ref4, src, shapes, lstart, mask)
+        assert rel(got.cpu().numpy(), G["mod.msda_4d"]) < REL
