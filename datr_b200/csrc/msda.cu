@@ -11,24 +11,20 @@
 // Design (this file is not a translation of the reference kernels):
 //   * fp32, 32 channels/head (the DINO configuration): eight lanes own one (b,q,m) row, each lane
 //     holds a float4 of channels, so one corner of one sample is a single 128-byte line read by one
-//     quarter-warp, and a warp instruction covers four rows.  Corner addresses are clamped and the
-//     bounds test is folded into the weights, which makes every load unconditional: the P sample
-//     points of a level are issued as one batch of 4*P independent 16-byte loads per lane.
-//   * a CTA owns 32 consecutive queries of ONE head so that neighbouring queries (which sample
-//     neighbouring pixels in the encoder) share L1 lines.
-//   * backward: channel reductions for grad_loc / grad_attn are 8-lane shuffle butterflies (the
-//     reference stages them in shared memory and sums serially on thread 0, cuh:377-393);
-//     grad_value uses 16-byte vector reductions (red.global.add.v4.f32), one per corner per lane,
-//     instead of 4 scalar atomics.
-//   * the P = 4 forward kernel (the DINO configuration; `_p4c` below) additionally removes the
-//     per-lane redundancy of the sample geometry: the 8 lanes of a row split its L*P samples between
-//     them (coalesced loc / attn loads), compute the geometry once and publish it to the other lanes
-//     as 16-byte records in a conflict-free per-warp shared-memory table.  Measured on B200 at the
-//     DINO-4scale encoder shape this halves the issued instructions (158 M -> 82 M warp
-//     instructions) and leaves the kernel bound by L1 line throughput: one 128-byte wavefront per
-//     (row, corner), 22.8 M per call, ~68 % of the l1tex data-pipe peak (profiles/).  For the
-//     backward kernel the same restructuring measured slower (the kernel is bound by L2 vector
-//     reductions: 82.5 M red sectors per call), so it keeps the direct per-lane geometry.
+//     quarter-warp, and a warp instruction covers four rows.  A CTA owns 32 consecutive queries of
+//     ONE head so that neighbouring queries (which sample neighbouring pixels in the encoder) share
+//     L1 lines.
+//   * sample geometry is computed ONCE per sample (the 8 lanes of a row split its L*P samples) and
+//     published to the row's lanes through a conflict-free shared-memory slot table; the 2x2 pixel
+//     block of a sample is anchored so that its four addresses are level-uniform offsets of one
+//     anchor pixel and always in range -- bounds handling lives in the slot weights, every load is
+//     unconditional, and the inner loop is LDS + mad.wide + LDG.128 + FMA only (see the comment
+//     above `place`).  First B200 profile of the previous per-lane-geometry kernels showed both
+//     directions issue-bound (65-72 % issue slots, 40 % of them address arithmetic; profiles/r01a_*).
+//   * backward: channel reductions for grad_loc / grad_attn are 8-lane shuffle butterflies over
+//     three per-lane partial sums (the reference stages them in shared memory and sums serially on
+//     thread 0, cuh:377-393); grad_value uses 16-byte vector reductions (red.global.add.v4.f32),
+//     one per slot per lane, predicated off for empty slots, instead of 4 scalar atomics.
 //   * any other channel count, and fp64, run the generic warp-per-row kernels below.
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -51,7 +47,7 @@ int fail(int code, const char* fmt, const char* detail = "") {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Sample geometry shared by all kernels.
+// Sample geometry of the generic kernels.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 struct Tap {
@@ -79,161 +75,64 @@ __device__ __forceinline__ Tap<T> locate(T locx, T locy, int H, int W) {
   return t;
 }
 
-__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
-
-// ordered (volatile) variant: keeps a batch of loads ahead of the arithmetic that consumes them
-__device__ __forceinline__ float4 ldg4_ordered(const float* p) {
-  float4 r;
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-  return r;
-}
-
-__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
-__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
-  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-}
-
-__device__ __forceinline__ float group8_sum(float v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 4);
-  v += __shfl_xor_sync(0xffffffffu, v, 2);
-  v += __shfl_xor_sync(0xffffffffu, v, 1);
-  return v;
-}
-
-constexpr int kRowsPerCta = 32;  // 256 threads / 8 lanes per row
-
 // ------------------------------------------------------------------------------------------------
-// fp32, D = 32 forward.
+// fp32, D = 32 kernels (the DINO configuration).
+//
+// Work split: a CTA of 256 threads owns 32 consecutive queries of ONE head; eight lanes own one
+// (b,q,m) row and each lane holds a float4 of its 32 channels, so a corner of a sample is one
+// 128-byte line read by a quarter-warp.
+//
+// Stage 1 (per warp, once per row): the 8 lanes of a row split its L*P samples, load loc / attn
+// coalesced, and turn each sample into a SLOT record in a per-warp shared-memory table:
+//   the 2x2 pixel block is anchored at (by,bx) = clamp((y0,x0), 0, size-2), so its four pixels sit
+//   at the level-uniform offsets {0, 1, W, W+1} (or 0 where a level is one pixel wide/high) and are
+//   always inside the level -- every load is unconditional and needs ONE mad.wide per corner;
+//   what would have been bounds tests becomes the weight of each slot: slot i of an axis carries
+//   weight h (=1-l, d/dcoord = -1), weight l (d/dcoord = +1) or nothing, depending on which of the
+//   sample's two corners landed on it (cuh:56-79 bounds rules, :288 sample guard).
+// Stage 2: every lane walks the table: 1-3 LDS.128, 4 mad.wide, 4 LDG.128 (+4 predicated
+//   RED.128 in backward) per sample, and pure FMAs.
 // ------------------------------------------------------------------------------------------------
-template <int kP>
-__global__ void __launch_bounds__(256)
-msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
-                 const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                 const float* __restrict__ attn, int N, int S, int M, int L, int Lq,
-                 float* __restrict__ out) {
-  const int sub = threadIdx.x & 7;
-  const int m = blockIdx.x % M;
-  const long long bq = (long long)(blockIdx.x / M) * kRowsPerCta + (threadIdx.x >> 3);
-  if (bq >= (long long)N * Lq) return;
-  const int b = int(bq / Lq);
-  const long long row = bq * M + m;
-  const int rs = M * 32;  // floats between consecutive pixels
-  const float* vb = value + (long long)b * S * rs + m * 32 + sub * 4;
-  const float* lp = loc + row * L * kP * 2;
-  const float* ap = attn + row * L * kP;
-
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int l = 0; l < L; ++l) {
-    const int H = int(__ldg(shapes + 2 * l)), W = int(__ldg(shapes + 2 * l + 1));
-    const float* vl = vb + (long long)__ldg(lstart + l) * rs;
-    float4 v[kP][4];
-    float w[kP][4];
-#pragma unroll
-    for (int p = 0; p < kP; ++p) {
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + l * kP + p);
-      const float a = __ldg(ap + l * kP + p);
-      const Tap<float> t = locate<float>(xy.x, xy.y, H, W);
-      const float wy0 = t.hy * a, wy1 = t.ly * a;
-      w[p][0] = t.in[0] ? wy0 * t.hx : 0.f;
-      w[p][1] = t.in[1] ? wy0 * t.lx : 0.f;
-      w[p][2] = t.in[2] ? wy1 * t.hx : 0.f;
-      w[p][3] = t.in[3] ? wy1 * t.lx : 0.f;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) v[p][i] = ldg4(vl + (long long)t.o[i] * rs);
-    }
-#pragma unroll
-    for (int p = 0; p < kP; ++p)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        acc.x = fmaf(w[p][i], v[p][i].x, acc.x);
-        acc.y = fmaf(w[p][i], v[p][i].y, acc.y);
-        acc.z = fmaf(w[p][i], v[p][i].z, acc.z);
-        acc.w = fmaf(w[p][i], v[p][i].w, acc.w);
-      }
-  }
-  *reinterpret_cast<float4*>(out + row * 32 + sub * 4) = acc;
-}
-
-// ------------------------------------------------------------------------------------------------
-// fp32, D = 32 backward.
-// ------------------------------------------------------------------------------------------------
-template <int kP>
-__global__ void __launch_bounds__(256)
-msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
-                 const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                 const float* __restrict__ attn, const float* __restrict__ grad_out,
-                 int N, int S, int M, int L, int Lq,
-                 float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
-  const int sub = threadIdx.x & 7;
-  const int m = blockIdx.x % M;
-  long long bq = (long long)(blockIdx.x / M) * kRowsPerCta + (threadIdx.x >> 3);
-  // keep whole warps alive for the shuffles: out-of-range rows redo the last row and skip all writes
-  const bool live = bq < (long long)N * Lq;
-  if (!live) bq = (long long)N * Lq - 1;
-  const int b = int(bq / Lq);
-  const long long row = bq * M + m;
-  const int rs = M * 32;
-  const long long voff = (long long)b * S * rs + m * 32 + sub * 4;
-  const float* vb = value + voff;
-  float* gvb = grad_value + voff;
-  const float* lp = loc + row * L * kP * 2;
-  const float* ap = attn + row * L * kP;
-  const float4 g = ldg4(grad_out + row * 32 + sub * 4);
-
-  for (int l = 0; l < L; ++l) {
-    const int H = int(__ldg(shapes + 2 * l)), W = int(__ldg(shapes + 2 * l + 1));
-    const long long lo = (long long)__ldg(lstart + l) * rs;
-    const float* vl = vb + lo;
-    float* gvl = gvb + lo;
-    float keep_a = 0.f, keep_x = 0.f, keep_y = 0.f;  // lane `p` keeps the results of sample p
-#pragma unroll
-    for (int p = 0; p < kP; ++p) {
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(lp) + l * kP + p);
-      const float a = __ldg(ap + l * kP + p);
-      const Tap<float> t = locate<float>(xy.x, xy.y, H, W);
-      float4 v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        v[i] = ldg4(vl + (long long)t.o[i] * rs);
-        if (!t.in[i]) v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      const float4 tv = make_float4(g.x * a, g.y * a, g.z * a, g.w * a);
-      const float cw[4] = {t.hy * t.hx, t.hy * t.lx, t.ly * t.hx, t.ly * t.lx};
-      if (live) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (t.in[i]) red_add4(gvl + (long long)t.o[i] * rs, cw[i] * tv.x, cw[i] * tv.y, cw[i] * tv.z, cw[i] * tv.w);
-      }
-      float4 val, dy, dx;
-#define DATR_MIX(c)                                                                  \
-  val.c = cw[0] * v[0].c + cw[1] * v[1].c + cw[2] * v[2].c + cw[3] * v[3].c;         \
-  dy.c = t.hx * (v[2].c - v[0].c) + t.lx * (v[3].c - v[1].c);                        \
-  dx.c = t.hy * (v[1].c - v[0].c) + t.ly * (v[3].c - v[2].c);
-      DATR_MIX(x) DATR_MIX(y) DATR_MIX(z) DATR_MIX(w)
-#undef DATR_MIX
-      const float pa = group8_sum(dot4(g, val));
-      const float px = group8_sum(dot4(tv, dx)) * float(W);
-      const float py = group8_sum(dot4(tv, dy)) * float(H);
-      if (sub == p) { keep_a = pa; keep_x = px; keep_y = py; }
-    }
-    if (live && sub < kP) {
-      grad_attn[row * L * kP + l * kP + sub] = keep_a;
-      reinterpret_cast<float2*>(grad_loc)[row * L * kP + l * kP + sub] = make_float2(keep_x, keep_y);
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// fp32, D = 32, P = 4 forward: the 8 lanes of a row split its L*P samples between them, compute the
-// sample geometry once and publish it through a per-warp shared-memory table (a chunk = 16 samples
-// = 4 levels).
-// ------------------------------------------------------------------------------------------------
-constexpr int kChunk = 16;                    // samples per chunk
-
 struct LevelGeom { int H, W, start; };
+constexpr int kMaxLevels = 32;
+constexpr int kRowsPerCta = 32;  // 256 threads / 8 lanes per row
+constexpr int kMaxTaps = 32;     // L*P limit of the fast path
+
+struct Slots {
+  int pix;                  // pixel index (level start included) of the anchor (by,bx)
+  float a;                  // attention weight (0 if the sample is rejected)
+  float wy0, wy1, wx0, wx1; // interpolation weight carried by each slot (0 = slot unused)
+  float sy0, sy1, sx0, sx1; // d(weight)/d(coordinate) of each slot: -1, +1 or 0
+};
+
+__device__ __forceinline__ Slots place(float locx, float locy, float a, const LevelGeom& g) {
+  const int H = g.H, W = g.W;
+  const float y = locy * float(H) - 0.5f;
+  const float x = locx * float(W) - 0.5f;
+  const bool ok = (y > -1.f) && (x > -1.f) && (y < float(H)) && (x < float(W));  // cuh:288; false for NaN
+  const float yf = floorf(y), xf = floorf(x);
+  const int y0 = ok ? int(yf) : 0, x0 = ok ? int(xf) : 0;
+  const float ly = y - yf, lx = x - xf, hy = 1.f - ly, hx = 1.f - lx;
+  const int by = min(max(y0, 0), max(H - 2, 0)), bx = min(max(x0, 0), max(W - 2, 0));
+  Slots s;
+  s.pix = g.start + by * W + bx;
+  s.a = ok ? a : 0.f;
+  const bool y_on0 = ok && y0 == by, y1_on0 = ok && y0 + 1 == by;          // slot 0 = row by
+  s.wy0 = y_on0 ? hy : (y1_on0 ? ly : 0.f);
+  s.sy0 = y_on0 ? -1.f : (y1_on0 ? 1.f : 0.f);
+  const bool row1 = ok && H >= 2;                                          // slot 1 = row by+1
+  const bool y1_on1 = row1 && y0 == by, y_on1 = row1 && y0 == by + 1;
+  s.wy1 = y1_on1 ? ly : (y_on1 ? hy : 0.f);
+  s.sy1 = y1_on1 ? 1.f : (y_on1 ? -1.f : 0.f);
+  const bool x_on0 = ok && x0 == bx, x1_on0 = ok && x0 + 1 == bx;
+  s.wx0 = x_on0 ? hx : (x1_on0 ? lx : 0.f);
+  s.sx0 = x_on0 ? -1.f : (x1_on0 ? 1.f : 0.f);
+  const bool col1 = ok && W >= 2;
+  const bool x1_on1 = col1 && x0 == bx, x_on1 = col1 && x0 == bx + 1;
+  s.wx1 = x1_on1 ? lx : (x_on1 ? hx : 0.f);
+  s.sx1 = x1_on1 ? 1.f : (x_on1 ? -1.f : 0.f);
+  return s;
+}
 
 __device__ __forceinline__ void load_levels(LevelGeom* sh, const int64_t* __restrict__ shapes,
                                             const int64_t* __restrict__ lstart, int L) {
@@ -245,101 +144,224 @@ __device__ __forceinline__ void load_levels(LevelGeom* sh, const int64_t* __rest
   __syncthreads();
 }
 
-constexpr int kMaxLevels = 32;
-
-// ------------------------------------------------------------------------------------------------
-// Compact geometry table (16 bytes per sample): {pixel index | flags << 26, lx, ly, attn}.
-// flags: bits 0-3 corner (y0x0, y0x1, y1x0, y1x1) contributes; bit 4: x1 is a distinct pixel
-// (x1c = x0c + 1); bit 5: y1 is a distinct row.  Lane `sub` prepares samples sub and sub + 8 of the
-// chunk, so the table writes are conflict-free; rows of a warp are 17 slots apart (bank offset 4).
-// ------------------------------------------------------------------------------------------------
-constexpr int kCRow = kChunk + 1;
-
-__device__ __forceinline__ uint4 pack_tap(float locx, float locy, float a, const LevelGeom& g, bool live) {
-  const Tap<float> t = locate<float>(locx, locy, g.H, g.W);
-  unsigned flags = (t.in[0] ? 1u : 0u) | (t.in[1] ? 2u : 0u) | (t.in[2] ? 4u : 0u) | (t.in[3] ? 8u : 0u);
-  if (!live) flags = 0u;
-  flags |= (t.o[1] != t.o[0]) ? 16u : 0u;
-  flags |= (t.o[2] != t.o[0]) ? 32u : 0u;
-  uint4 q;
-  q.x = unsigned(g.start + t.o[0]) | (flags << 26);
-  q.y = __float_as_uint(t.lx); q.z = __float_as_uint(t.ly); q.w = __float_as_uint(a);
-  return q;
+// base + pix * stride_bytes in one IMAD.WIDE (volatile: keeps ptxas from splitting it into a shared
+// product plus a 64-bit add per corner, which doubles the address instructions of the inner loop)
+__device__ __forceinline__ const float* pixel_ptr(const float* base, int pix, int stride_bytes) {
+  unsigned long long r;
+  asm volatile("mad.wide.s32 %0, %1, %2, %3;" : "=l"(r) : "r"(pix), "r"(stride_bytes), "l"(base));
+  return reinterpret_cast<const float*>(r);
 }
 
-template <int kBatch>
+// ordered (volatile) 16-byte read-only load: keeps a batch of loads ahead of the arithmetic
+__device__ __forceinline__ float4 ldg4_ordered(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// 16-byte vector reduction, skipped when the slot weight is zero
+__device__ __forceinline__ void red_add4_if(const float* p, float w, const float4& g) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.neu.f32 q, %5, 0f00000000;\n\t"
+      "@q red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+      ::"l"(p), "f"(w * g.x), "f"(w * g.y), "f"(w * g.z), "f"(w * g.w), "f"(w) : "memory");
+}
+
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+// row stride (in 16-byte records) of the slot tables: 4 rows of a warp read 4 different records per
+// LDS.128; they fall on disjoint bank groups iff stride mod 8 is not 0 or 4.
+__host__ __device__ inline int table_stride(int taps) {
+  int s = taps + 1;
+  if ((s & 3) == 0) ++s;
+  return s;
+}
+__host__ __device__ inline int pix_stride(int taps) { return taps | 1; }
+
+constexpr int kGeomBytes = 512;  // kMaxLevels * sizeof(LevelGeom) rounded up
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+template <int kP, int kBatch>
 __global__ void __launch_bounds__(256)
-msda_fwd_f32_d32_p4c(const float* __restrict__ value, const int64_t* __restrict__ shapes,
-                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                     const float* __restrict__ attn, int N, int S, int M, int L, int Lq,
-                     float* __restrict__ out) {
-  __shared__ __align__(16) uint4 taps[8][4][kCRow];
-  __shared__ LevelGeom geom[kMaxLevels];
+msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                 const int64_t* __restrict__ lstart, const float* __restrict__ loc,
+                 const float* __restrict__ attn, int N, int S, int M, int L, int Lq,
+                 float* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  LevelGeom* geom = reinterpret_cast<LevelGeom*>(smem);
+  const int LP = L * kP, ws = table_stride(LP), ps = pix_stride(LP);
+  uint4* wtab = reinterpret_cast<uint4*>(smem + kGeomBytes);            // [32][ws] {w00,w01,w10,w11} * attn
+  int* ptab = reinterpret_cast<int*>(wtab + kRowsPerCta * ws);          // [32][ps] anchor pixel
   load_levels(geom, shapes, lstart, L);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 3, sub = lane & 7;
+  const int r = threadIdx.x >> 3, sub = threadIdx.x & 7;
   const int m = blockIdx.x % M;
-  long long bq = (long long)(blockIdx.x / M) * kRowsPerCta + warp * 4 + r;
+  long long bq = (long long)(blockIdx.x / M) * kRowsPerCta + r;
   const bool live = bq < (long long)N * Lq;
   if (!live) bq = (long long)N * Lq - 1;
   const int b = int(bq / Lq);
   const long long row = bq * M + m;
-  const int rs = M * 32;
-  const int LP = L * 4;
-  const float* vb = value + (long long)b * S * rs + m * 32 + sub * 4;
-  uint4* mytaps = &taps[warp][r][0];
+  const int rs4 = M * 32 * 4;  // bytes between consecutive pixels
+  const float* vb = value + (long long)b * S * (M * 32) + m * 32 + sub * 4;
+  uint4* myw = wtab + r * ws;
+  int* myp = ptab + r * ps;
+
+  for (int s = sub; s < LP; s += 8) {
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
+    const float a = __ldg(attn + row * LP + s);
+    const Slots t = place(xy.x, xy.y, a, geom[s / kP]);
+    const float ay0 = t.wy0 * t.a, ay1 = t.wy1 * t.a;
+    myw[s] = make_uint4(__float_as_uint(ay0 * t.wx0), __float_as_uint(ay0 * t.wx1),
+                        __float_as_uint(ay1 * t.wx0), __float_as_uint(ay1 * t.wx1));
+    myp[s] = t.pix;
+  }
+  __syncwarp();
 
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int s0 = 0; s0 < LP; s0 += kChunk) {
+  for (int l = 0; l < L; ++l) {
+    const int W = geom[l].W, H = geom[l].H;
+    const int d01 = W >= 2 ? rs4 : 0;
+    const long long d10 = H >= 2 ? (long long)W * rs4 : 0;
+    const float* vb01 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vb) + d01);
+    const float* vb10 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vb) + d10);
+    const float* vb11 = reinterpret_cast<const float*>(reinterpret_cast<const char*>(vb10) + d01);
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int s = s0 + sub + 8 * k;
-      if (s < LP) {
-        const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
-        const float a = __ldg(attn + row * LP + s);
-        mytaps[sub + 8 * k] = pack_tap(xy.x, xy.y, a, geom[s >> 2], true);
+    for (int p0 = 0; p0 < kP; p0 += kBatch) {
+      float4 v[kBatch][4];
+      uint4 w[kBatch];
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int s = l * kP + p0 + j;
+        const int pix = myp[s];
+        w[j] = myw[s];
+        v[j][0] = ldg4_ordered(pixel_ptr(vb, pix, rs4));
+        v[j][1] = ldg4_ordered(pixel_ptr(vb01, pix, rs4));
+        v[j][2] = ldg4_ordered(pixel_ptr(vb10, pix, rs4));
+        v[j][3] = ldg4_ordered(pixel_ptr(vb11, pix, rs4));
       }
-    }
-    __syncwarp();
-    const int n = min(kChunk, LP - s0);
-    for (int j0 = 0; j0 < n; j0 += 4) {
-      const int W = geom[(s0 + j0) >> 2].W;
 #pragma unroll
-      for (int jb = 0; jb < 4; jb += kBatch) {
-        float4 v[kBatch][4];
-        float w[kBatch][4];
+      for (int j = 0; j < kBatch; ++j) {
+        const float wj[4] = {__uint_as_float(w[j].x), __uint_as_float(w[j].y), __uint_as_float(w[j].z),
+                             __uint_as_float(w[j].w)};
 #pragma unroll
-        for (int j = 0; j < kBatch; ++j) {
-          const uint4 q = mytaps[j0 + jb + j];
-          const unsigned flags = q.x >> 26;
-          const int base = int(q.x & 0x03ffffffu);
-          const int dx = (flags >> 4) & 1, dy = (flags & 32u) ? W : 0;
-          const float lx = __uint_as_float(q.y), ly = __uint_as_float(q.z), a = __uint_as_float(q.w);
-          const float wy0 = (1.f - ly) * a, wy1 = ly * a, hx = 1.f - lx;
-          w[j][0] = (flags & 1u) ? wy0 * hx : 0.f;
-          w[j][1] = (flags & 2u) ? wy0 * lx : 0.f;
-          w[j][2] = (flags & 4u) ? wy1 * hx : 0.f;
-          w[j][3] = (flags & 8u) ? wy1 * lx : 0.f;
-          const float* p00 = vb + (long long)base * rs;
-          v[j][0] = ldg4_ordered(p00);
-          v[j][1] = ldg4_ordered(p00 + dx * rs);
-          v[j][2] = ldg4_ordered(p00 + (long long)dy * rs);
-          v[j][3] = ldg4_ordered(p00 + (long long)(dy + dx) * rs);
+        for (int i = 0; i < 4; ++i) {
+          acc.x = fmaf(wj[i], v[j][i].x, acc.x);
+          acc.y = fmaf(wj[i], v[j][i].y, acc.y);
+          acc.z = fmaf(wj[i], v[j][i].z, acc.z);
+          acc.w = fmaf(wj[i], v[j][i].w, acc.w);
         }
-#pragma unroll
-        for (int j = 0; j < kBatch; ++j)
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc.x = fmaf(w[j][i], v[j][i].x, acc.x);
-            acc.y = fmaf(w[j][i], v[j][i].y, acc.y);
-            acc.z = fmaf(w[j][i], v[j][i].z, acc.z);
-            acc.w = fmaf(w[j][i], v[j][i].w, acc.w);
-          }
       }
     }
-    __syncwarp();
   }
   if (live) *reinterpret_cast<float4*>(out + row * 32 + sub * 4) = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------
+template <int kP>
+__global__ void __launch_bounds__(256, 4)
+msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+                 const int64_t* __restrict__ lstart, const float* __restrict__ loc,
+                 const float* __restrict__ attn, const float* __restrict__ grad_out,
+                 int N, int S, int M, int L, int Lq,
+                 float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  LevelGeom* geom = reinterpret_cast<LevelGeom*>(smem);
+  const int LP = L * kP, ws = table_stride(LP);
+  uint4* tab0 = reinterpret_cast<uint4*>(smem + kGeomBytes);   // [32][ws] {pix, a, a*W, a*H}
+  uint4* tab1 = tab0 + kRowsPerCta * ws;                       // {wy0, wy1, wx0, wx1}
+  uint4* tab2 = tab1 + kRowsPerCta * ws;                       // {sy0, sy1, sx0, sx1}
+  load_levels(geom, shapes, lstart, L);
+
+  const int r = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  const int m = blockIdx.x % M;
+  long long bq = (long long)(blockIdx.x / M) * kRowsPerCta + r;
+  // keep whole warps alive for the shuffles: out-of-range rows redo the last row and skip all writes
+  const bool live = bq < (long long)N * Lq;
+  if (!live) bq = (long long)N * Lq - 1;
+  const int b = int(bq / Lq);
+  const long long row = bq * M + m;
+  const int rs4 = M * 32 * 4;
+  const long long voff = (long long)b * S * (M * 32) + m * 32 + sub * 4;
+  const float* vb = value + voff;
+  const float* gb = grad_value + voff;
+  uint4* my0 = tab0 + r * ws;
+  uint4* my1 = tab1 + r * ws;
+  uint4* my2 = tab2 + r * ws;
+
+  for (int s = sub; s < LP; s += 8) {
+    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
+    const float a = __ldg(attn + row * LP + s);
+    const LevelGeom g = geom[s / kP];
+    const Slots t = place(xy.x, xy.y, a, g);
+    const float al = live ? t.a : 0.f;  // dead rows scatter nothing
+    my0[s] = make_uint4(unsigned(t.pix), __float_as_uint(al), __float_as_uint(t.a * float(g.W)),
+                        __float_as_uint(t.a * float(g.H)));
+    my1[s] = make_uint4(__float_as_uint(t.wy0), __float_as_uint(t.wy1), __float_as_uint(t.wx0), __float_as_uint(t.wx1));
+    my2[s] = make_uint4(__float_as_uint(t.sy0), __float_as_uint(t.sy1), __float_as_uint(t.sx0), __float_as_uint(t.sx1));
+  }
+  const float4 g = ldg4(grad_out + row * 32 + sub * 4);
+  __syncwarp();
+
+  float keep_a = 0.f, keep_x = 0.f, keep_y = 0.f;  // lane (s & 7) keeps the results of sample s
+  for (int l = 0; l < L; ++l) {
+    const int W = geom[l].W, H = geom[l].H;
+    const int d01 = W >= 2 ? rs4 : 0;
+    const long long d10 = H >= 2 ? (long long)W * rs4 : 0;
+    const long long d11 = d10 + d01;
+#pragma unroll
+    for (int p = 0; p < kP; ++p) {
+      const int s = l * kP + p;
+      const uint4 q0 = my0[s], q1 = my1[s], q2 = my2[s];
+      const int pix = int(q0.x);
+      const float a = __uint_as_float(q0.y);
+      const float wy0 = __uint_as_float(q1.x), wy1 = __uint_as_float(q1.y);
+      const float wx0 = __uint_as_float(q1.z), wx1 = __uint_as_float(q1.w);
+      const float* p00 = pixel_ptr(vb, pix, rs4);
+      const float4 v00 = ldg4_ordered(p00);
+      const float4 v01 = ldg4_ordered(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p00) + d01));
+      const float4 v10 = ldg4_ordered(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p00) + d10));
+      const float4 v11 = ldg4_ordered(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p00) + d11));
+      // grad_value: slot weight * attn * grad_out, one 16-byte reduction per slot (skipped if weight 0)
+      const float* g00 = pixel_ptr(gb, pix, rs4);
+      const float ay0 = wy0 * a, ay1 = wy1 * a;
+      red_add4_if(g00, ay0 * wx0, g);
+      red_add4_if(reinterpret_cast<const float*>(reinterpret_cast<const char*>(g00) + d01), ay0 * wx1, g);
+      red_add4_if(reinterpret_cast<const float*>(reinterpret_cast<const char*>(g00) + d10), ay1 * wx0, g);
+      red_add4_if(reinterpret_cast<const float*>(reinterpret_cast<const char*>(g00) + d11), ay1 * wx1, g);
+      // <grad_out, slot value> over this lane's 4 channels
+      const float e00 = dot4(g, v00), e01 = dot4(g, v01), e10 = dot4(g, v10), e11 = dot4(g, v11);
+      const float r0 = fmaf(wx1, e01, wx0 * e00), r1 = fmaf(wx1, e11, wx0 * e10);       // interpolate along x
+      const float sx0 = __uint_as_float(q2.z), sx1 = __uint_as_float(q2.w);
+      const float t0 = fmaf(sx1, e01, sx0 * e00), t1 = fmaf(sx1, e11, sx0 * e10);       // differentiate along x
+      float pa = fmaf(wy1, r1, wy0 * r0);                                                // cuh:156
+      float px = fmaf(wy1, t1, wy0 * t0);                                                // cuh:157 (x)
+      float py = fmaf(__uint_as_float(q2.y), r1, __uint_as_float(q2.x) * r0);            // cuh:158 (y)
+      pa = group8_sum(pa); px = group8_sum(px); py = group8_sum(py);
+      if (sub == (s & 7)) { keep_a = pa; keep_x = px * __uint_as_float(q0.z); keep_y = py * __uint_as_float(q0.w); }
+      if ((s & 7) == 7 || s == LP - 1) {
+        const int s0 = s & ~7;
+        if (live && s0 + sub <= s) {
+          grad_attn[row * LP + s0 + sub] = keep_a;
+          reinterpret_cast<float2*>(grad_loc)[row * LP + s0 + sub] = make_float2(keep_x, keep_y);
+        }
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -461,9 +483,26 @@ int after_launch(const char* what) {
   return DATR_OK;
 }
 
-bool fast_ok(int D, int P, int dtype, const void* a, const void* b, const void* c, const void* d) {
-  return dtype == DATR_DTYPE_F32 && D == 32 && (P == 4 || P == 1 || P == 2 || P == 8) && aligned(a, 16) &&
-         aligned(b, 16) && aligned(c, 8) && aligned(d, 16);
+bool fast_ok(int D, int P, int L, int dtype, const void* a, const void* b, const void* c, const void* d) {
+  return dtype == DATR_DTYPE_F32 && D == 32 && (P == 4 || P == 1 || P == 2 || P == 8) && L <= kMaxLevels &&
+         L * P <= kMaxTaps && aligned(a, 16) && aligned(b, 16) && aligned(c, 8) && aligned(d, 16);
+}
+
+// The backward slot tables of L*P = 32 taps need 51 KB of dynamic shared memory: opt in once per device.
+int allow_big_smem() {
+  static std::atomic<uint64_t> done{0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaGetDevice failed%s");
+  const uint64_t bit = 1ull << (dev & 63);
+  if (done.load(std::memory_order_acquire) & bit) return DATR_OK;
+  const int bytes = 64 * 1024;
+  cudaError_t e = cudaSuccess;
+#define DATR_OPT(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+  DATR_OPT(msda_bwd_f32_d32<1>); DATR_OPT(msda_bwd_f32_d32<2>); DATR_OPT(msda_bwd_f32_d32<4>); DATR_OPT(msda_bwd_f32_d32<8>);
+#undef DATR_OPT
+  if (e != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  done.fetch_or(bit, std::memory_order_release);
+  return DATR_OK;
 }
 
 }  // namespace
@@ -477,23 +516,22 @@ int datr_msda_forward(const void* value, const int64_t* shapes, const int64_t* l
   if (!out) return fail(DATR_ERR_BAD_ARGUMENT, "null output pointer%s");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long rows = (long long)N * Lq * M;
-  if (fast_ok(D, P, dtype, value, out, loc, attn)) {
+  if (fast_ok(D, P, L, dtype, value, out, loc, attn)) {
     const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
     if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
     const float* v = static_cast<const float*>(value);
     const float* lc = static_cast<const float*>(loc);
     const float* at = static_cast<const float*>(attn);
     float* o = static_cast<float*>(out);
-#define DATR_FWD(PP) msda_fwd_f32_d32<PP><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o)
-    if (P == 4 && L <= kMaxLevels && (long long)S < (1LL << 26)) {
-      msda_fwd_f32_d32_p4c<2><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o);
-      return after_launch("msda_fwd_f32_d32_p4c");
-    }
+    const int LP = L * P;
+    const size_t smem = kGeomBytes + (size_t)kRowsPerCta * (table_stride(LP) * 16 + pix_stride(LP) * 4);
+#define DATR_FWD(PP, BB) \
+  msda_fwd_f32_d32<PP, BB><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o)
     switch (P) {
-      case 1: DATR_FWD(1); break;
-      case 2: DATR_FWD(2); break;
-      case 4: DATR_FWD(4); break;
-      default: DATR_FWD(8); break;
+      case 1: DATR_FWD(1, 1); break;
+      case 2: DATR_FWD(2, 2); break;
+      case 4: DATR_FWD(4, 2); break;
+      default: DATR_FWD(8, 2); break;
     }
 #undef DATR_FWD
     return after_launch("msda_fwd_f32_d32");
@@ -521,7 +559,7 @@ int datr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
   const cudaError_t me = cudaMemsetAsync(grad_value, 0, es * (size_t)N * S * M * D, stream);
   if (me != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaMemsetAsync(grad_value): %s", cudaGetErrorString(me));
   const long long rows = (long long)N * Lq * M;
-  if (fast_ok(D, P, dtype, value, grad_out, grad_loc, grad_attn) && aligned(grad_value, 16) && aligned(loc, 8) &&
+  if (fast_ok(D, P, L, dtype, value, grad_out, grad_loc, grad_attn) && aligned(grad_value, 16) && aligned(loc, 8) &&
       aligned(attn, 4)) {
     const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
     if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
@@ -532,8 +570,10 @@ int datr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
     float* gv = static_cast<float*>(grad_value);
     float* gl = static_cast<float*>(grad_loc);
     float* ga = static_cast<float*>(grad_attn);
+    const size_t smem = kGeomBytes + (size_t)kRowsPerCta * table_stride(L * P) * 48;
 #define DATR_BWD(PP) \
-  msda_bwd_f32_d32<PP><<<(unsigned)ctas, 256, 0, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga)
+  msda_bwd_f32_d32<PP><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga)
+    if (int rc = allow_big_smem()) return rc;
     switch (P) {
       case 1: DATR_BWD(1); break;
       case 2: DATR_BWD(2); break;
