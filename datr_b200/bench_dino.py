@@ -40,6 +40,11 @@ class DinoStep:
     def __init__(self, device, rank=0, world=1, batch_size=2, height=H_IMG, width=W_IMG, **over):
         from datr_b200.models.dino.dino import build_dino
         self.device, self.rank, self.world = device, rank, world
+        # dense contractions run on the tensor cores with TF32 operands / fp32 accumulation (10-bit mantissa, above the
+        # bf16 floor BASELINE.json allows); DATR_MATMUL=fp32 restores SIMT fp32 GEMMs (what the parity tests use)
+        self.matmul = os.environ.get("DATR_MATMUL", "tf32")
+        torch.backends.cuda.matmul.allow_tf32 = self.matmul == "tf32"
+        torch.backends.cudnn.allow_tf32 = True
         torch.manual_seed(42)                                   # identical initial weights on every rank
         args = dino_args(device=str(device), **over)
         self.args = args

@@ -1,0 +1,45 @@
+/*
+ * datr_linear.h -- C ABI of the tensor-core linear layer of libdatr_b200.so (sm_100a: TMA + tcgen05 + TMEM).
+ *
+ *   datr_linear_tf32  <-  every nn.Linear on the DINO transformer hot path, i.e. torch.nn.functional.linear as
+ *                         called from the reference's models/dino/ops/modules/ms_deform_attn.py:94-125
+ *                         (value_proj, sampling_offsets, attention_weights, output_proj) and
+ *                         models/dino/deformable_transformer.py:784-805, :941-947 (linear1 + activation, linear2),
+ *                         with the bias add, the ReLU and the residual add that follow it fused into the epilogue.
+ *
+ *   y[M,N] = act( x[M,K] . w[N,K]^T + bias[N] ) + residual[M,N]
+ *
+ * All buffers are fp32 device memory, row-major, contiguous, 16-byte aligned, owned by the caller; `bias` and
+ * `residual` may be NULL; relu != 0 applies max(.,0) before the residual add.  Requirements: K % 32 == 0, N % 4 == 0.
+ * Products are TF32 (10-bit mantissa, round-to-nearest on the TMA load), accumulation is fp32.  Work is enqueued on
+ * `stream` (cudaStream_t as void*), no host synchronisation.  Returns 0 or a negative code;
+ * datr_linear_last_error() gives the calling thread's message.  There is no CPU implementation.
+ */
+#ifndef DATR_LINEAR_H_
+#define DATR_LINEAR_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  DATR_LINEAR_OK = 0,
+  DATR_LINEAR_ERR_BAD_ARGUMENT = -1,
+  DATR_LINEAR_ERR_ALIGNMENT = -2,
+  DATR_LINEAR_ERR_CUDA = -3
+};
+
+int datr_linear_tf32(const float* x, const float* w, const float* bias, const float* residual, float* y,
+                     int M, int N, int K, int relu, void* stream);
+
+const char* datr_linear_last_error(void);
+
+/* Number of tensor-core linear kernels launched by this process (bench accounting). */
+uint64_t datr_linear_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DATR_LINEAR_H_ */
