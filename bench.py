@@ -41,6 +41,9 @@ IMAGES_PER_STEP_PER_GPU = 4        # batch_size 2 -> 2 source + 2 target images 
 MSDA_WORKLOAD = ("MSDeformAttn calls of one DINO-4scale DA training step, 1333x800, batch_size 2/GPU: "
                  "12 encoder (N=2,Lq=S=22223) + 6 decoder Lq=1100 + 6 decoder Lq=900, forward+backward, fp32")
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the config-2/3 encoder call, from the committed
+# `ncu --set full` capture (profiles/r01b_msda_ncu_full.txt)
+TRAFFIC_NCU = {"msda_fwd_f32_d32": 142.6e6, "msda_bwd_f32_d32": 340.9e6}
 
 
 def hbm_peak():
@@ -209,24 +212,36 @@ class MsdaStep:
         return h2d, d2h
 
     def roofline(self, timers, peak, peak_src):
-        """Dominant kernel = the one with the largest share of the timed region; achieved = algorithmic
-        bytes of its launches / their event-timed duration."""
+        """Dominant kernel = the hand-written kernel group with the largest share of the event-timed launches;
+        achieved = algorithmic bytes of its launches / their event-timed duration.  MSDeformAttn groups by
+        direction and encoder/decoder; the tcgen05 linear kernel groups by (N, K) and also reports TFLOP/s."""
         groups = {}
         for kind, key, e0, e1 in timers:
+            dt = e0.elapsed_time(e1) * 1e-3
+            if kind == "linear":
+                M, N, K, res = key
+                name = f"linear_tf32 N={N} K={K}" + ("+res" if res else "")
+                g = groups.setdefault(name, [0.0, 0, 0, 0.0])
+                g[0] += dt; g[1] += 4 * (M * K + N * K + M * N * (2 if res else 1)); g[2] += 1; g[3] += 2.0 * M * N * K
+                continue
             N, S, M, D, L, Lq, P, es = key
             name = f"msda_{kind}_f32_d32<{P}> " + ("encoder" if Lq == S else "decoder")
             fb, bb = msda_algo_bytes(N, S, M, D, L, Lq, P, es)
-            g = groups.setdefault(name, [0.0, 0, 0])
-            g[0] += e0.elapsed_time(e1) * 1e-3; g[1] += fb if kind == "fwd" else bb; g[2] += 1
+            g = groups.setdefault(name, [0.0, 0, 0, 0.0])
+            g[0] += dt; g[1] += fb if kind == "fwd" else bb; g[2] += 1
         total = sum(g[0] for g in groups.values())
         top = max(groups, key=lambda k: groups[k][0])
-        t, b, n = groups[top]
-        per_kernel = {k: {"launches": v[2], "avg_us": v[0] / v[2] * 1e6, "gbs": v[1] / v[0] / 1e9,
-                          "frac": v[1] / v[0] / 1e9 / peak, "share": v[0] / total} for k, v in groups.items()}
+        t, b, n, _ = groups[top]
+        per_kernel = {}
+        for k, v in groups.items():
+            per_kernel[k] = {"launches": v[2], "avg_us": v[0] / v[2] * 1e6, "gbs": v[1] / v[0] / 1e9,
+                             "frac": v[1] / v[0] / 1e9 / peak, "share": v[0] / total}
+            if v[3]:
+                per_kernel[k]["tflops"] = v[3] / v[0] / 1e12
         return {"bound": "hbm", "kernel": top, "achieved": b / t / 1e9, "peak": peak, "peak_source": peak_src,
-                "unit": "GB/s", "frac": b / t / 1e9 / peak, "traffic": None,
+                "unit": "GB/s", "frac": b / t / 1e9 / peak, "traffic": TRAFFIC_NCU.get(top.split("<")[0]),
                 "algorithmic_bytes_per_launch": b / n, "avg_launch_us": t / n * 1e6, "share_of_step": t / total,
-                "per_kernel": per_kernel}
+                "handwritten_kernel_ms_per_step": None, "per_kernel": per_kernel}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -330,8 +345,9 @@ def main():
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    MSDA._timers = []
-    n0 = native.launch_count()
+    from datr_b200 import linear as DL
+    MSDA._timers = DL._timers = []
+    n0 = native.launch_count() + native.linear_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -339,8 +355,8 @@ def main():
         wl.step()
     e1.record()
     barrier()
-    launches = native.launch_count() - n0
-    timers, MSDA._timers = MSDA._timers, None
+    launches = native.launch_count() + native.linear_launch_count() - n0
+    timers, MSDA._timers, DL._timers = MSDA._timers, None, None
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -370,10 +386,11 @@ def main():
     value = images * args.steps / (ms * 1e-3)
     e2e = images * k2 / (ms_e2e * 1e-3)
     roof = wl.roofline(timers, peak, peak_src)
+    roof["handwritten_kernel_ms_per_step"] = sum(e0.elapsed_time(e1) for _, _, e0, e1 in timers) / args.steps
     line = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "vs_baseline": None, "dtype": getattr(wl, "dtype", "f32"), "data": "synthetic",
         "config": {"workload": wl.workload, "images_per_step_per_gpu": IMAGES_PER_STEP_PER_GPU,
                    "l2": "every call of a step reads its own buffers; the step cycles >3 GB (L2 is 126 MB)",
                    "parallelism": f"dp{world}"},

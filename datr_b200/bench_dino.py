@@ -18,7 +18,8 @@ from datr_b200.util.misc import NestedTensor
 
 H_IMG, W_IMG = 800, 1333
 WORKLOAD = ("DINO-4scale ResNet-50 DA training step (forward + losses + backward + gradient all-reduce + clip + AdamW), "
-            "synthetic 1333x800, batch_size 2/GPU = 2 source + 2 target images, 900 queries + CDN, fp32")
+            "synthetic 1333x800, batch_size 2/GPU = 2 source + 2 target images, 900 queries + CDN; fp32 tensors, "
+            "MSDeformAttn fp32, dense layers TF32 products with fp32 accumulation")
 
 
 def synth_targets(rng, n_images, num_classes, device):
@@ -43,8 +44,11 @@ class DinoStep:
         # dense contractions run on the tensor cores with TF32 operands / fp32 accumulation (10-bit mantissa, above the
         # bf16 floor BASELINE.json allows); DATR_MATMUL=fp32 restores SIMT fp32 GEMMs (what the parity tests use)
         self.matmul = os.environ.get("DATR_MATMUL", "tf32")
+        self.dtype = "tf32" if self.matmul == "tf32" and device.type == "cuda" else "f32"
         torch.backends.cuda.matmul.allow_tf32 = self.matmul == "tf32"
         torch.backends.cudnn.allow_tf32 = True
+        from datr_b200 import linear as dl
+        dl.set_mode("tf32" if self.matmul == "tf32" and device.type == "cuda" else "fp32")
         torch.manual_seed(42)                                   # identical initial weights on every rank
         args = dino_args(device=str(device), **over)
         self.args = args

@@ -11,11 +11,15 @@
 //     of W into a shared-memory ring guarded by full/empty mbarriers;
 //   * one elected thread issues tcgen05.mma.kind::tf32 (M = 128, N = BN, K = 8 per instruction, both operands
 //     K-major straight from the swizzled tiles); the fp32 accumulator lives in tensor memory (BN columns);
-//   * four epilogue warps read the accumulator back with tcgen05.ld (32 lanes x 32 columns per instruction), add the
-//     bias, apply ReLU, add the residual and store rows -- the bias/activation/residual passes of the reference
-//     (three extra reads + writes of the [M, N] activation) never touch HBM;
-//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue (a warp may only
-//     touch TMEM lanes 32*(warp%4) .. +31, so four consecutive warps cover the 128 accumulator rows).
+//   * four epilogue warps read the accumulator back with tcgen05.ld (32 lanes x 32 columns per instruction),
+//     transpose each 32 x 32 chunk through padded shared memory, add the bias, apply ReLU, add the residual and
+//     store whole 128-byte rows -- the bias/activation/residual passes of the reference (three extra reads + writes
+//     of the [M, N] activation) never touch HBM;
+//   * persistent CTAs (one per SM) walk the output tiles; the accumulator is double-buffered in TMEM so the epilogue
+//     of one tile overlaps the TMA/MMA main loop of the next;
+//   * warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue (a warp may only
+//     touch TMEM lanes 32*(warp%4) .. +31, so four consecutive warps cover the 128 accumulator rows; two such groups
+//     split the tile's columns).
 //
 // Numerics: TF32 products (10-bit mantissa), fp32 accumulation: ~3e-4 relative on K = 256 contractions, inside the
 // 1e-2 reduced-precision bar of BASELINE.json (the strict-fp32 parity tests keep cuBLAS SIMT fp32).
@@ -25,6 +29,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "datr_linear.h"
@@ -42,7 +47,8 @@ int lfail(int code, const char* fmt, const char* detail = "") {
 constexpr int BM = 128;       // accumulator rows = TMEM lanes
 constexpr int BK = 32;        // fp32 elements per 128-byte swizzle row
 constexpr int UMMA_K = 8;     // K of one tcgen05.mma.kind::tf32
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-9 epilogue
+constexpr int kEpiWarps = 8;
 
 // ---------------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -118,15 +124,25 @@ __host__ __device__ constexpr uint32_t tf32_idesc() {
   return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(BN >> 3) << 17) | (uint32_t(BM >> 4) << 24);
 }
 
+constexpr int kStagePitch = 36;                       // floats per row of the epilogue staging tile (32 + 4 pad)
+constexpr int kStageTile = 32 * kStagePitch * 4;      // bytes per epilogue warp
+
 template <int BN, int STAGES>
 struct Smem {
   static constexpr int kA = BM * BK * 4, kB = BN * BK * 4, kStage = kA + kB;
+  static constexpr int kEpi = kEpiWarps * kStageTile;
   static constexpr int kBars = 1024;  // barriers + TMEM slot
-  static constexpr int kTotal = STAGES * kStage + kBars + 1024 /* alignment slack */;
+  static constexpr int kTotal = STAGES * kStage + kEpi + kBars + 1024 /* alignment slack */;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// kernel: one CTA per 128 x BN output tile
+// kernel: persistent, one CTA per SM, static round-robin over 128 x BN output tiles (tiles that share an X row
+// block are adjacent in the order, so concurrently running CTAs hit the same X tile in L2).  The accumulator is
+// double-buffered in tensor memory (2 x BN columns): the epilogue of tile i overlaps the TMA/MMA main loop of tile i+1.
 // ---------------------------------------------------------------------------------------------------------------
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -136,102 +152,150 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_const
   using L = Smem<BN, STAGES>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage);
+  float* epi = reinterpret_cast<float*>(smem + STAGES * L::kStage);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage + L::kEpi);
   uint64_t* empty = full + STAGES;
-  uint64_t* acc_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_full = empty + STAGES;     // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
   const int kblocks = K / BK;
+  const int n_tiles = (N + BN - 1) / BN, m_tiles = (M + BM - 1) / BM;
+  const int tiles = n_tiles * m_tiles;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_w) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-    mbar_init(acc_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(acc_full + s, 1); mbar_init(acc_empty + s, kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(empty + s, ((kb / STAGES) & 1) ^ 1);
-        mbar_expect_tx(full + s, L::kStage);
-        unsigned char* a = smem + s * L::kStage;
-        tma_load_2d(a, &tma_x, kb * BK, m0, full + s);
-        tma_load_2d(a + L::kA, &tma_w, kb * BK, n0, full + s);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          mbar_wait(empty + s, ((it / STAGES) & 1) ^ 1);
+          mbar_expect_tx(full + s, L::kStage);
+          unsigned char* a = smem + s * L::kStage;
+          // concurrently running tiles start their K sweep at different k-blocks, so that the CTAs of a wave do not
+          // all pull the same W lines out of the same L2 slices at the same time (the sum is order-independent)
+          const int kk = (kb + tile) % kblocks;
+          tma_load_2d(a, &tma_x, kk * BK, m0, full + s);
+          tma_load_2d(a + L::kA, &tma_w, kk * BK, n0, full + s);
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = tf32_idesc<BN>();
-      for (int kb = 0; kb < kblocks; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(full + s, (kb / STAGES) & 1);
+      uint32_t it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+        const uint32_t as = ti & 1;
+        mbar_wait(acc_empty + as, ((ti >> 1) & 1) ^ 1);     // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t a = smem_u32(smem + s * L::kStage);
-        const uint64_t ad = kmajor_sw128_desc(a), bd = kmajor_sw128_desc(a + L::kA);
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const uint32_t s = it % STAGES;
+          mbar_wait(full + s, (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a = smem_u32(smem + s * L::kStage);
+          const uint64_t ad = kmajor_sw128_desc(a), bd = kmajor_sw128_desc(a + L::kA);
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes along K inside the swizzle row = +2 in the address field
-          umma_tf32(tmem_d, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0);
-        umma_commit(empty + s);                // frees the stage once these MMAs have read it
+          for (int k = 0; k < BK / UMMA_K; ++k)   // +32 bytes along K inside the swizzle row = +2 in the address field
+            umma_tf32(tmem_d, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0);
+          umma_commit(empty + s);                // frees the stage once these MMAs have read it
+        }
+        umma_commit(acc_full + as);              // accumulator complete
       }
-      umma_commit(acc_full);                   // accumulator complete
     }
   } else {
-    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = output rows m0 + that
+    // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 and one half of the tile's columns.  Each 32 x 32
+    // accumulator chunk goes through a padded shared-memory tile so that global stores (and residual loads) are whole
+    // 128-byte rows; the residual rows of the next chunk are fetched while the current one is processed.
     const int lane_base = (warp & 3) * 32;
-    const int row = m0 + lane_base + lane;
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    float* yr = y + (size_t)row * N;
-    const float* rr = residual ? residual + (size_t)row * N : nullptr;
+    const int half = (warp - 2) >> 2;                        // warps 2-5: columns [0, BN/2), warps 6-9: [BN/2, BN)
+    float* tile_s = epi + (warp - 2) * (kStageTile / 4);
+    const int tr = lane >> 3, tc = (lane & 7) * 4;           // transposed role: row tr + 4*j, columns tc .. tc+3
+    constexpr int kCols = BN / 2;
+    uint32_t ti = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
+      const int m0 = (tile / n_tiles) * BM, n0 = (tile % n_tiles) * BN + half * kCols;
+      const uint32_t as = ti & 1;
+      const int row0 = m0 + lane_base + tr;
+      float4 res[8];
+      auto fetch_residual = [&](int c) {
+        const int col = n0 + c + tc;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int row = row0 + 4 * j;
+          res[j] = (residual && row < M && col + 4 <= N)
+                       ? __ldg(reinterpret_cast<const float4*>(residual + (size_t)row * N + col))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      fetch_residual(0);                                      // zeros when there is no residual
+      mbar_wait(acc_full + as, (ti >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN + half * kCols + (uint32_t(lane_base) << 16);
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_d + (uint32_t(lane_base) << 16) + uint32_t(c), v);
-      const int col0 = n0 + c;
-      if (row < M && col0 < N) {
-        if (col0 + 32 <= N) {
+      for (int c = 0; c < kCols; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_d + uint32_t(c), v);
+        if (c + 32 >= kCols) {                                // last chunk read: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty + as);
+        }
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                   __uint_as_float(v[j + 3]));
-            if (bias) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + col0 + j));
-              o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
-            }
-            if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            if (rr) {
-              const float4 r4 = __ldg(reinterpret_cast<const float4*>(rr + col0 + j));
-              o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
-            }
-            *reinterpret_cast<float4*>(yr + col0 + j) = o;
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<uint4*>(tile_s + lane * kStagePitch + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const int col = n0 + c + tc;
+        float4 o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = *reinterpret_cast<const float4*>(tile_s + (tr + 4 * j) * kStagePitch + tc);
+        __syncwarp();
+        if (col < N) {
+          const bool vec = col + 4 <= N;
+          float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (bias) {
+            if (vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
+            else { b4.x = __ldg(bias + col); if (col + 1 < N) b4.y = __ldg(bias + col + 1); if (col + 2 < N) b4.z = __ldg(bias + col + 2); }
           }
-        } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (col0 + j >= N) break;
-            float o = __uint_as_float(v[j]);
-            if (bias) o += __ldg(bias + col0 + j);
-            if (relu) o = fmaxf(o, 0.f);
-            if (rr) o += __ldg(rr + col0 + j);
-            yr[col0 + j] = o;
+          for (int j = 0; j < 8; ++j) {
+            const int row = row0 + 4 * j;
+            if (row >= M) break;
+            float4 t = o[j];
+            t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
+            if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+            const size_t off = (size_t)row * N + col;
+            if (vec) {
+              t.x += res[j].x; t.y += res[j].y; t.z += res[j].z; t.w += res[j].w;
+              *reinterpret_cast<float4*>(y + off) = t;
+            } else {
+              const float ov[4] = {t.x, t.y, t.z, t.w};
+              for (int e = 0; e < 4 && col + e < N; ++e) y[off + e] = ov[e] + (residual ? __ldg(residual + off + e) : 0.f);
+            }
           }
         }
+        if (residual && c + 32 < kCols) fetch_residual(c + 32);
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_d, BN);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -285,7 +349,14 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, cons
     if (e != cudaSuccess) return lfail(DATR_LINEAR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     opted.fetch_or(bit, std::memory_order_release);
   }
-  const dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  static std::atomic<int> sm_count[64];
+  int sms = sm_count[dev & 63].load(std::memory_order_relaxed);
+  if (sms == 0) {
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    sm_count[dev & 63].store(sms, std::memory_order_relaxed);
+  }
+  const long long tiles = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const unsigned grid = unsigned(tiles < sms ? tiles : sms);
   linear_tf32_kernel<BN, STAGES><<<grid, kThreads, L::kTotal, stream>>>(mx, mw, bias, residual, y, M, N, K, relu);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return lfail(DATR_LINEAR_ERR_CUDA, "linear_tf32_kernel launch: %s", cudaGetErrorString(e));
@@ -308,11 +379,12 @@ int datr_linear_tf32(const float* x, const float* w, const float* bias, const fl
     return lfail(DATR_LINEAR_ERR_ALIGNMENT, "buffers must be 16-byte aligned%s");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUtensorMap mx, mw;
-  const bool wide = N > 128;
+  static const int force_bn = getenv("DATR_LINEAR_BN") ? atoi(getenv("DATR_LINEAR_BN")) : 0;   // tuning hook
+  const bool wide = force_bn ? force_bn == 256 : N > 256;   // 128-wide tiles fill the 148 SMs better at N <= 256
   if (int rc = make_map(&mx, x, M, K, BM)) return rc;
   if (int rc = make_map(&mw, w, N, K, wide ? 256 : 128)) return rc;
-  return wide ? launch<256, 4>(mx, mw, bias, residual, y, M, N, K, relu, stream)
-              : launch<128, 6>(mx, mw, bias, residual, y, M, N, K, relu, stream);
+  return wide ? launch<256, 3>(mx, mw, bias, residual, y, M, N, K, relu, stream)
+              : launch<128, 5>(mx, mw, bias, residual, y, M, N, K, relu, stream);
 }
 
 const char* datr_linear_last_error(void) { return g_lin_err; }

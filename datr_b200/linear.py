@@ -22,6 +22,10 @@ from . import native
 
 _MODE = "fp32"
 
+# Optional launch timers: bench.py sets this to a list and each launch appends
+# ("linear", (M, N, K, has_residual), start_event, end_event) recorded on the launching stream.
+_timers = None
+
 
 def set_mode(mode: str) -> None:
     """'fp32': every Linear runs as torch.nn.functional.linear (cuBLAS, TF32 off unless the caller enables it);
@@ -48,9 +52,16 @@ def _launch(x2, w, bias, residual2, relu):
     y = torch.empty((M, N), dtype=torch.float32, device=x2.device)
     lib = native.lib()
     with torch.cuda.device(x2.device):
+        stream = torch.cuda.current_stream()
+        if _timers is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
         rc = lib.datr_linear_tf32(x2.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
                                   residual2.data_ptr() if residual2 is not None else None, y.data_ptr(), M, N, K,
-                                  1 if relu else 0, torch.cuda.current_stream().cuda_stream)
+                                  1 if relu else 0, stream.cuda_stream)
+        if _timers is not None:
+            e1.record(stream)
+            _timers.append(("linear", (M, N, K, residual2 is not None), e0, e1))
     if rc != 0:
         raise RuntimeError(f"datr_linear_tf32 failed (code {rc}): {lib.datr_linear_last_error().decode()}")
     return y

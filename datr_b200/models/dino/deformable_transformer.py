@@ -29,6 +29,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from datr_b200.util.misc import inverse_sigmoid
+from datr_b200 import linear as dl
 from .ops.modules import MSDeformAttn
 from .utils import MLP, _get_activation_fn, gen_encoder_output_proposals, gen_sineembed_for_position, level_sizes
 
@@ -58,15 +59,22 @@ class PackedSelfAttention(nn.Module):
         convention) or an additive float mask.  Returns [N, T, C]."""
         N, T, C = qk_in.shape
         H = self.num_heads
-        qk = F.linear(qk_in, self.in_proj_weight[:2 * C], self.in_proj_bias[:2 * C])
-        v = F.linear(v_in, self.in_proj_weight[2 * C:], self.in_proj_bias[2 * C:])
+        qk = dl.linear(qk_in, self.in_proj_weight[:2 * C], self.in_proj_bias[:2 * C])
+        v = dl.linear(v_in, self.in_proj_weight[2 * C:], self.in_proj_bias[2 * C:])
         q, k = qk.view(N, T, 2, H, C // H).permute(2, 0, 3, 1, 4)
         v = v.view(N, T, H, C // H).transpose(1, 2)
         if attn_mask is not None and attn_mask.dtype == torch.bool:
             attn_mask = ~attn_mask                      # SDPA: True = may attend
         o = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask,
                                            dropout_p=self.dropout if self.training else 0.0)
-        return self.out_proj(o.transpose(1, 2).reshape(N, T, C))
+        return dl.linear(o.transpose(1, 2).reshape(N, T, C), self.out_proj.weight, self.out_proj.bias)
+
+
+def _fusable(layer, *dropouts):
+    """Bias / ReLU / residual epilogue fusion is exact only when the dropouts in between are inactive (p = 0, the
+    DINO configuration, or eval mode) and the activation is ReLU."""
+    act = getattr(layer, "activation", F.relu)
+    return act is F.relu and all(d is None or d.p == 0.0 or not layer.training for d in dropouts)
 
 
 class DeformableTransformerEncoderLayer(nn.Module):
@@ -90,9 +98,17 @@ class DeformableTransformerEncoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def forward_ffn(self, src):
+        if _fusable(self, self.dropout2, self.dropout3):
+            # linear1 + bias + ReLU and linear2 + bias + residual are one kernel each (datr_b200.linear)
+            hidden = dl.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
+            return self.norm2(dl.linear(hidden, self.linear2.weight, self.linear2.bias, residual=src))
         return self.norm2(src + self.dropout3(self.linear2(self.dropout2(self.activation(self.linear1(src))))))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask=None):
+        if _fusable(self, self.dropout1):
+            return self.forward_ffn(self.norm1(self.self_attn(self.with_pos_embed(src, pos), reference_points, src,
+                                                              spatial_shapes, level_start_index, key_padding_mask,
+                                                              residual=src)))
         attn = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                               level_start_index, key_padding_mask)
         return self.forward_ffn(self.norm1(src + self.dropout1(attn)))
@@ -170,6 +186,9 @@ class DeformableTransformerDecoderLayer(nn.Module):
         return tensor if pos is None else tensor + pos
 
     def forward_ffn(self, tgt):
+        if _fusable(self, self.dropout3, self.dropout4):
+            hidden = dl.linear(tgt, self.linear1.weight, self.linear1.bias, relu=True)
+            return self.norm3(dl.linear(hidden, self.linear2.weight, self.linear2.bias, residual=tgt))
         return self.norm3(tgt + self.dropout4(self.linear2(self.dropout3(self.activation(self.linear1(tgt))))))
 
     def forward_sa(self, tgt, tgt_query_pos=None, self_attn_mask=None):
@@ -180,6 +199,10 @@ class DeformableTransformerDecoderLayer(nn.Module):
 
     def forward_ca(self, tgt, tgt_query_pos, tgt_reference_points, memory, memory_key_padding_mask,
                    memory_level_start_index, memory_spatial_shapes):
+        if _fusable(self, self.dropout1):
+            return self.norm1(self.cross_attn(self.with_pos_embed(tgt, tgt_query_pos), tgt_reference_points, memory,
+                                              memory_spatial_shapes, memory_level_start_index,
+                                              memory_key_padding_mask, residual=tgt))
         attn = self.cross_attn(self.with_pos_embed(tgt, tgt_query_pos), tgt_reference_points, memory,
                                memory_spatial_shapes, memory_level_start_index, memory_key_padding_mask)
         return self.norm1(tgt + self.dropout1(attn))
@@ -393,7 +416,7 @@ class DeformableTransformer(nn.Module):
         if self.two_stage_type == "standard":
             input_hw = self.two_stage_wh_embedding.weight[0] if self.two_stage_learn_wh else None
             output_memory, output_proposals = gen_encoder_output_proposals(memory, mask_flat, shapes_list, input_hw)
-            output_memory = self.enc_output_norm(self.enc_output(output_memory))
+            output_memory = self.enc_output_norm(dl.linear(output_memory, self.enc_output.weight, self.enc_output.bias))
             class_all = self.enc_out_class_embed(output_memory)
             topk = torch.topk(class_all.max(-1)[0], self.num_queries, dim=1)[1]               # [N,nq] int64
             tgt_undetach = torch.gather(output_memory, 1, topk.unsqueeze(-1).expand(-1, -1, self.d_model))

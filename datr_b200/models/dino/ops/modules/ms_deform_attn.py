@@ -13,6 +13,8 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from datr_b200 import linear as dl
+
 from ..functions import MSDeformAttnFunction
 
 
@@ -58,23 +60,25 @@ class MSDeformAttn(nn.Module):
             nn.init.constant_(proj.bias.data, 0.0)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
-                input_level_start_index, input_padding_mask=None):
+                input_level_start_index, input_padding_mask=None, residual=None):
         """query [N,Lq,C]; reference_points [N,Lq,L,2] (centres) or [N,Lq,L,4] (cx,cy,w,h boxes), in [0,1];
         input_flatten [N,S,C]; input_spatial_shapes [L,2]=(H,W); input_level_start_index [L];
-        input_padding_mask [N,S] bool, True on padding.  Returns [N,Lq,C]."""
+        input_padding_mask [N,S] bool, True on padding.  Returns [N,Lq,C].
+        `residual` (extension, optional [N,Lq,C]) is added to the result inside the output projection's epilogue."""
         N, Lq, _ = query.shape
         S = input_flatten.shape[1]
         M, L, P = self.n_heads, self.n_levels, self.n_points
         # (the reference asserts sum(H*W) == S here with a device->host sync, ms_deform_attn.py:92; the C ABI
         #  bounds every gather by clamping, so the check is left to the caller)
 
-        value = self.value_proj(input_flatten)
+        value = dl.linear(input_flatten, self.value_proj.weight, self.value_proj.bias)
         if input_padding_mask is not None:
             value = value.masked_fill(input_padding_mask[..., None], 0.0)
         value = value.view(N, S, M, self.d_model // M)
 
-        offsets = self.sampling_offsets(query).view(N, Lq, M, L, P, 2)
-        weights = F.softmax(self.attention_weights(query).view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+        offsets = dl.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(N, Lq, M, L, P, 2)
+        weights = F.softmax(dl.linear(query, self.attention_weights.weight, self.attention_weights.bias)
+                            .view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
 
         ref_dim = reference_points.shape[-1]
         if ref_dim == 2:      # offsets are in pixels of each level: normalise by (W_l, H_l)
@@ -89,7 +93,8 @@ class MSDeformAttn(nn.Module):
         if value.dtype == torch.float16:   # AMP: the op itself runs in fp32 (reference :114-121)
             sampled = MSDeformAttnFunction.apply(value.float(), input_spatial_shapes, input_level_start_index,
                                                  locations.float(), weights.float(), self.im2col_step)
-            return self.output_proj(sampled.to(torch.float16))
+            out = self.output_proj(sampled.to(torch.float16))
+            return out if residual is None else out + residual
         sampled = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                              locations, weights, self.im2col_step)
-        return self.output_proj(sampled)
+        return dl.linear(sampled, self.output_proj.weight, self.output_proj.bias, residual=residual)

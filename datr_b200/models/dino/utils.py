@@ -8,6 +8,8 @@ import math
 
 import torch
 import torch.nn.functional as F
+
+from datr_b200 import linear as dl
 from torch import nn
 
 
@@ -78,10 +80,8 @@ class MLP(nn.Module):
         self.layers = nn.ModuleList(nn.Linear(a, b) for a, b in zip(dims[:-1], dims[1:]))
 
     def forward(self, x):
-        for i, layer in enumerate(self.layers):
-            x = layer(x)
-            if i + 1 < self.num_layers:
-                x = F.relu(x)
+        for i, layer in enumerate(self.layers):      # bias + ReLU ride in the GEMM epilogue (datr_b200.linear)
+            x = dl.linear(x, layer.weight, layer.bias, relu=i + 1 < self.num_layers)
         return x
 
 
