@@ -348,6 +348,7 @@ def main():
     from datr_b200 import linear as DL
     MSDA._timers = DL._timers = []
     n0 = native.launch_count() + native.linear_launch_count()
+    g0 = getattr(getattr(wl, "graphs", None), "replayed_native_launches", 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -359,6 +360,23 @@ def main():
     timers, MSDA._timers, DL._timers = MSDA._timers, None, None
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
+    timing_note = "per-launch CUDA events on the launching stream inside the timed region"
+    sg = getattr(wl, "graphs", None)
+    if sg is not None:
+        # graph replays launch our kernels without passing through the Python shims: count them from the capture
+        # bookkeeping, and take the per-launch event timings from eager steps of the same workload right after
+        launches += sg.replayed_native_launches - g0
+        wl.set_graphs(False)
+        wl.step(); wl.step()
+        MSDA._timers = DL._timers = []
+        k_eager = max(1, min(args.steps, 3))
+        for _ in range(k_eager):
+            wl.step()
+        torch.cuda.synchronize()
+        timers, MSDA._timers, DL._timers = MSDA._timers, None, None
+        wl.set_graphs(True)
+        timing_note = (f"per-launch CUDA events in {k_eager} eager steps of the same workload run right after the timed "
+                       "region (graph replays cannot carry per-kernel events); value/e2e are measured with graph replay")
 
     # end-to-end leg: host buffers in, host results out, through the public op / model API
     for _ in range(2):
@@ -386,7 +404,9 @@ def main():
     value = images * args.steps / (ms * 1e-3)
     e2e = images * k2 / (ms_e2e * 1e-3)
     roof = wl.roofline(timers, peak, peak_src)
-    roof["handwritten_kernel_ms_per_step"] = sum(e0.elapsed_time(e1) for _, _, e0, e1 in timers) / args.steps
+    n_timed_steps = args.steps if sg is None else k_eager
+    roof["handwritten_kernel_ms_per_step"] = sum(e0.elapsed_time(e1) for _, _, e0, e1 in timers) / n_timed_steps
+    roof["timing"] = timing_note
     line = {
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -49,11 +49,21 @@ class DinoStep:
         torch.backends.cudnn.allow_tf32 = True
         from datr_b200 import linear as dl
         dl.set_mode("tf32" if self.matmul == "tf32" and device.type == "cuda" else "fp32")
+        # CUDA graphs for the ResNet body, encoder and decoder (datr_b200/graphs.py); DATR_GRAPHS=0 keeps the step eager
+        self.graphs = None
+        if device.type == "cuda" and os.environ.get("DATR_GRAPHS", "1") != "0":
+            from datr_b200 import graphs
+            self.graphs = graphs.StepGraphs()
+        self.set_graphs(True)
         torch.manual_seed(42)                                   # identical initial weights on every rank
         args = dino_args(device=str(device), **over)
         self.args = args
         self.model, self.criterion, _ = build_dino(args)
         self.model.to(device).train()
+        if device.type == "cuda" and os.environ.get("DATR_CHANNELS_LAST", "1") != "0":
+            # NHWC activations/weights: cuDNN's tensor-core convolutions run without NCHW<->NHWC transposes, and
+            # flattening a feature map to [N, HW, C] tokens becomes a view
+            self.model.to(memory_format=torch.channels_last)
         self.criterion.train()
         broadcast_parameters(self.model)
         self.grads = FlatGradients(self.model)
@@ -66,14 +76,23 @@ class DinoStep:
         if device.type == "cuda":
             self.host_images, self.host_mask = self.host_images.pin_memory(), self.host_mask.pin_memory()
         self.host_targets = synth_targets(rng, batch_size, args.num_classes, "cpu")
+        self.channels_last = device.type == "cuda" and os.environ.get("DATR_CHANNELS_LAST", "1") != "0"
         self.images = self.host_images.to(device)
+        if self.channels_last:
+            self.images = self.images.contiguous(memory_format=torch.channels_last)
         self.mask = self.host_mask.to(device)
         self.targets = [{k: v.to(device) for k, v in t.items()} for t in self.host_targets]
         self.n_images = n
         self.last_loss = None
         torch.manual_seed(1000 + rank)                          # CDN noise stream
 
+    def set_graphs(self, on: bool):
+        from datr_b200 import graphs
+        graphs.ACTIVE = self.graphs if on else None
+
     def _step(self, images, mask, targets):
+        if self.graphs is not None:
+            self.graphs.begin_step()
         self.grads.zero()
         out = self.model(NestedTensor(images, mask), targets)
         losses = self.criterion(out, targets)
@@ -91,6 +110,8 @@ class DinoStep:
     def e2e_step(self):
         """Host batch in (pinned -> device copies inside the step), loss value out (device -> host read)."""
         images = self.host_images.to(self.device, non_blocking=True)
+        if self.channels_last:
+            images = images.contiguous(memory_format=torch.channels_last)
         mask = self.host_mask.to(self.device, non_blocking=True)
         targets = [{k: v.to(self.device, non_blocking=True) for k, v in t.items()} for t in self.host_targets]
         loss = self._step(images, mask, targets)
@@ -104,8 +125,10 @@ class DinoStep:
         return bench.MsdaStep.roofline(self, timers, peak, peak_src)
 
     def extra(self):
-        return {"loss": float(self.last_loss) if self.last_loss is not None else None,
-                "grad_allreduce_bytes": self.grads.numel * 4}
+        return {"loss": float(self.last_loss.detach()) if self.last_loss is not None else None,
+                "grad_allreduce_bytes": self.grads.numel * 4,
+                "cuda_graphs": None if self.graphs is None else {"segments": self.graphs.captures,
+                                                                 "what": "ResNet body, encoder x2, decoder x2 (forward + backward)"}}
 
 
 def reference_arm(args, threads):

@@ -1,0 +1,107 @@
+"""CUDA graphs for the static segments of the DINO training step.
+
+The step is launch-bound on the host (tools/segment_times.py: ~10 k kernel launches, forward 47 ms of pure enqueue
+time).  The ResNet body, the deformable encoder and the decoder are pure tensor functions with static shapes for a
+fixed image size / number of de-noising queries, so each is captured ONCE -- forward and backward -- with
+torch.cuda.make_graphed_callables and replayed afterwards: no Python, no per-kernel launch cost.  The pieces in between
+(de-noising query construction, two-stage top-k, heads, prototypes, criterion with the scipy Hungarian matcher)
+stay eager because they depend on the targets or synchronise with the host.
+
+Usage (what bench_dino.DinoStep does):
+    graphs.ACTIVE = graphs.StepGraphs()      # opt in
+    ...each step:  graphs.ACTIVE.begin_step(); loss = criterion(model(...)); loss.backward()
+
+A segment is keyed by (name, index of the call inside the step, shapes/dtypes of its tensor arguments): the two
+transformer passes of a step get separate graphs because the activations of the first must survive until its
+backward.  A new shape signature simply captures another graph.  Capture failures are raised, never hidden.
+
+Our own kernels are capture-safe: they run on the current stream, allocate through torch's caching allocator (the
+graph's private pool during capture), pass tensor maps by value and use cudaMemsetAsync for the zero fill.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import native
+
+ACTIVE = None          # a StepGraphs instance when graph replay is enabled
+
+
+def _native_launches():
+    return native.launch_count() + native.linear_launch_count()
+
+
+class StepGraphs:
+    def __init__(self, warmup_iters: int = 3):
+        self.cache = {}
+        self.calls = {}
+        self.warmup_iters = warmup_iters
+        self.replayed_native_launches = 0      # hand-written kernel launches executed by graph replays
+        self.captures = 0
+
+    def begin_step(self):
+        self.calls.clear()
+
+    def run(self, name, make_module, args):
+        """Run segment `name` on tensor arguments `args` through its graph (capturing it on first use)."""
+        idx = self.calls.get(name, 0)
+        self.calls[name] = idx + 1
+        key = (name, idx, torch.is_grad_enabled()) + tuple((tuple(a.shape), a.dtype, a.requires_grad) for a in args)
+        entry = self.cache.get(key)
+        if entry is None:
+            if not torch.is_grad_enabled():
+                return make_module()(*args)              # inference passes stay eager
+            module = make_module()
+            sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
+            n0 = _native_launches()
+            graphed = torch.cuda.make_graphed_callables(module, sample, num_warmup_iters=self.warmup_iters,
+                                                        allow_unused_input=True)
+            # warm-up iterations + one capture each ran forward and backward eagerly/under capture once
+            per_pair = (_native_launches() - n0) // (self.warmup_iters + 1)
+            entry = self.cache[key] = (graphed, per_pair)
+            self.captures += 1
+        graphed, per_pair = entry
+        self.replayed_native_launches += per_pair
+        return graphed(*args)
+
+
+class BodySegment(nn.Module):
+    """ResNet body: images [B,3,H,W] -> tuple of the requested stage outputs."""
+
+    def __init__(self, body):
+        super().__init__()
+        self.body = body
+        self.train(body.training)
+
+    def forward(self, x):
+        return tuple(self.body(x).values())
+
+
+class EncoderSegment(nn.Module):
+    def __init__(self, encoder, shapes_list):
+        super().__init__()
+        self.encoder, self.shapes_list = encoder, list(shapes_list)
+        self.train(encoder.training)
+
+    def forward(self, src, pos, spatial_shapes, level_start_index, valid_ratios, key_padding_mask):
+        return self.encoder(src, pos=pos, spatial_shapes=spatial_shapes, level_start_index=level_start_index,
+                            valid_ratios=valid_ratios, key_padding_mask=key_padding_mask,
+                            shapes_list=self.shapes_list)[0]
+
+
+class DecoderSegment(nn.Module):
+    """Decoder stack: returns the per-layer outputs followed by the reference boxes as one flat tuple."""
+
+    def __init__(self, decoder, has_mask):
+        super().__init__()
+        self.decoder, self.has_mask = decoder, has_mask
+        self.train(decoder.training)
+
+    def forward(self, tgt, memory, memory_key_padding_mask, pos, refpoints_unsigmoid, level_start_index,
+                spatial_shapes, valid_ratios, *tgt_mask):
+        hs, refs = self.decoder(tgt=tgt, memory=memory, memory_key_padding_mask=memory_key_padding_mask, pos=pos,
+                                refpoints_unsigmoid=refpoints_unsigmoid, level_start_index=level_start_index,
+                                spatial_shapes=spatial_shapes, valid_ratios=valid_ratios,
+                                tgt_mask=tgt_mask[0] if self.has_mask else None)
+        return tuple(hs) + tuple(refs)

@@ -29,6 +29,7 @@ import torch.nn.functional as F
 from torch import Tensor, nn
 
 from datr_b200.util.misc import inverse_sigmoid
+from datr_b200 import graphs
 from datr_b200 import linear as dl
 from .ops.modules import MSDeformAttn
 from .utils import MLP, _get_activation_fn, gen_encoder_output_proposals, gen_sineembed_for_position, level_sizes
@@ -409,9 +410,13 @@ class DeformableTransformer(nn.Module):
                                             device=src_flat.device)
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
 
-        memory, _, _ = self.encoder(src_flat, pos=pos_flat, level_start_index=level_start_index,
-                                    spatial_shapes=spatial_shapes, valid_ratios=valid_ratios,
-                                    key_padding_mask=mask_flat, shapes_list=shapes_list)
+        if graphs.ACTIVE is not None and src_flat.is_cuda:
+            memory = graphs.ACTIVE.run("encoder", lambda: graphs.EncoderSegment(self.encoder, shapes_list),
+                                       (src_flat, pos_flat, spatial_shapes, level_start_index, valid_ratios, mask_flat))
+        else:
+            memory, _, _ = self.encoder(src_flat, pos=pos_flat, level_start_index=level_start_index,
+                                        spatial_shapes=spatial_shapes, valid_ratios=valid_ratios,
+                                        key_padding_mask=mask_flat, shapes_list=shapes_list)
 
         if self.two_stage_type == "standard":
             input_hw = self.two_stage_wh_embedding.weight[0] if self.two_stage_learn_wh else None
@@ -437,9 +442,16 @@ class DeformableTransformer(nn.Module):
         else:
             refpoint_embed, tgt = refpoint_sel, tgt_sel
 
-        hs, references = self.decoder(tgt=tgt, memory=memory, memory_key_padding_mask=mask_flat, pos=pos_flat,
-                                      refpoints_unsigmoid=refpoint_embed, level_start_index=level_start_index,
-                                      spatial_shapes=spatial_shapes, valid_ratios=valid_ratios, tgt_mask=attn_mask)
+        if graphs.ACTIVE is not None and tgt.is_cuda:
+            dec_args = (tgt, memory, mask_flat, pos_flat, refpoint_embed, level_start_index, spatial_shapes, valid_ratios)
+            flat = graphs.ACTIVE.run("decoder", lambda: graphs.DecoderSegment(self.decoder, attn_mask is not None),
+                                     dec_args + ((attn_mask,) if attn_mask is not None else ()))
+            n_layers = len(self.decoder.layers)
+            hs, references = list(flat[:n_layers]), list(flat[n_layers:])
+        else:
+            hs, references = self.decoder(tgt=tgt, memory=memory, memory_key_padding_mask=mask_flat, pos=pos_flat,
+                                          refpoints_unsigmoid=refpoint_embed, level_start_index=level_start_index,
+                                          spatial_shapes=spatial_shapes, valid_ratios=valid_ratios, tgt_mask=attn_mask)
 
         hs_enc = ref_enc = None
         if self.two_stage_type == "standard":

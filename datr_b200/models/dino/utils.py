@@ -104,5 +104,5 @@ def gen_sineembed_for_position(pos_tensor):
     dim_t = 10000 ** (2 * torch.div(idx, 2, rounding_mode="floor") / 128)
     ang = pos_tensor.unsqueeze(-1) * (2 * math.pi) / dim_t                       # [..., k, 128]
     emb = torch.stack((ang[..., 0::2].sin(), ang[..., 1::2].cos()), dim=-1).flatten(-2)
-    order = [1, 0] if k == 2 else [1, 0, 2, 3]
-    return emb[..., order, :].flatten(-2)
+    # (y, x[, w, h]) order by slicing: an index list would be uploaded from the host (not CUDA-graph capturable)
+    return torch.cat((emb[..., 1:2, :], emb[..., 0:1, :], emb[..., 2:, :]), dim=-2).flatten(-2)

@@ -25,7 +25,9 @@ class FlatGradients:
         self.flat = torch.zeros(self.numel, dtype=dt, device=dev)
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            # the view takes the parameter's own (dense) strides, e.g. channels_last convolution weights
+            assert p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last), "parameters must be dense"
+            p.grad = self.flat[off:off + p.numel()].as_strided(p.size(), p.stride())
             off += p.numel()
         self.group = process_group
 

@@ -170,3 +170,42 @@ def test_tensor_core_mode_stays_inside_the_reduced_precision_bar(G, small):
     assert native.linear_launch_count() - n0 == 10, "tcgen05 linear kernels are not on the path"   # 6 + 4
     assert rel(got_layer, G["mod.enc_layer"]) < 1e-2
     assert rel(got_attn, G["mod.msda_2d"]) < 1e-2
+
+
+def _train_losses_and_grads(model, crit, tg, images):
+    model.train(); crit.train()
+    model.global_proto = None
+    torch.manual_seed(7)
+    out = model(images, tg)
+    losses = crit(out, tg)
+    total = mcase.total_loss(losses, crit.weight_dict)
+    model.zero_grad()
+    total.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    return float(total.detach()), grads
+
+
+def test_channels_last_and_graph_replay_match_eager(small, cpu_noise):
+    """The benchmark configuration (NHWC weights/activations + CUDA-graph replay of body / encoder / decoder) must
+    compute the same step as the plain eager model: loss and gradients within fp32 reordering noise."""
+    import copy
+    from datr_b200 import graphs
+    model, crit, _ = small
+    tg = mcase.targets(device="cuda")
+    images = [i.cuda() for i in mcase.images()]
+    want_loss, want = _train_losses_and_grads(model, crit, tg, images)
+    fast = copy.deepcopy(model).to(memory_format=torch.channels_last)
+    sg = graphs.StepGraphs()
+    graphs.ACTIVE = sg
+    try:
+        for _ in range(2):                      # first step captures, second replays
+            sg.begin_step()
+            got_loss, got = _train_losses_and_grads(fast, crit, tg, images)
+    finally:
+        graphs.ACTIVE = None
+    assert sg.captures == 5
+    assert abs(got_loss - want_loss) < 1e-4 * abs(want_loss)
+    assert set(got) == set(want)
+    for k in want:
+        den = max(float(want[k].abs().max()), 1e-6)
+        assert float((got[k] - want[k]).abs().max()) / den < 5e-3, k

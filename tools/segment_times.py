@@ -20,6 +20,8 @@ def seg(fn):
 
 acc = {}
 for it in range(3):
+    if wl.graphs is not None:
+        wl.graphs.begin_step()
     _, h, w = seg(wl.grads.zero); acc.setdefault("zero", []).append((h, w))
     out, h, w = seg(lambda: wl.model(NestedTensor(wl.images, wl.mask), wl.targets)); acc.setdefault("forward", []).append((h, w))
     losses, h, w = seg(lambda: wl.criterion(out, wl.targets)); acc.setdefault("criterion", []).append((h, w))
