@@ -31,6 +31,7 @@ from torch import Tensor, nn
 from datr_b200.util.misc import inverse_sigmoid
 from datr_b200 import graphs
 from datr_b200 import linear as dl
+from datr_b200.layernorm import layer_norm as ln
 from .ops.modules import MSDeformAttn
 from .utils import MLP, _get_activation_fn, gen_encoder_output_proposals, gen_sineembed_for_position, level_sizes
 
@@ -102,17 +103,17 @@ class DeformableTransformerEncoderLayer(nn.Module):
         if _fusable(self, self.dropout2, self.dropout3):
             # linear1 + bias + ReLU and linear2 + bias + residual are one kernel each (datr_b200.linear)
             hidden = dl.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
-            return self.norm2(dl.linear(hidden, self.linear2.weight, self.linear2.bias, residual=src))
-        return self.norm2(src + self.dropout3(self.linear2(self.dropout2(self.activation(self.linear1(src))))))
+            return ln(self.norm2, dl.linear(hidden, self.linear2.weight, self.linear2.bias, residual=src))
+        return ln(self.norm2, src + self.dropout3(self.linear2(self.dropout2(self.activation(self.linear1(src))))))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask=None):
         if _fusable(self, self.dropout1):
-            return self.forward_ffn(self.norm1(self.self_attn(self.with_pos_embed(src, pos), reference_points, src,
+            return self.forward_ffn(ln(self.norm1, self.self_attn(self.with_pos_embed(src, pos), reference_points, src,
                                                               spatial_shapes, level_start_index, key_padding_mask,
                                                               residual=src)))
         attn = self.self_attn(self.with_pos_embed(src, pos), reference_points, src, spatial_shapes,
                               level_start_index, key_padding_mask)
-        return self.forward_ffn(self.norm1(src + self.dropout1(attn)))
+        return self.forward_ffn(ln(self.norm1, src + self.dropout1(attn)))
 
 
 class TransformerEncoder(nn.Module):
@@ -152,7 +153,7 @@ class TransformerEncoder(nn.Module):
             out = layer(src=out, pos=pos, reference_points=ref, spatial_shapes=spatial_shapes,
                         level_start_index=level_start_index, key_padding_mask=key_padding_mask)
         if self.norm is not None:
-            out = self.norm(out)
+            out = ln(self.norm, out)
         return out, None, None
 
 
@@ -189,24 +190,24 @@ class DeformableTransformerDecoderLayer(nn.Module):
     def forward_ffn(self, tgt):
         if _fusable(self, self.dropout3, self.dropout4):
             hidden = dl.linear(tgt, self.linear1.weight, self.linear1.bias, relu=True)
-            return self.norm3(dl.linear(hidden, self.linear2.weight, self.linear2.bias, residual=tgt))
-        return self.norm3(tgt + self.dropout4(self.linear2(self.dropout3(self.activation(self.linear1(tgt))))))
+            return ln(self.norm3, dl.linear(hidden, self.linear2.weight, self.linear2.bias, residual=tgt))
+        return ln(self.norm3, tgt + self.dropout4(self.linear2(self.dropout3(self.activation(self.linear1(tgt))))))
 
     def forward_sa(self, tgt, tgt_query_pos=None, self_attn_mask=None):
         if self.self_attn is None:
             return tgt
         qk = self.with_pos_embed(tgt, tgt_query_pos)
-        return self.norm2(tgt + self.dropout2(self.self_attn(qk, tgt, attn_mask=self_attn_mask)))
+        return ln(self.norm2, tgt + self.dropout2(self.self_attn(qk, tgt, attn_mask=self_attn_mask)))
 
     def forward_ca(self, tgt, tgt_query_pos, tgt_reference_points, memory, memory_key_padding_mask,
                    memory_level_start_index, memory_spatial_shapes):
         if _fusable(self, self.dropout1):
-            return self.norm1(self.cross_attn(self.with_pos_embed(tgt, tgt_query_pos), tgt_reference_points, memory,
+            return ln(self.norm1, self.cross_attn(self.with_pos_embed(tgt, tgt_query_pos), tgt_reference_points, memory,
                                               memory_spatial_shapes, memory_level_start_index,
                                               memory_key_padding_mask, residual=tgt))
         attn = self.cross_attn(self.with_pos_embed(tgt, tgt_query_pos), tgt_reference_points, memory,
                                memory_spatial_shapes, memory_level_start_index, memory_key_padding_mask)
-        return self.norm1(tgt + self.dropout1(attn))
+        return ln(self.norm1, tgt + self.dropout1(attn))
 
     def forward(self, tgt, tgt_query_pos=None, tgt_query_sine_embed=None, tgt_key_padding_mask=None,
                 tgt_reference_points=None, memory=None, memory_key_padding_mask=None, memory_level_start_index=None,
@@ -276,7 +277,7 @@ class TransformerDecoder(nn.Module):
                 new_ref = (self.bbox_embed[lid](out) + inverse_sigmoid(ref)).sigmoid()
                 ref = new_ref if (self.rm_detach and "dec" in self.rm_detach) else new_ref.detach()
                 refs.append(ref if self.use_detached_boxes_dec_out else new_ref)
-            inter.append(self.norm(out))
+            inter.append(ln(self.norm, out))
         return [inter, refs]
 
 
@@ -421,7 +422,7 @@ class DeformableTransformer(nn.Module):
         if self.two_stage_type == "standard":
             input_hw = self.two_stage_wh_embedding.weight[0] if self.two_stage_learn_wh else None
             output_memory, output_proposals = gen_encoder_output_proposals(memory, mask_flat, shapes_list, input_hw)
-            output_memory = self.enc_output_norm(dl.linear(output_memory, self.enc_output.weight, self.enc_output.bias))
+            output_memory = ln(self.enc_output_norm, dl.linear(output_memory, self.enc_output.weight, self.enc_output.bias))
             class_all = self.enc_out_class_embed(output_memory)
             topk = torch.topk(class_all.max(-1)[0], self.num_queries, dim=1)[1]               # [N,nq] int64
             tgt_undetach = torch.gather(output_memory, 1, topk.unsqueeze(-1).expand(-1, -1, self.d_model))

@@ -13,14 +13,16 @@ import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-SOURCES = [os.path.join(_PKG, "csrc", "msda.cu"), os.path.join(_PKG, "csrc", "linear_tf32.cu")]
+SOURCES = [os.path.join(_PKG, "csrc", "msda.cu"), os.path.join(_PKG, "csrc", "linear_tf32.cu"),
+           os.path.join(_PKG, "csrc", "layernorm.cu")]
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_last_error", "datr_abi_version",
-           "datr_launch_count", "datr_linear_tf32", "datr_linear_last_error", "datr_linear_launch_count")
+           "datr_launch_count", "datr_linear_tf32", "datr_linear_last_error", "datr_linear_launch_count",
+           "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count")
 
 _lock = threading.Lock()
 _lib = None
@@ -83,6 +85,10 @@ def lib() -> ctypes.CDLL:
         L.datr_linear_tf32.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
         L.datr_linear_last_error.restype = ctypes.c_char_p
         L.datr_linear_launch_count.restype = ctypes.c_uint64
+        L.datr_layernorm256_backward.restype = i
+        L.datr_layernorm256_backward.argtypes = [vp] * 9 + [i, vp]
+        L.datr_layernorm_last_error.restype = ctypes.c_char_p
+        L.datr_layernorm_launch_count.restype = ctypes.c_uint64
         if L.datr_abi_version() != 1:
             raise NativeLibraryError("libdatr_b200.so ABI version mismatch; rebuild")
         _lib = L
@@ -92,6 +98,11 @@ def lib() -> ctypes.CDLL:
 def launch_count() -> int:
     """MSDeformAttn kernel launches issued through the library by this process."""
     return int(lib().datr_launch_count())
+
+
+def layernorm_launch_count() -> int:
+    """LayerNorm backward kernel launches issued through the library by this process."""
+    return int(lib().datr_layernorm_launch_count())
 
 
 def linear_launch_count() -> int:
