@@ -278,14 +278,18 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_const
             if (row >= M) break;
             float4 t = o[j];
             t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
-            if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+            if (relu == 1) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
             const size_t off = (size_t)row * N + col;
             if (vec) {
               t.x += res[j].x; t.y += res[j].y; t.z += res[j].z; t.w += res[j].w;
+              if (relu == 2) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
               *reinterpret_cast<float4*>(y + off) = t;
             } else {
               const float ov[4] = {t.x, t.y, t.z, t.w};
-              for (int e = 0; e < 4 && col + e < N; ++e) y[off + e] = ov[e] + (residual ? __ldg(residual + off + e) : 0.f);
+              for (int e = 0; e < 4 && col + e < N; ++e) {
+                const float o1 = ov[e] + (residual ? __ldg(residual + off + e) : 0.f);
+                y[off + e] = relu == 2 ? fmaxf(o1, 0.f) : o1;
+              }
             }
           }
         }

@@ -58,7 +58,7 @@ def _launch(x2, w, bias, residual2, relu):
             e0.record(stream)
         rc = lib.datr_linear_tf32(x2.data_ptr(), w.data_ptr(), bias.data_ptr() if bias is not None else None,
                                   residual2.data_ptr() if residual2 is not None else None, y.data_ptr(), M, N, K,
-                                  1 if relu else 0, stream.cuda_stream)
+                                  int(relu), stream.cuda_stream)
         if _timers is not None:
             e1.record(stream)
             _timers.append(("linear", (M, N, K, residual2 is not None), e0, e1))
@@ -81,7 +81,8 @@ class _LinearTF32(torch.autograd.Function):
         y = _launch(x2, w, _c(bias) if bias is not None else None, r2, relu)
         ctx.relu, ctx.has_bias, ctx.has_res = relu, bias is not None, residual is not None
         ctx.xshape = x.shape
-        ctx.save_for_backward(x2, w, y if relu else None, r2 if relu else None)
+        ctx.rshape = residual.shape if residual is not None else None
+        ctx.save_for_backward(x2, w, y if relu else None, r2 if relu == 1 else None)
         return y.view(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
@@ -90,10 +91,11 @@ class _LinearTF32(torch.autograd.Function):
         x2, w, y, r2 = ctx.saved_tensors
         N, K = w.shape
         g2 = _c(gy.reshape(-1, N))
-        gres = gy if ctx.has_res else None
-        if ctx.relu:
-            act = y if r2 is None else y - r2
-            g2 = g2 * (act > 0)
+        if ctx.relu == 2:     # ReLU after the residual add: the mask applies to both branches
+            g2 = torch.ops.aten.threshold_backward(g2, y, 0.0)
+        gres = g2.view(ctx.rshape) if ctx.has_res else None
+        if ctx.relu == 1:     # one fused mask kernel (ATen's ReLU backward) instead of compare + multiply
+            g2 = torch.ops.aten.threshold_backward(g2, y if r2 is None else y - r2, 0.0)
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = _launch(g2, _c(w.t()), None, None, False).view(ctx.xshape) if N % 32 == 0 and K % 4 == 0 else (g2 @ w).view(ctx.xshape)
@@ -105,10 +107,14 @@ class _LinearTF32(torch.autograd.Function):
 
 
 def linear(x, weight, bias=None, relu=False, residual=None):
-    """act(x @ weight.T + bias) + residual.  Tensor-core kernel in 'tf32' mode for eligible shapes, else torch."""
+    """relu False/0: x @ weight.T + bias + residual;  True/1: relu(x @ weight.T + bias) + residual;
+    2: relu(x @ weight.T + bias + residual).  Tensor-core kernel in 'tf32' mode for eligible shapes, else torch."""
+    relu = int(relu)
     if _MODE == "tf32" and eligible(x, weight):
         return _LinearTF32.apply(x, weight, bias, residual, relu)
     y = F.linear(x, weight, bias)
-    if relu:
+    if relu == 1:
         y = F.relu(y)
-    return y if residual is None else y + residual
+    if residual is not None:
+        y = y + residual
+    return F.relu(y) if relu == 2 else y

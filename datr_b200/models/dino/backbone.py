@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from datr_b200 import graphs
+from datr_b200 import linear as dl
 
 from datr_b200.util.misc import NestedTensor
 from .position_encoding import build_position_encoding
@@ -45,6 +46,25 @@ class FrozenBatchNorm2d(nn.Module):
         return torch.addcmul(shift.view(1, -1, 1, 1), x, scale.view(1, -1, 1, 1))
 
 
+def _pointwise_on_tensor_cores(x):
+    return (dl.get_mode() == "tf32" and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def _conv1x1_bn(x, conv, bn, relu, residual=None):
+    """FrozenBN(conv1x1(x)) [+ residual] with optional ReLU on an NHWC tensor, as one fused GEMM over pixels."""
+    assert conv.kernel_size == (1, 1) and conv.padding == (0, 0) and conv.groups == 1 and conv.bias is None
+    if conv.stride != (1, 1):
+        x = x[:, :, ::conv.stride[0], ::conv.stride[1]].contiguous(memory_format=torch.channels_last)
+    n, cin, h, w = x.shape
+    cout = conv.out_channels
+    scale, shift = bn.scale_shift()
+    weight = conv.weight.reshape(cout, cin) * scale[:, None]
+    res = residual.permute(0, 2, 3, 1).reshape(-1, cout) if residual is not None else None
+    y = dl.linear(x.permute(0, 2, 3, 1).reshape(-1, cin), weight, shift, relu=relu, residual=res)
+    return y.view(n, h, w, cout).permute(0, 3, 1, 2)
+
+
 class Bottleneck(nn.Module):
     expansion = 4
 
@@ -60,6 +80,14 @@ class Bottleneck(nn.Module):
         self.stride = stride
 
     def forward(self, x):
+        if _pointwise_on_tensor_cores(x):
+            # NHWC activations: the three 1x1 convolutions are GEMMs over pixels; FrozenBN folds into weight / bias
+            # and ReLU / the residual add ride in the tcgen05 kernel's epilogue (datr_b200.linear); 3x3 stays cuDNN
+            y = _conv1x1_bn(x, self.conv1, self.bn1, relu=1)
+            y = F.relu(self.bn2(self.conv2(y)))
+            if self.downsample is not None:
+                x = _conv1x1_bn(x, self.downsample[0], self.downsample[1], relu=0)
+            return _conv1x1_bn(y, self.conv3, self.bn3, relu=2, residual=x)
         y = F.relu(self.bn1(self.conv1(x)))
         y = F.relu(self.bn2(self.conv2(y)))
         y = self.bn3(self.conv3(y))

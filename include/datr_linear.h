@@ -5,12 +5,17 @@
  *                         called from the reference's models/dino/ops/modules/ms_deform_attn.py:94-125
  *                         (value_proj, sampling_offsets, attention_weights, output_proj) and
  *                         models/dino/deformable_transformer.py:784-805, :941-947 (linear1 + activation, linear2),
- *                         with the bias add, the ReLU and the residual add that follow it fused into the epilogue.
+ *                         with the bias add, the ReLU and the residual add that follow it fused into the epilogue;
+ *                         and the 1x1 convolutions of the ResNet-50 bottlenecks on NHWC activations
+ *                         (models/dino/backbone.py:97 -> torchvision Bottleneck conv1 / conv3 / downsample) with the
+ *                         FrozenBatchNorm2d affine (backbone.py:62-72) folded into weight and bias.
  *
- *   y[M,N] = act( x[M,K] . w[N,K]^T + bias[N] ) + residual[M,N]
+ *   relu == 0:  y[M,N] =        x[M,K] . w[N,K]^T + bias[N]   + residual[M,N]
+ *   relu == 1:  y[M,N] = max(0, x[M,K] . w[N,K]^T + bias[N] ) + residual[M,N]      (FFN linear1)
+ *   relu == 2:  y[M,N] = max(0, x[M,K] . w[N,K]^T + bias[N]   + residual[M,N] )    (ResNet bottleneck output)
  *
  * All buffers are fp32 device memory, row-major, contiguous, 16-byte aligned, owned by the caller; `bias` and
- * `residual` may be NULL; relu != 0 applies max(.,0) before the residual add.  Requirements: K % 32 == 0, N % 4 == 0.
+ * `residual` may be NULL.  Requirements: K % 32 == 0, N % 4 == 0.
  * Products are TF32 (10-bit mantissa, round-to-nearest on the TMA load), accumulation is fp32.  Work is enqueued on
  * `stream` (cudaStream_t as void*), no host synchronisation.  Returns 0 or a negative code;
  * datr_linear_last_error() gives the calling thread's message.  There is no CPU implementation.

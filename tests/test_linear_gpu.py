@@ -90,3 +90,66 @@ def test_ineligible_shapes_and_cpu_fall_to_torch_semantics():
     finally:
         dl.set_mode("fp32")
     assert rel(y, x.double() @ w.double().t() + b.double()) < REL_TF32
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 256, 64), (333, 512, 256)])
+def test_relu_after_residual_mode(M, N, K):
+    """relu == 2 (ResNet bottleneck output): y = max(0, x W^T + b + r); forward and all four gradients."""
+    from datr_b200 import linear as dl
+    x, w, b, r = make(M, N, K, True, True, 31 + M)
+    g = torch.randn(M, N, generator=torch.Generator(device="cpu").manual_seed(6)).cuda()
+    leaves = [t.clone().requires_grad_(True) for t in (x, w, b, r)]
+    dl.set_mode("tf32")
+    try:
+        y = dl.linear(leaves[0], leaves[1], leaves[2], relu=2, residual=leaves[3])
+        y.backward(g)
+    finally:
+        dl.set_mode("fp32")
+    ref = [t.double().clone().requires_grad_(True) for t in (x, w, b, r)]
+    z = ref[0] @ ref[1].t() + ref[2] + ref[3]
+    assert rel(y.detach(), z.detach().clamp_min(0)) < REL_TF32
+    (z * (y.detach() > 0)).backward(g.double())
+    for got, want in zip(leaves, ref):
+        assert rel(got.grad, want.grad) < REL_TF32
+
+
+def test_resnet_bottleneck_pointwise_path_matches_cudnn():
+    """NHWC bottleneck with the 1x1 convolutions + FrozenBN (+ReLU, +residual) on the tcgen05 kernel vs the same
+    block on cuDNN: output and gradients within the tensor-core bar."""
+    from datr_b200 import linear as dl, native
+    from datr_b200.models.dino.backbone import Bottleneck, FrozenBatchNorm2d
+    torch.manual_seed(0)
+    down = torch.nn.Sequential(torch.nn.Conv2d(64, 256, 1, stride=2, bias=False), FrozenBatchNorm2d(256))
+    blk = Bottleneck(64, 64, stride=2, downsample=down).cuda()
+    for m in blk.modules():
+        if isinstance(m, FrozenBatchNorm2d):
+            m.weight.uniform_(0.5, 1.5); m.bias.normal_(); m.running_mean.normal_(); m.running_var.uniform_(0.5, 2.0)
+    blk = blk.to(memory_format=torch.channels_last)
+    x = torch.randn(2, 64, 38, 50, device="cuda").contiguous(memory_format=torch.channels_last)
+    g = torch.randn(2, 256, 19, 25, device="cuda").contiguous(memory_format=torch.channels_last)
+    torch.backends.cudnn.allow_tf32 = False
+
+    def run(mode):
+        dl.set_mode(mode)
+        try:
+            xa = x.clone().requires_grad_(True)
+            blk.zero_grad()
+            y = blk(xa)
+            y.backward(g)
+        finally:
+            dl.set_mode("fp32")
+        return [y.detach(), xa.grad] + [p.grad.clone() for p in blk.parameters()]
+
+    n0 = native.linear_launch_count()
+    got = run("tf32")
+    assert native.linear_launch_count() - n0 >= 6
+    want = run("fp32")
+    errs = [rel(a, b.double()) for a, b in zip(got, want)]
+    assert errs[0] < 5e-3, errs                     # forward output
+    # gradients cross three ReLUs whose active sets differ for a few near-zero pre-activations (TF32 vs fp32 products):
+    # isolated elements move by one path's worth.  With TF32 noise ~3e-4 of the pre-activation scale about 2e-4 of
+    # the units flip, i.e. an L2 error near sqrt(2e-4) = 1.4e-2 (measured 1.2-1.4e-2 on every gradient); the masked
+    # single-layer tests above pin the kernels themselves at 2e-3.
+    l2 = [float((a.double() - b.double()).norm() / b.double().norm()) for a, b in zip(got[1:], want[1:])]
+    assert max(l2) < 3e-2, (l2, errs)
+    assert max(errs[1:]) < 0.15, errs
