@@ -347,7 +347,7 @@ def main():
         sampler.start()
     from datr_b200 import linear as DL
     MSDA._timers = DL._timers = []
-    n0 = native.launch_count() + native.linear_launch_count() + native.layernorm_launch_count()
+    n0 = native.all_launch_count()
     g0 = getattr(getattr(wl, "graphs", None), "replayed_native_launches", 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -356,7 +356,7 @@ def main():
         wl.step()
     e1.record()
     barrier()
-    launches = native.launch_count() + native.linear_launch_count() + native.layernorm_launch_count() - n0
+    launches = native.all_launch_count() - n0
     timers, MSDA._timers, DL._timers = MSDA._timers, None, None
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None

@@ -29,7 +29,7 @@ ACTIVE = None          # a StepGraphs instance when graph replay is enabled
 
 
 def _native_launches():
-    return native.launch_count() + native.linear_launch_count() + native.layernorm_launch_count()
+    return native.all_launch_count()
 
 
 class StepGraphs:

@@ -71,6 +71,25 @@ def _c(t):
     return t if t.is_contiguous() and t.data_ptr() % 16 == 0 else t.contiguous()
 
 
+def _colsum(g2, y_act=None):
+    """Bias gradient sum_rows g2 (csrc/colsum.cu).  With `y_act` the ReLU mask (y_act > 0) is applied first and the
+    masked gradient is returned too: (dz, db)."""
+    M, N = g2.shape
+    lib = native.lib()
+    db = torch.empty(N, dtype=torch.float32, device=g2.device)
+    with torch.cuda.device(g2.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        if y_act is None:
+            rc = lib.datr_colsum(g2.data_ptr(), db.data_ptr(), M, N, stream)
+            dz = g2
+        else:
+            dz = torch.empty_like(g2)
+            rc = lib.datr_relu_bwd_colsum(g2.data_ptr(), y_act.data_ptr(), dz.data_ptr(), db.data_ptr(), M, N, stream)
+    if rc != 0:
+        raise RuntimeError(f"datr_colsum failed (code {rc}): {lib.datr_colsum_last_error().decode()}")
+    return dz, db
+
+
 class _LinearTF32(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, relu):
@@ -91,18 +110,27 @@ class _LinearTF32(torch.autograd.Function):
         x2, w, y, r2 = ctx.saved_tensors
         N, K = w.shape
         g2 = _c(gy.reshape(-1, N))
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        gb = None
         if ctx.relu == 2:     # ReLU after the residual add: the mask applies to both branches
-            g2 = torch.ops.aten.threshold_backward(g2, y, 0.0)
+            if want_gb:
+                g2, gb = _colsum(g2, y)
+            else:
+                g2 = torch.ops.aten.threshold_backward(g2, y, 0.0)
         gres = g2.view(ctx.rshape) if ctx.has_res else None
-        if ctx.relu == 1:     # one fused mask kernel (ATen's ReLU backward) instead of compare + multiply
-            g2 = torch.ops.aten.threshold_backward(g2, y if r2 is None else y - r2, 0.0)
-        gx = gw = gb = None
+        if ctx.relu == 1:     # ReLU mask (+ bias gradient) in one pass
+            act = y if r2 is None else y - r2
+            if want_gb:
+                g2, gb = _colsum(g2, act)
+            else:
+                g2 = torch.ops.aten.threshold_backward(g2, act, 0.0)
+        if want_gb and gb is None:
+            gb = _colsum(g2)[1]
+        gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = _launch(g2, _c(w.t()), None, None, False).view(ctx.xshape) if N % 32 == 0 and K % 4 == 0 else (g2 @ w).view(ctx.xshape)
         if ctx.needs_input_grad[1]:
             gw = g2.t() @ x2
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g2.sum(0)
         return gx, gw, gb, gres, None
 
 

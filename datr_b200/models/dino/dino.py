@@ -29,7 +29,7 @@ from .backbone import build_backbone
 from .DA_utils import FCDiscriminator_img, decompose_features, get_prototype_class_wise, grad_reverse
 from .deformable_transformer import build_deformable_transformer
 from .dn_components import dn_post_process, prepare_for_cdn
-from .matcher import build_matcher
+from .matcher import build_matcher, match_many
 from .utils import MLP, sigmoid_focal_loss
 
 
@@ -367,8 +367,14 @@ class SetCriterion(nn.Module):
             outputs_without_aux = {k: v for k, v in outputs.items() if k != "aux_outputs"}
             device = next(iter(outputs.values())).device
 
+        key_aux = "aux_outputs_target" if target_domain_flag else "aux_outputs"
+        key_interm = "interm_outputs_target" if target_domain_flag else "interm_outputs"
+        pre = None
         if len(targets) > 0:
-            indices = self.matcher(outputs_without_aux, targets)
+            # all matchings of the step (final, auxiliary decoder layers, intermediate) in one batched pass
+            sets = [outputs_without_aux] + list(outputs.get(key_aux, [])) + ([outputs[key_interm]] if key_interm in outputs else [])
+            pre = match_many(self.matcher, sets, targets)
+            indices = pre[0]
             num_boxes = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=device)
             indices0, indices_list = indices, []
         else:       # no pseudo labels on this rank: still take part in the collective below
@@ -399,10 +405,9 @@ class SetCriterion(nn.Module):
                 losses.update({k: torch.as_tensor(0.0, device=device) for k in dn_zero})
             losses.update(self._group(outputs, targets, indices, num_boxes, "", log_labels=True))
 
-        key_aux = "aux_outputs_target" if target_domain_flag else "aux_outputs"
         if key_aux in outputs:
             for i, aux in enumerate(outputs[key_aux]):
-                indices = self.matcher(aux, targets)
+                indices = pre[1 + i]
                 if return_indices:
                     indices_list.append(indices)
                 losses.update(self._group(aux, targets, indices, num_boxes, f"_{i}"))
@@ -412,10 +417,9 @@ class SetCriterion(nn.Module):
                     else:
                         losses.update({f"{k}_{i}": torch.as_tensor(0.0, device=device) for k in dn_zero})
 
-        key_interm = "interm_outputs_target" if target_domain_flag else "interm_outputs"
         if key_interm in outputs:
             interm = outputs[key_interm]
-            indices = self.matcher(interm, targets)
+            indices = pre[1 + len(outputs.get(key_aux, []))]
             if return_indices:
                 indices_list.append(indices)
             losses.update(self._group(interm, targets, indices, num_boxes, "_interm"))

@@ -43,6 +43,27 @@ class HungarianMatcher(nn.Module):
         return [(torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)) for i, j in pairs]
 
 
+def match_many(matcher, outputs_list, targets):
+    """Assignments for several prediction sets against the same targets with ONE cost-matrix pass and ONE device->host
+    copy: the sets are stacked along the batch axis, which leaves every row of the cost matrix -- and so
+    every assignment -- bit-identical to matching them one by one (the reference does 7 matchings with 7 syncs per
+    step, dino.py:723-933 / matcher.py:91).  Returns one index list per prediction set."""
+    same = all(o["pred_logits"].shape == outputs_list[0]["pred_logits"].shape for o in outputs_list)
+    if not isinstance(matcher, HungarianMatcher) or not same or len(outputs_list) == 1:
+        return [matcher(o, targets) for o in outputs_list]
+    bs = outputs_list[0]["pred_logits"].shape[0]
+    stacked = {"pred_logits": torch.cat([o["pred_logits"] for o in outputs_list], 0),
+               "pred_boxes": torch.cat([o["pred_boxes"] for o in outputs_list], 0)}
+    with torch.no_grad():
+        C, sizes = _cost_matrix(stacked, targets, matcher.cost_class, matcher.cost_bbox, matcher.cost_giou, matcher.focal_alpha)
+        C = C.cpu()
+    out = []
+    for g in range(len(outputs_list)):
+        pairs = [linear_sum_assignment(c[g * bs + i]) for i, c in enumerate(C.split(sizes, -1))]
+        out.append([(torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)) for i, j in pairs])
+    return out
+
+
 class SimpleMinsumMatcher(nn.Module):
     def __init__(self, cost_class: float = 1, cost_bbox: float = 1, cost_giou: float = 1, focal_alpha=0.25):
         super().__init__()

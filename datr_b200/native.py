@@ -14,7 +14,7 @@ import threading
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SOURCES = [os.path.join(_PKG, "csrc", "msda.cu"), os.path.join(_PKG, "csrc", "linear_tf32.cu"),
-           os.path.join(_PKG, "csrc", "layernorm.cu")]
+           os.path.join(_PKG, "csrc", "layernorm.cu"), os.path.join(_PKG, "csrc", "colsum.cu")]
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -22,7 +22,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_last_error", "datr_abi_version",
            "datr_launch_count", "datr_linear_tf32", "datr_linear_last_error", "datr_linear_launch_count",
-           "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count")
+           "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count",
+           "datr_colsum", "datr_relu_bwd_colsum", "datr_colsum_last_error", "datr_colsum_launch_count")
 
 _lock = threading.Lock()
 _lib = None
@@ -89,6 +90,12 @@ def lib() -> ctypes.CDLL:
         L.datr_layernorm256_backward.argtypes = [vp] * 9 + [i, vp]
         L.datr_layernorm_last_error.restype = ctypes.c_char_p
         L.datr_layernorm_launch_count.restype = ctypes.c_uint64
+        L.datr_colsum.restype = i
+        L.datr_colsum.argtypes = [vp, vp, i, i, vp]
+        L.datr_relu_bwd_colsum.restype = i
+        L.datr_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, i, i, vp]
+        L.datr_colsum_last_error.restype = ctypes.c_char_p
+        L.datr_colsum_launch_count.restype = ctypes.c_uint64
         if L.datr_abi_version() != 1:
             raise NativeLibraryError("libdatr_b200.so ABI version mismatch; rebuild")
         _lib = L
@@ -98,6 +105,16 @@ def lib() -> ctypes.CDLL:
 def launch_count() -> int:
     """MSDeformAttn kernel launches issued through the library by this process."""
     return int(lib().datr_launch_count())
+
+
+def colsum_launch_count() -> int:
+    """Bias-gradient (column-sum) kernel launches issued through the library by this process."""
+    return int(lib().datr_colsum_launch_count())
+
+
+def all_launch_count() -> int:
+    """Every hand-written kernel launch issued through the library by this process."""
+    return launch_count() + linear_launch_count() + layernorm_launch_count() + colsum_launch_count()
 
 
 def layernorm_launch_count() -> int:
