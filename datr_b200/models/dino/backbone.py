@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from datr_b200 import graphs
+from datr_b200 import conv as dconv
 from datr_b200 import linear as dl
 
 from datr_b200.util.misc import NestedTensor
@@ -84,7 +85,12 @@ class Bottleneck(nn.Module):
             # NHWC activations: the three 1x1 convolutions are GEMMs over pixels; FrozenBN folds into weight / bias
             # and ReLU / the residual add ride in the tcgen05 kernel's epilogue (datr_b200.linear); 3x3 stays cuDNN
             y = _conv1x1_bn(x, self.conv1, self.bn1, relu=1)
-            y = F.relu(self.bn2(self.conv2(y)))
+            if dconv.eligible(y, self.conv2):
+                # conv2 + FrozenBN + ReLU: im2col-free implicit GEMM (4-D TMA box per tap, datr_b200.conv)
+                scale, shift = self.bn2.scale_shift()
+                y = dconv.conv3x3_bias_relu(y, self.conv2.weight * scale.view(-1, 1, 1, 1), shift, self.conv2.stride[0])
+            else:
+                y = F.relu(self.bn2(self.conv2(y)))
             if self.downsample is not None:
                 x = _conv1x1_bn(x, self.downsample[0], self.downsample[1], relu=0)
             return _conv1x1_bn(y, self.conv3, self.bn3, relu=2, residual=x)

@@ -276,7 +276,13 @@ class SetCriterion(nn.Module):
     @torch.no_grad()
     def loss_cardinality(self, outputs, targets, indices, num_boxes):
         logits = outputs["pred_logits"]
-        n_tgt = torch.as_tensor([len(v["labels"]) for v in targets], device=logits.device)
+        counts = [len(v["labels"]) for v in targets]
+        cached = getattr(self, "_n_tgt", None)          # one host->device copy per criterion call, not one per group
+        if cached is not None and cached[0] == counts and cached[1].device == logits.device:
+            n_tgt = cached[1]
+        else:
+            n_tgt = torch.as_tensor(counts, device=logits.device)
+            self._n_tgt = (counts, n_tgt)
         n_pred = (logits.argmax(-1) != logits.shape[-1] - 1).sum(1)
         return {"cardinality_error": F.l1_loss(n_pred.float(), n_tgt.float())}
 

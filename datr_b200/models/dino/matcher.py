@@ -57,10 +57,26 @@ def match_many(matcher, outputs_list, targets):
     with torch.no_grad():
         C, sizes = _cost_matrix(stacked, targets, matcher.cost_class, matcher.cost_bbox, matcher.cost_giou, matcher.focal_alpha)
         C = C.cpu()
-    out = []
-    for g in range(len(outputs_list)):
-        pairs = [linear_sum_assignment(c[g * bs + i]) for i, c in enumerate(C.split(sizes, -1))]
-        out.append([(torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)) for i, j in pairs])
+    pairs = [[linear_sum_assignment(c[g * bs + i]) for i, c in enumerate(C.split(sizes, -1))]
+             for g in range(len(outputs_list))]
+    # all index vectors travel to the device in ONE pinned, asynchronous copy (the losses index device tensors with
+    # them; CPU index tensors would cost a pageable host->device copy per use, ~40 per step)
+    import numpy as np
+    flat = np.concatenate([np.asarray(v, dtype=np.int64) for grp in pairs for ij in grp for v in ij]) \
+        if any(len(ij[0]) for grp in pairs for ij in grp) else np.zeros(0, dtype=np.int64)
+    dev = stacked["pred_logits"].device
+    host = torch.from_numpy(flat)
+    if dev.type == "cuda":
+        host = host.pin_memory()
+    flat_dev = host.to(dev, non_blocking=True)
+    out, off = [], 0
+    for grp in pairs:
+        cur = []
+        for i, j in grp:
+            n = len(i)
+            cur.append((flat_dev[off:off + n], flat_dev[off + n:off + 2 * n]))
+            off += 2 * n
+        out.append(cur)
     return out
 
 

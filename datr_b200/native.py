@@ -14,7 +14,8 @@ import threading
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SOURCES = [os.path.join(_PKG, "csrc", "msda.cu"), os.path.join(_PKG, "csrc", "linear_tf32.cu"),
-           os.path.join(_PKG, "csrc", "layernorm.cu"), os.path.join(_PKG, "csrc", "colsum.cu")]
+           os.path.join(_PKG, "csrc", "layernorm.cu"), os.path.join(_PKG, "csrc", "colsum.cu"),
+           os.path.join(_PKG, "csrc", "conv3x3_tf32.cu")]
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -23,7 +24,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_last_error", "datr_abi_version",
            "datr_launch_count", "datr_linear_tf32", "datr_linear_last_error", "datr_linear_launch_count",
            "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count",
-           "datr_colsum", "datr_relu_bwd_colsum", "datr_colsum_last_error", "datr_colsum_launch_count")
+           "datr_colsum", "datr_relu_bwd_colsum", "datr_colsum_last_error", "datr_colsum_launch_count",
+           "datr_conv3x3_nhwc_tf32", "datr_conv_last_error", "datr_conv_launch_count")
 
 _lock = threading.Lock()
 _lib = None
@@ -37,7 +39,8 @@ def _stale() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = SOURCES + [os.path.join(INCLUDE_DIR, f) for f in os.listdir(INCLUDE_DIR)]
+    deps = SOURCES + [os.path.join(INCLUDE_DIR, f) for f in os.listdir(INCLUDE_DIR)] \
+        + [os.path.join(_PKG, "csrc", f) for f in os.listdir(os.path.join(_PKG, "csrc")) if f.endswith(".cuh")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -96,6 +99,10 @@ def lib() -> ctypes.CDLL:
         L.datr_relu_bwd_colsum.argtypes = [vp, vp, vp, vp, i, i, vp]
         L.datr_colsum_last_error.restype = ctypes.c_char_p
         L.datr_colsum_launch_count.restype = ctypes.c_uint64
+        L.datr_conv3x3_nhwc_tf32.restype = i
+        L.datr_conv3x3_nhwc_tf32.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
+        L.datr_conv_last_error.restype = ctypes.c_char_p
+        L.datr_conv_launch_count.restype = ctypes.c_uint64
         if L.datr_abi_version() != 1:
             raise NativeLibraryError("libdatr_b200.so ABI version mismatch; rebuild")
         _lib = L
@@ -114,7 +121,13 @@ def colsum_launch_count() -> int:
 
 def all_launch_count() -> int:
     """Every hand-written kernel launch issued through the library by this process."""
-    return launch_count() + linear_launch_count() + layernorm_launch_count() + colsum_launch_count()
+    return (launch_count() + linear_launch_count() + layernorm_launch_count() + colsum_launch_count()
+            + conv_launch_count())
+
+
+def conv_launch_count() -> int:
+    """Implicit-GEMM 3x3 convolution kernel launches issued through the library by this process."""
+    return int(lib().datr_conv_launch_count())
 
 
 def layernorm_launch_count() -> int:

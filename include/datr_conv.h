@@ -1,0 +1,35 @@
+/*
+ * datr_conv.h -- C ABI of the implicit-GEMM 3x3 convolution of libdatr_b200.so (sm_100a: 4-D TMA + tcgen05 + TMEM).
+ *
+ *   datr_conv3x3_nhwc_tf32  <-  conv2 (3x3, padding 1, stride 1 or 2, no bias) of the ResNet-50 bottlenecks the
+ *                               reference's backbone runs through cuDNN (models/dino/backbone.py:97 ->
+ *                               torchvision.models.resnet Bottleneck.conv2), followed by FrozenBatchNorm2d
+ *                               (backbone.py:62-72; folded into `w` and `bias` by the caller) and ReLU.
+ *
+ *   y[n, oy, ox, co] = act( bias[co] + sum_{ky,kx,ci} x[n, s*oy + ky - 1, s*ox + kx - 1, ci] * w[co, ky, kx, ci] )
+ *
+ * x [N,H,W,Cin], w [Cout,3,3,Cin], y [N,Ho,Wo,Cout] (Ho = (H-1)/s + 1, Wo likewise): fp32, contiguous (NHWC /
+ * channels_last), 16-byte aligned, caller-owned device memory; bias [Cout] may be NULL; Cin % 32 == 0, Cout % 4 == 0.
+ * TF32 products, fp32 accumulation.  Work is enqueued on `stream`; returns 0 or a negative code.
+ * Forward only: the gradients of this layer are taken with the library convolution-backward routines.
+ */
+#ifndef DATR_CONV_H_
+#define DATR_CONV_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { DATR_CONV_OK = 0, DATR_CONV_ERR_BAD_ARGUMENT = -1, DATR_CONV_ERR_ALIGNMENT = -2, DATR_CONV_ERR_CUDA = -3 };
+
+int datr_conv3x3_nhwc_tf32(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Cin,
+                           int Cout, int stride, int relu, void* stream);
+const char* datr_conv_last_error(void);
+uint64_t datr_conv_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DATR_CONV_H_ */
