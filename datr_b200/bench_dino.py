@@ -128,7 +128,7 @@ class DinoStep:
         return {"loss": float(self.last_loss.detach()) if self.last_loss is not None else None,
                 "grad_allreduce_bytes": self.grads.numel * 4,
                 "cuda_graphs": None if self.graphs is None else {"segments": self.graphs.captures,
-                                                                 "what": "ResNet body, encoder x2, decoder x2 (forward + backward)"}}
+                                                                 "what": "ResNet body, encoder x2, two-stage selection x2, decoder x2, heads, image discriminator, criterion losses (forward + backward each)"}}
 
 
 def reference_arm(args, threads):

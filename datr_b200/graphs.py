@@ -43,15 +43,22 @@ class StepGraphs:
     def begin_step(self):
         self.calls.clear()
 
-    def run(self, name, make_module, args):
+    def call(self, name, owner, fn, *args):
+        """Run `fn(*args)` (args: any pytree of tensors and hashable constants; `owner`: the nn.Module whose
+        parameters fn uses, or None) as a graph segment; returns fn's output pytree."""
+        return _call_segment(self, name, owner, fn, args)
+
+    def run(self, name, make_module, args, key_extra=(), want_module=False):
         """Run segment `name` on tensor arguments `args` through its graph (capturing it on first use)."""
         idx = self.calls.get(name, 0)
         self.calls[name] = idx + 1
-        key = (name, idx, torch.is_grad_enabled()) + tuple((tuple(a.shape), a.dtype, a.requires_grad) for a in args)
+        key = (name, idx, torch.is_grad_enabled(), key_extra) + tuple((tuple(a.shape), a.dtype, a.requires_grad) for a in args)
         entry = self.cache.get(key)
         if entry is None:
             if not torch.is_grad_enabled():
-                return make_module()(*args)              # inference passes stay eager
+                module = make_module()                   # inference passes stay eager
+                out = module(*args)
+                return (out, module) if want_module else out
             module = make_module()
             sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
             n0 = _native_launches()
@@ -63,7 +70,53 @@ class StepGraphs:
             self.captures += 1
         graphed, per_pair = entry
         self.replayed_native_launches += per_pair
-        return graphed(*args)
+        out = graphed(*args)
+        return (out, graphed) if want_module else out
+
+
+class FnSegment(nn.Module):
+    """A pure function of a pytree of tensors (plus constants) run as a graph segment.  `owner` supplies the
+    parameters the function may touch (their gradients come back from the graphed backward); non-tensor leaves of the
+    arguments are baked into the capture and are part of the cache key."""
+
+    def __init__(self, owner, fn, spec, consts, n_leaves):
+        super().__init__()
+        self.owner = owner                      # registers the owner's parameters with this segment
+        self._fn, self._spec, self._consts, self._n = fn, spec, dict(consts), n_leaves
+        self.out_spec, self.out_consts = None, None
+        if owner is not None:
+            self.train(owner.training)
+
+    def forward(self, *tensors):
+        from torch.utils import _pytree as pytree
+        it = iter(tensors)
+        leaves = [self._consts[i] if i in self._consts else next(it) for i in range(self._n)]
+        out = self._fn(*pytree.tree_unflatten(leaves, self._spec))
+        flat, spec = pytree.tree_flatten(out)
+        self.out_spec = spec
+        self.out_consts = {i: l for i, l in enumerate(flat) if not isinstance(l, torch.Tensor)}
+        self.out_n = len(flat)
+        return tuple(l for l in flat if isinstance(l, torch.Tensor))
+
+
+def _call_segment(sg: "StepGraphs", name, owner, fn, args):
+    from torch.utils import _pytree as pytree
+    leaves, spec = pytree.tree_flatten(args)
+    consts = tuple((i, l) for i, l in enumerate(leaves) if not isinstance(l, torch.Tensor))
+    tensors = tuple(l for l in leaves if isinstance(l, torch.Tensor))
+    holder = {}
+
+    def make():
+        holder["m"] = FnSegment(owner, fn, spec, consts, len(leaves))
+        return holder["m"]
+
+    key_extra = (repr(spec), repr(consts))
+    out_tensors, module = sg.run(name, make, tensors, key_extra=key_extra, want_module=True)
+    if not isinstance(out_tensors, tuple):
+        out_tensors = (out_tensors,)
+    it = iter(out_tensors)
+    flat = [module.out_consts[i] if i in module.out_consts else next(it) for i in range(module.out_n)]
+    return pytree.tree_unflatten(flat, module.out_spec)
 
 
 class BodySegment(nn.Module):

@@ -16,7 +16,6 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from datr_b200 import graphs
 from datr_b200 import conv as dconv
 from datr_b200 import linear as dl
 
@@ -176,11 +175,7 @@ class BackboneBase(nn.Module):
         self.num_channels = num_channels
 
     def forward(self, tensor_list: NestedTensor):
-        if graphs.ACTIVE is not None and tensor_list.tensors.is_cuda:
-            keys = list(self.body.return_layers.values())
-            feats = dict(zip(keys, graphs.ACTIVE.run("body", lambda: graphs.BodySegment(self.body), (tensor_list.tensors,))))
-        else:
-            feats = self.body(tensor_list.tensors)
+        feats = self.body(tensor_list.tensors)
         m = tensor_list.mask
         assert m is not None
         out: Dict[str, NestedTensor] = {}

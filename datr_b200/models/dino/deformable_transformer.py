@@ -388,6 +388,38 @@ class DeformableTransformer(nn.Module):
             self.refpoint_embed.weight.data[:, :2] = inverse_sigmoid(self.refpoint_embed.weight.data[:, :2])
             self.refpoint_embed.weight.data[:, :2].requires_grad = False
 
+    def _select_queries(self, memory, mask_flat, refpoint_embed, tgt, shapes_list):
+        """Two-stage query selection (pure device work): encoder proposals -> top-k -> decoder queries / references,
+        concatenated behind the de-noising queries.  Returns (refpoints_unsigmoid, tgt, tgt_undetach, refpoint_undetach,
+        init_box_proposal, output_memory, coord_all, output_proposals); unused entries are None."""
+        bs = memory.shape[0]
+        tgt_undetach = refpoint_undetach = output_memory = coord_all = output_proposals = None
+        if self.two_stage_type == "standard":
+            input_hw = self.two_stage_wh_embedding.weight[0] if self.two_stage_learn_wh else None
+            output_memory, output_proposals = gen_encoder_output_proposals(memory, mask_flat, shapes_list, input_hw)
+            output_memory = ln(self.enc_output_norm, dl.linear(output_memory, self.enc_output.weight, self.enc_output.bias))
+            class_all = self.enc_out_class_embed(output_memory)
+            topk = torch.topk(class_all.max(-1)[0], self.num_queries, dim=1)[1]               # [N,nq] int64
+            tgt_undetach = torch.gather(output_memory, 1, topk.unsqueeze(-1).expand(-1, -1, self.d_model))
+            prop_sel = torch.gather(output_proposals, 1, topk.unsqueeze(-1).expand(-1, -1, 4))
+            refpoint_undetach = self.enc_out_bbox_embed(tgt_undetach) + prop_sel              # logits
+            refpoint_sel = refpoint_undetach.detach()
+            init_box_proposal = prop_sel.sigmoid()
+            tgt_sel = self.tgt_embed.weight[None].expand(bs, -1, -1) if self.embed_init_tgt else tgt_undetach.detach()
+            if self.two_stage_keep_all_tokens:
+                coord_all = self.enc_out_bbox_embed(output_memory) + output_proposals
+        else:
+            tgt_sel = self.tgt_embed.weight[None].expand(bs, -1, -1)
+            refpoint_sel = self.refpoint_embed.weight[None].expand(bs, -1, -1)
+            init_box_proposal = refpoint_sel.sigmoid()
+        if refpoint_embed is not None:
+            refpoint_embed = torch.cat([refpoint_embed, refpoint_sel], dim=1)
+            tgt = torch.cat([tgt, tgt_sel], dim=1)
+        else:
+            refpoint_embed, tgt = refpoint_sel, tgt_sel.contiguous()   # materialise the broadcast of the embedding
+
+        return refpoint_embed, tgt, tgt_undetach, refpoint_undetach, init_box_proposal, output_memory, coord_all, output_proposals
+
     def forward(self, srcs, masks, refpoint_embed, pos_embeds, tgt, attn_mask=None):
         """srcs / pos_embeds: per level [N,C,H,W]; masks: per level [N,H,W] (True = padding);
         refpoint_embed [N,n_dn,4] / tgt [N,n_dn,C]: de-noising queries (None at inference).
@@ -419,29 +451,12 @@ class DeformableTransformer(nn.Module):
                                         spatial_shapes=spatial_shapes, valid_ratios=valid_ratios,
                                         key_padding_mask=mask_flat, shapes_list=shapes_list)
 
-        if self.two_stage_type == "standard":
-            input_hw = self.two_stage_wh_embedding.weight[0] if self.two_stage_learn_wh else None
-            output_memory, output_proposals = gen_encoder_output_proposals(memory, mask_flat, shapes_list, input_hw)
-            output_memory = ln(self.enc_output_norm, dl.linear(output_memory, self.enc_output.weight, self.enc_output.bias))
-            class_all = self.enc_out_class_embed(output_memory)
-            topk = torch.topk(class_all.max(-1)[0], self.num_queries, dim=1)[1]               # [N,nq] int64
-            tgt_undetach = torch.gather(output_memory, 1, topk.unsqueeze(-1).expand(-1, -1, self.d_model))
-            prop_sel = torch.gather(output_proposals, 1, topk.unsqueeze(-1).expand(-1, -1, 4))
-            refpoint_undetach = self.enc_out_bbox_embed(tgt_undetach) + prop_sel              # logits
-            refpoint_sel = refpoint_undetach.detach()
-            init_box_proposal = prop_sel.sigmoid()
-            tgt_sel = self.tgt_embed.weight[None].expand(bs, -1, -1) if self.embed_init_tgt else tgt_undetach.detach()
-            if self.two_stage_keep_all_tokens:
-                coord_all = self.enc_out_bbox_embed(output_memory) + output_proposals
+        if graphs.ACTIVE is not None and memory.is_cuda:
+            sel = graphs.ACTIVE.call("two_stage", self, self._select_queries, memory, mask_flat, refpoint_embed, tgt,
+                                     tuple(shapes_list))
         else:
-            tgt_sel = self.tgt_embed.weight[None].expand(bs, -1, -1)
-            refpoint_sel = self.refpoint_embed.weight[None].expand(bs, -1, -1)
-            init_box_proposal = refpoint_sel.sigmoid()
-        if refpoint_embed is not None:
-            refpoint_embed = torch.cat([refpoint_embed, refpoint_sel], dim=1)
-            tgt = torch.cat([tgt, tgt_sel], dim=1)
-        else:
-            refpoint_embed, tgt = refpoint_sel, tgt_sel
+            sel = self._select_queries(memory, mask_flat, refpoint_embed, tgt, tuple(shapes_list))
+        refpoint_embed, tgt, tgt_undetach, refpoint_undetach, init_box_proposal, output_memory, coord_all, output_proposals = sel
 
         if graphs.ACTIVE is not None and tgt.is_cuda:
             dec_args = (tgt, memory, mask_flat, pos_flat, refpoint_embed, level_start_index, spatial_shapes, valid_ratios)

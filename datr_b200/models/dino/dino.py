@@ -21,6 +21,7 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from datr_b200 import graphs
 from datr_b200.util import box_ops
 from datr_b200.util.misc import (NestedTensor, accuracy, get_world_size, inverse_sigmoid,
                                  is_dist_avail_and_initialized, nested_tensor_from_tensor_list)
@@ -147,7 +148,23 @@ class DINO(nn.Module):
     # ------------------------------------------------------------------------------------------
     def _features(self, samples: NestedTensor):
         """Backbone + input projections (+ the extra stride-2 levels): per level (src, mask, pos)."""
+        if graphs.ACTIVE is not None and samples.tensors.is_cuda:
+            base = self.backbone[0]
+            feats = graphs.ACTIVE.run("body", lambda: graphs.BodySegment(base.body), (samples.tensors,))
+            srcs, masks, poss = graphs.ACTIVE.call("project", self, self._project, tuple(feats), samples.mask)
+            return list(srcs), list(masks), list(poss)
         features, poss = self.backbone(samples)
+        return self._project_levels(features, poss, samples.mask)
+
+    def _project(self, feats, mask):
+        """Everything between the ResNet body and the transformer as a pure tensor function: mask down-sampling
+        (BackboneBase.forward), sine position encoding (Joiner) and the input projections."""
+        features = [NestedTensor(x, F.interpolate(mask[None].float(), size=x.shape[-2:]).to(torch.bool)[0]) for x in feats]
+        poss = [self.backbone[1](f).to(f.tensors.dtype) for f in features]
+        srcs, masks, poss = self._project_levels(features, poss, mask)
+        return tuple(srcs), tuple(masks), tuple(poss)
+
+    def _project_levels(self, features, poss, full_mask):
         srcs, masks = [], []
         for l, feat in enumerate(features):
             src, mask = feat.decompose()
@@ -156,7 +173,7 @@ class DINO(nn.Module):
             masks.append(mask)
         for l in range(len(srcs), self.num_feature_levels):
             src = self.input_proj[l](features[-1].tensors if l == len(features) else srcs[-1])
-            mask = F.interpolate(samples.mask[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
+            mask = F.interpolate(full_mask[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
             poss.append(self.backbone[1](NestedTensor(src, mask)).to(src.dtype))
             srcs.append(src)
             masks.append(mask)
@@ -184,6 +201,28 @@ class DINO(nn.Module):
             feats, logits, self.num_classes, global_proto=self.global_proto.detach(), global_amount=self.Amount)
         return proto, present
 
+    def _image_discriminator(self, srcs_all):
+        """Image-level domain discriminator behind a gradient reversal, on every level of both domains: [2B, S, 1]."""
+        d_img = [self.D_img(grad_reverse(s)) for s in srcs_all]
+        return torch.cat([d.flatten(2).transpose(1, 2) for d in d_img], dim=1)
+
+    def _outputs_from(self, hs, reference, hs_enc, ref_enc, init_box_proposal, dn_meta):
+        """Decoder outputs -> the output dict (per-layer heads, de-noising split, auxiliary and intermediate sets):
+        pure device work."""
+        hs = list(hs)
+        hs[0] = hs[0] + self.label_enc.weight[0, 0] * 0.0        # keeps label_enc in the graph when there are no objects
+        outputs_class, outputs_coord = self._heads(hs, reference)
+        if self.dn_number > 0 and dn_meta is not None:
+            dn_meta = dict(dn_meta)
+            outputs_class, outputs_coord = dn_post_process(outputs_class, outputs_coord, dn_meta, self.aux_loss, self._set_aux_loss)
+        out = {"pred_logits": outputs_class[-1], "pred_boxes": outputs_coord[-1]}
+        if self.aux_loss:
+            out["aux_outputs"] = self._set_aux_loss(outputs_class, outputs_coord)
+        if hs_enc is not None:
+            self._interm(out, hs_enc, ref_enc, init_box_proposal)
+        out["dn_meta"] = dn_meta
+        return out
+
     def forward(self, samples: NestedTensor, targets: List = None, self_training_flag=False):
         """samples: NestedTensor (tensors [B,3,H,W], mask [B,H,W] True on padding), a tensor or a list of images.
         In training mode the first half of the batch is the source domain (with `targets`), the second half the
@@ -205,24 +244,20 @@ class DINO(nn.Module):
             srcs, masks, poss, srcs_all, masks_all, poss_all, srcs_t, masks_t, poss_t = decompose_features(srcs, masks, poss)
 
         hs, reference, hs_enc, ref_enc, init_box_proposal = self.transformer(srcs, masks, dn_bbox, poss, dn_label, attn_mask)
-        hs[0] = hs[0] + self.label_enc.weight[0, 0] * 0.0        # keeps label_enc in the graph when there are no objects
-
-        outputs_class, outputs_coord = self._heads(hs, reference)
-        if self.dn_number > 0 and dn_meta is not None:
-            outputs_class, outputs_coord = dn_post_process(outputs_class, outputs_coord, dn_meta, self.aux_loss, self._set_aux_loss)
-        out = {"pred_logits": outputs_class[-1], "pred_boxes": outputs_coord[-1]}
-        if self.aux_loss:
-            out["aux_outputs"] = self._set_aux_loss(outputs_class, outputs_coord)
-        if hs_enc is not None:
-            self._interm(out, hs_enc, ref_enc, init_box_proposal)
-        out["dn_meta"] = dn_meta
+        if graphs.ACTIVE is not None and hs[0].is_cuda:
+            out = graphs.ACTIVE.call("heads", self, self._outputs_from, tuple(hs), tuple(reference), hs_enc, ref_enc,
+                                     init_box_proposal, dn_meta)
+        else:
+            out = self._outputs_from(tuple(hs), tuple(reference), hs_enc, ref_enc, init_box_proposal, dn_meta)
         if not self.training:
             return out
 
         # ---- domain adaptation -----------------------------------------------------------------
         da = {}
-        d_img = [self.D_img(grad_reverse(s)) for s in srcs_all]                       # every level, both domains
-        da["backbone_DA"] = torch.cat([d.flatten(2).transpose(1, 2) for d in d_img], dim=1)
+        if graphs.ACTIVE is not None and srcs_all[0].is_cuda:
+            da["backbone_DA"] = graphs.ACTIVE.call("d_img", self, self._image_discriminator, tuple(srcs_all))
+        else:
+            da["backbone_DA"] = self._image_discriminator(tuple(srcs_all))
 
         pad = dn_meta["pad_size"] if dn_meta is not None else 0
         proto_s, present_s = self._prototypes(hs[-1][:, pad:, :], out["pred_logits"])
@@ -361,45 +396,19 @@ class SetCriterion(nn.Module):
             out.update({k + suffix: v for k, v in self.get_loss(loss, outputs, targets, indices, num_boxes, **kwargs).items()})
         return out
 
-    def forward(self, outputs, targets, return_indices=False, target_domain_flag=False):
-        """outputs: the model's dict; targets: list of {'labels','boxes'} per (source or pseudo-labelled) image.
-        With target_domain_flag the *_target keys are scored instead (self-training)."""
-        if target_domain_flag:
-            outputs_without_aux = {k.replace("_target", ""): v for k, v in outputs.items() if k != "aux_outputs_target"}
-            outputs.update({"pred_boxes": outputs.pop("pred_boxes_target")})
-            outputs.update({"pred_logits": outputs.pop("pred_logits_target")})
-            device = outputs["pred_logits"].device
-        else:
-            outputs_without_aux = {k: v for k, v in outputs.items() if k != "aux_outputs"}
-            device = next(iter(outputs.values())).device
-
+    def _losses_from(self, outputs, targets, pre, num_boxes, target_domain_flag, training, return_indices):
+        """All losses given the matchings `pre` (device index tensors): pure device work, no host synchronisation."""
+        device = outputs["pred_logits"].device
         key_aux = "aux_outputs_target" if target_domain_flag else "aux_outputs"
         key_interm = "interm_outputs_target" if target_domain_flag else "interm_outputs"
-        pre = None
-        if len(targets) > 0:
-            # all matchings of the step (final, auxiliary decoder layers, intermediate) in one batched pass
-            sets = [outputs_without_aux] + list(outputs.get(key_aux, [])) + ([outputs[key_interm]] if key_interm in outputs else [])
-            pre = match_many(self.matcher, sets, targets)
-            indices = pre[0]
-            num_boxes = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=device)
-            indices0, indices_list = indices, []
-        else:       # no pseudo labels on this rank: still take part in the collective below
-            indices = None
-            num_boxes = torch.as_tensor([1], dtype=torch.float, device=outputs["pred_logits"].device)
-        if is_dist_avail_and_initialized():
-            torch.distributed.all_reduce(num_boxes)
-        if indices is None:
-            num_boxes = num_boxes - 1
-        num_boxes = torch.clamp(num_boxes / get_world_size(), min=1).item()
-        if indices is None:
-            return {}
-
+        indices = indices0 = pre[0]
+        indices_list = []
         losses = {}
         dn_zero = ("loss_bbox_dn", "loss_giou_dn", "loss_ce_dn", "loss_xy_dn", "loss_hw_dn", "cardinality_error_dn")
         use_dn = False
         if not target_domain_flag:
             dn_meta = outputs["dn_meta"]
-            use_dn = bool(self.training and dn_meta and "output_known_lbs_bboxes" in dn_meta)
+            use_dn = bool(training and dn_meta and "output_known_lbs_bboxes" in dn_meta)
             if use_dn:
                 known = dn_meta["output_known_lbs_bboxes"]
                 scalar, pad_size = dn_meta["num_dn_group"], dn_meta["pad_size"]
@@ -448,6 +457,47 @@ class SetCriterion(nn.Module):
             indices_list.append(indices0)
             return losses, indices_list
         return losses
+
+    def forward(self, outputs, targets, return_indices=False, target_domain_flag=False):
+        """outputs: the model's dict; targets: list of {'labels','boxes'} per (source or pseudo-labelled) image.
+        With target_domain_flag the *_target keys are scored instead (self-training)."""
+        if target_domain_flag:
+            outputs_without_aux = {k.replace("_target", ""): v for k, v in outputs.items() if k != "aux_outputs_target"}
+            outputs.update({"pred_boxes": outputs.pop("pred_boxes_target")})
+            outputs.update({"pred_logits": outputs.pop("pred_logits_target")})
+            device = outputs["pred_logits"].device
+        else:
+            outputs_without_aux = {k: v for k, v in outputs.items() if k != "aux_outputs"}
+            device = next(iter(outputs.values())).device
+
+        key_aux = "aux_outputs_target" if target_domain_flag else "aux_outputs"
+        key_interm = "interm_outputs_target" if target_domain_flag else "interm_outputs"
+        pre = None
+        if len(targets) > 0:
+            # all matchings of the step (final, auxiliary decoder layers, intermediate) in one batched pass
+            sets = [outputs_without_aux] + list(outputs.get(key_aux, [])) + ([outputs[key_interm]] if key_interm in outputs else [])
+            pre = match_many(self.matcher, sets, targets)
+            indices = pre[0]
+            num_boxes = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=device)
+            indices0, indices_list = indices, []
+        else:       # no pseudo labels on this rank: still take part in the collective below
+            indices = None
+            num_boxes = torch.as_tensor([1], dtype=torch.float, device=outputs["pred_logits"].device)
+        if is_dist_avail_and_initialized():
+            torch.distributed.all_reduce(num_boxes)
+        if indices is None:
+            num_boxes = num_boxes - 1
+        num_boxes = torch.clamp(num_boxes / get_world_size(), min=1).item()
+        if indices is None:
+            return {}
+
+        if (graphs.ACTIVE is not None and device.type == "cuda" and torch.is_grad_enabled() and not return_indices
+                and not target_domain_flag):
+            # every loss of the step as one captured segment: the matched indices, targets and predictions are its
+            # tensor inputs, everything host-side (matching, num_boxes) happened above
+            return graphs.ACTIVE.call("criterion", None, self._losses_from, outputs, targets, pre, num_boxes,
+                                      target_domain_flag, self.training, False)
+        return self._losses_from(outputs, targets, pre, num_boxes, target_domain_flag, self.training, return_indices)
 
     def prep_for_dn(self, dn_meta):
         groups, pad = dn_meta["num_dn_group"], dn_meta["pad_size"]
