@@ -39,6 +39,8 @@ class StepGraphs:
         self.warmup_iters = warmup_iters
         self.replayed_native_launches = 0      # hand-written kernel launches executed by graph replays
         self.captures = 0
+        import os
+        self.skip = set(filter(None, os.environ.get("DATR_GRAPH_SKIP", "").split(",")))   # segment names kept eager
 
     def begin_step(self):
         self.calls.clear()
@@ -46,6 +48,8 @@ class StepGraphs:
     def call(self, name, owner, fn, *args):
         """Run `fn(*args)` (args: any pytree of tensors and hashable constants; `owner`: the nn.Module whose
         parameters fn uses, or None) as a graph segment; returns fn's output pytree."""
+        if name in self.skip:
+            return fn(*args)
         return _call_segment(self, name, owner, fn, args)
 
     def run(self, name, make_module, args, key_extra=(), want_module=False):

@@ -452,7 +452,12 @@ class DeformableTransformer(nn.Module):
                                         key_padding_mask=mask_flat, shapes_list=shapes_list)
 
         if graphs.ACTIVE is not None and memory.is_cuda:
-            sel = graphs.ACTIVE.call("two_stage", self, self._select_queries, memory, mask_flat, refpoint_embed, tgt,
+            owners = self.__dict__.setdefault("_two_stage_owner", nn.ModuleList(
+                [m for m in (getattr(self, "enc_output", None), getattr(self, "enc_output_norm", None),
+                             self.enc_out_class_embed, self.enc_out_bbox_embed, self.tgt_embed,
+                             getattr(self, "refpoint_embed", None), getattr(self, "two_stage_wh_embedding", None))
+                 if isinstance(m, nn.Module)]))
+            sel = graphs.ACTIVE.call("two_stage", owners, self._select_queries, memory, mask_flat, refpoint_embed, tgt,
                                      tuple(shapes_list))
         else:
             sel = self._select_queries(memory, mask_flat, refpoint_embed, tgt, tuple(shapes_list))

@@ -151,7 +151,7 @@ class DINO(nn.Module):
         if graphs.ACTIVE is not None and samples.tensors.is_cuda:
             base = self.backbone[0]
             feats = graphs.ACTIVE.run("body", lambda: graphs.BodySegment(base.body), (samples.tensors,))
-            srcs, masks, poss = graphs.ACTIVE.call("project", self, self._project, tuple(feats), samples.mask)
+            srcs, masks, poss = graphs.ACTIVE.call("project", self.input_proj, self._project, tuple(feats), samples.mask)
             return list(srcs), list(masks), list(poss)
         features, poss = self.backbone(samples)
         return self._project_levels(features, poss, samples.mask)
@@ -179,18 +179,27 @@ class DINO(nn.Module):
             masks.append(mask)
         return srcs, masks, poss
 
-    def _heads(self, hs, reference):
-        """Per-decoder-layer boxes (sigmoid(delta + logit(reference))) and class logits, stacked over layers."""
-        coords = torch.stack([(head(h) + inverse_sigmoid(ref)).sigmoid()
-                              for ref, head, h in zip(reference[:-1], self.bbox_embed, hs)])
+    def _class_logits(self, hs, hs_enc):
+        """Per-decoder-layer class logits [n_layers, N, nq, classes] and the logits of the selected encoder proposals.
+        (Kept outside the captured head segment: the 91-wide library GEMMs of these layers do not survive CUDA-graph
+        capture of their backward on this stack; they are 7 small launches.)"""
         classes = torch.stack([head(h) for head, h in zip(self.class_embed, hs)])
-        return classes, coords
+        interm = self.transformer.enc_out_class_embed(hs_enc[-1]) if hs_enc is not None else None
+        return classes, interm
 
-    def _interm(self, out, hs_enc, ref_enc, init_box_proposal, suffix=""):
-        interm_class = self.transformer.enc_out_class_embed(hs_enc[-1])
+    def _boxes(self, hs, reference):
+        """Per-decoder-layer boxes: sigmoid(delta + logit(reference)), stacked over layers."""
+        return torch.stack([(head(h) + inverse_sigmoid(ref)).sigmoid()
+                            for ref, head, h in zip(reference[:-1], self.bbox_embed, hs)])
+
+    def _heads(self, hs, reference):
+        """Per-decoder-layer class logits and boxes, stacked over layers."""
+        return self._class_logits(hs, None)[0], self._boxes(hs, reference)
+
+    def _interm(self, out, interm_class, ref_enc, init_box_proposal, suffix=""):
         out["interm_outputs" + suffix] = {"pred_logits": interm_class, "pred_boxes": ref_enc[-1]}
         out["interm_outputs_for_matching_pre" + suffix] = {"pred_logits": interm_class, "pred_boxes": init_box_proposal}
-        if hs_enc.shape[0] > 1:      # per-encoder-layer heads: unreachable with two_stage_type 'standard' (one entry)
+        if ref_enc.shape[0] > 1:     # per-encoder-layer heads: unreachable with two_stage_type 'standard' (one entry)
             raise NotImplementedError("per-encoder-layer outputs (enc_outputs) are outside the DINO hot path")
 
     def _prototypes(self, feats, logits):
@@ -201,25 +210,31 @@ class DINO(nn.Module):
             feats, logits, self.num_classes, global_proto=self.global_proto.detach(), global_amount=self.Amount)
         return proto, present
 
+    def _segment_owner(self, name, modules):
+        """The sub-modules whose parameters a graph segment touches, as one (unregistered) container: a segment's
+        graphed backward returns gradients for exactly these parameters."""
+        cache = self.__dict__.setdefault("_segment_owners", {})
+        if name not in cache:
+            cache[name] = nn.ModuleList([m for m in modules if m is not None])
+        return cache[name]
+
     def _image_discriminator(self, srcs_all):
         """Image-level domain discriminator behind a gradient reversal, on every level of both domains: [2B, S, 1]."""
         d_img = [self.D_img(grad_reverse(s)) for s in srcs_all]
         return torch.cat([d.flatten(2).transpose(1, 2) for d in d_img], dim=1)
 
-    def _outputs_from(self, hs, reference, hs_enc, ref_enc, init_box_proposal, dn_meta):
-        """Decoder outputs -> the output dict (per-layer heads, de-noising split, auxiliary and intermediate sets):
-        pure device work."""
-        hs = list(hs)
-        hs[0] = hs[0] + self.label_enc.weight[0, 0] * 0.0        # keeps label_enc in the graph when there are no objects
-        outputs_class, outputs_coord = self._heads(hs, reference)
+    def _outputs_from(self, hs, reference, outputs_class, interm_class, ref_enc, init_box_proposal, dn_meta):
+        """Decoder outputs + class logits -> the output dict (box heads, de-noising split, auxiliary and intermediate
+        sets): pure device work."""
+        outputs_coord = self._boxes(list(hs), reference)
         if self.dn_number > 0 and dn_meta is not None:
             dn_meta = dict(dn_meta)
             outputs_class, outputs_coord = dn_post_process(outputs_class, outputs_coord, dn_meta, self.aux_loss, self._set_aux_loss)
         out = {"pred_logits": outputs_class[-1], "pred_boxes": outputs_coord[-1]}
         if self.aux_loss:
             out["aux_outputs"] = self._set_aux_loss(outputs_class, outputs_coord)
-        if hs_enc is not None:
-            self._interm(out, hs_enc, ref_enc, init_box_proposal)
+        if interm_class is not None:
+            self._interm(out, interm_class, ref_enc, init_box_proposal)
         out["dn_meta"] = dn_meta
         return out
 
@@ -244,18 +259,23 @@ class DINO(nn.Module):
             srcs, masks, poss, srcs_all, masks_all, poss_all, srcs_t, masks_t, poss_t = decompose_features(srcs, masks, poss)
 
         hs, reference, hs_enc, ref_enc, init_box_proposal = self.transformer(srcs, masks, dn_bbox, poss, dn_label, attn_mask)
+        # keeps label_enc in the autograd graph when there are no objects.  (Eager on purpose: label_enc already feeds
+        # the eager de-noising query construction, and a parameter must not be shared between a live eager graph and a
+        # segment being captured.)
+        hs[0] = hs[0] + self.label_enc.weight[0, 0] * 0.0
+        outputs_class, interm_class = self._class_logits(hs, hs_enc)
         if graphs.ACTIVE is not None and hs[0].is_cuda:
-            out = graphs.ACTIVE.call("heads", self, self._outputs_from, tuple(hs), tuple(reference), hs_enc, ref_enc,
-                                     init_box_proposal, dn_meta)
+            out = graphs.ACTIVE.call("heads", self.bbox_embed, self._outputs_from, tuple(hs), tuple(reference),
+                                     outputs_class, interm_class, ref_enc, init_box_proposal, dn_meta)
         else:
-            out = self._outputs_from(tuple(hs), tuple(reference), hs_enc, ref_enc, init_box_proposal, dn_meta)
+            out = self._outputs_from(tuple(hs), tuple(reference), outputs_class, interm_class, ref_enc, init_box_proposal, dn_meta)
         if not self.training:
             return out
 
         # ---- domain adaptation -----------------------------------------------------------------
         da = {}
         if graphs.ACTIVE is not None and srcs_all[0].is_cuda:
-            da["backbone_DA"] = graphs.ACTIVE.call("d_img", self, self._image_discriminator, tuple(srcs_all))
+            da["backbone_DA"] = graphs.ACTIVE.call("d_img", self.D_img, self._image_discriminator, tuple(srcs_all))
         else:
             da["backbone_DA"] = self._image_discriminator(tuple(srcs_all))
 
@@ -278,7 +298,8 @@ class DINO(nn.Module):
             if self.aux_loss:
                 out["aux_outputs_target"] = self._set_aux_loss(class_t, coord_t)
             if hs_enc_t is not None:
-                self._interm(out, hs_enc_t, ref_enc_t, init_box_proposal_t, suffix="_target")
+                self._interm(out, self.transformer.enc_out_class_embed(hs_enc_t[-1]), ref_enc_t, init_box_proposal_t,
+                             suffix="_target")
         return out
 
     @torch.jit.unused
@@ -301,7 +322,7 @@ class SetCriterion(nn.Module):
         idx = self._get_src_permutation_idx(indices)
         matched = torch.cat([t["labels"][J] for t, (_, J) in zip(targets, indices)])
         onehot = torch.zeros_like(logits)
-        onehot[idx[0], idx[1], matched] = 1
+        onehot.index_put_((idx[0], idx[1], matched), onehot.new_ones(()))      # (a python scalar would be a host->device copy)
         loss_ce = sigmoid_focal_loss(logits, onehot, num_boxes, alpha=self.focal_alpha, gamma=2) * logits.shape[1]
         losses = {"loss_ce": loss_ce}
         if log:
@@ -417,7 +438,7 @@ class SetCriterion(nn.Module):
                 dn_pos_idx = self._dn_indices(targets, single_pad, scalar, device)
                 losses.update(self._group(known, targets, dn_pos_idx, num_boxes * scalar, "_dn"))
             else:
-                losses.update({k: torch.as_tensor(0.0, device=device) for k in dn_zero})
+                losses.update({k: torch.zeros((), device=device) for k in dn_zero})
             losses.update(self._group(outputs, targets, indices, num_boxes, "", log_labels=True))
 
         if key_aux in outputs:
@@ -430,7 +451,7 @@ class SetCriterion(nn.Module):
                     if use_dn:
                         losses.update(self._group(known["aux_outputs"][i], targets, dn_pos_idx, num_boxes * scalar, f"_dn_{i}"))
                     else:
-                        losses.update({f"{k}_{i}": torch.as_tensor(0.0, device=device) for k in dn_zero})
+                        losses.update({f"{k}_{i}": torch.zeros((), device=device) for k in dn_zero})
 
         if key_interm in outputs:
             interm = outputs[key_interm]
