@@ -420,12 +420,9 @@ class DeformableTransformer(nn.Module):
 
         return refpoint_embed, tgt, tgt_undetach, refpoint_undetach, init_box_proposal, output_memory, coord_all, output_proposals
 
-    def forward(self, srcs, masks, refpoint_embed, pos_embeds, tgt, attn_mask=None):
-        """srcs / pos_embeds: per level [N,C,H,W]; masks: per level [N,H,W] (True = padding);
-        refpoint_embed [N,n_dn,4] / tgt [N,n_dn,C]: de-noising queries (None at inference).
-        Returns (hs: list of [N,nq,C] per decoder layer, references: list of [N,nq,4] (layers + 1),
-        hs_enc [1,N,nq,C] | None, ref_enc [1,N,nq,4] | None, init_box_proposal [N,nq,4])."""
-        shapes_list = [tuple(s.shape[-2:]) for s in srcs]
+    def _flatten_levels(self, srcs, masks, pos_embeds):
+        """Per-level [N,C,H,W] maps -> token sequences [N,S,C] (+ level embedding on the positions), the flat
+        padding mask [N,S] and the valid ratios [N,L,2]: pure device work."""
         feats, poses = [], []
         for lvl, (src, pos) in enumerate(zip(srcs, pos_embeds)):
             feats.append(src.flatten(2).transpose(1, 2))
@@ -433,15 +430,39 @@ class DeformableTransformer(nn.Module):
             if self.num_feature_levels > 1 and self.level_embed is not None:
                 pos = pos + self.level_embed[lvl].view(1, 1, -1)
             poses.append(pos)
-        src_flat = torch.cat(feats, 1)
-        pos_flat = torch.cat(poses, 1)
-        mask_flat = torch.cat([m.flatten(1) for m in masks], 1)
-        bs = src_flat.shape[0]
-        spatial_shapes = torch.as_tensor(shapes_list, dtype=torch.long, device=src_flat.device)
-        sizes = [h * w for h, w in shapes_list]
-        level_start_index = torch.as_tensor([sum(sizes[:i]) for i in range(len(sizes))], dtype=torch.long,
-                                            device=src_flat.device)
         valid_ratios = torch.stack([self.get_valid_ratio(m) for m in masks], 1)
+        return torch.cat(feats, 1), torch.cat(poses, 1), torch.cat([m.flatten(1) for m in masks], 1), valid_ratios
+
+    def _shape_tensors(self, shapes_list, device):
+        """(spatial_shapes [L,2], level_start_index [L]) int64 on the device, cached per shape list (the reference
+        rebuilds them from python lists -- two pageable host->device copies -- at every call)."""
+        cache = self.__dict__.setdefault("_shape_cache", {})
+        key = (tuple(shapes_list), str(device))
+        if key not in cache:
+            sizes = [h * w for h, w in shapes_list]
+            cache[key] = (torch.as_tensor(shapes_list, dtype=torch.long, device=device),
+                          torch.as_tensor([sum(sizes[:i]) for i in range(len(sizes))], dtype=torch.long, device=device))
+        return cache[key]
+
+    def forward(self, srcs, masks, refpoint_embed, pos_embeds, tgt, attn_mask=None):
+        """srcs / pos_embeds: per level [N,C,H,W]; masks: per level [N,H,W] (True = padding);
+        refpoint_embed [N,n_dn,4] / tgt [N,n_dn,C]: de-noising queries (None at inference).
+        Returns (hs: list of [N,nq,C] per decoder layer, references: list of [N,nq,4] (layers + 1),
+        hs_enc [1,N,nq,C] | None, ref_enc [1,N,nq,4] | None, init_box_proposal [N,nq,4])."""
+        shapes_list = [tuple(s.shape[-2:]) for s in srcs]
+        if graphs.ACTIVE is not None and srcs[0].is_cuda:
+            owner = self.__dict__.get("_level_embed_owner")
+            if owner is None:                                   # exposes the bare level_embed parameter to the segment
+                owner = nn.Module()
+                if self.level_embed is not None:
+                    owner.register_parameter("level_embed", self.level_embed)
+                self.__dict__["_level_embed_owner"] = owner
+            src_flat, pos_flat, mask_flat, valid_ratios = graphs.ACTIVE.call(
+                "flatten", owner, self._flatten_levels, tuple(srcs), tuple(masks), tuple(pos_embeds))
+        else:
+            src_flat, pos_flat, mask_flat, valid_ratios = self._flatten_levels(tuple(srcs), tuple(masks), tuple(pos_embeds))
+        bs = src_flat.shape[0]
+        spatial_shapes, level_start_index = self._shape_tensors(shapes_list, src_flat.device)
 
         if graphs.ACTIVE is not None and src_flat.is_cuda:
             memory = graphs.ACTIVE.run("encoder", lambda: graphs.EncoderSegment(self.encoder, shapes_list),
