@@ -421,11 +421,17 @@ def main():
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:
-        ips, step_s, t_call = cpu_port_images_per_s(threads, repeats=1)
-        line["cpu_baseline"] = {
-            "value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": "1 encoder + 1 decoder(1100) + 1 decoder(900) call fwd+bwd of the grid_sample CPU path "
-                      "(oracle/msda.py core_torch), extrapolated x12/x6/x6 to the step; %.2f s per step" % step_s}
+        if args.workload == "dino":
+            # the same training step on the host cores (bounded sample: one step of 1 source + 1 target image)
+            from datr_b200 import bench_dino
+            ref = bench_dino.reference_arm(argparse.Namespace(steps=1, warmup=0, gpus=1), threads)
+            line["cpu_baseline"] = ref["cpu_baseline"]
+        else:
+            ips, step_s, t_call = cpu_port_images_per_s(threads, repeats=1)
+            line["cpu_baseline"] = {
+                "value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                "sample": "1 encoder + 1 decoder(1100) + 1 decoder(900) call fwd+bwd of the grid_sample CPU path "
+                          "(oracle/msda.py core_torch), extrapolated x12/x6/x6 to the step; %.2f s per step" % step_s}
     extra = getattr(wl, "extra", None)
     if extra:
         line.update(extra() if callable(extra) else extra)

@@ -1,0 +1,241 @@
+// wgrad_tf32.cu -- weight and bias gradients of a Linear layer on the 5th-generation tensor cores (sm_100a):
+//
+//     dW[N, K] = dz[M, N]^T . x[M, K]          db[N] = sum_m dz[m, n]
+//
+// for the nn.Linear layers of the DINO transformer and the 1x1 convolutions of the ResNet bottlenecks (reference
+// autograd of torch.nn.functional.linear at models/dino/ops/modules/ms_deform_attn.py:94-125 and
+// models/dino/deformable_transformer.py:784-805, :941-947), M = batch * tokens = 44 446 rows (or pixels).
+//
+//   * the contraction runs over the ROWS of both operands, so both are "MN-major" for the MMA: a TMA box of
+//     {32 columns, 32 rows} lands as 32 rows of 128 bytes (128-byte swizzle with 32-byte atoms), and
+//     tcgen05.mma.kind::tf32 reads it with the transposed-operand bits set in the instruction descriptor (leading
+//     byte offset = distance between 32-column chunks, each MMA consumes 8 rows) -- neither operand is ever
+//     transposed in memory;
+//   * split-K: the M rows are cut into slabs; a CTA owns one 128 x BN tile of dW and one slab, accumulates in TMEM and
+//     adds its partial tile to dW with vector reductions (dW / db are zero-filled by the library on the stream);
+//   * db rides along as one extra MMA per 8 rows against a constant tile of ones (16 more TMEM columns);
+//   * warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue; 4-stage mbarrier ring.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <cstdio>
+
+#include "datr_linear.h"
+#include "tcgen05_common.cuh"
+
+namespace {
+
+using namespace datr_tc;
+
+thread_local char g_wg_err[512] = "";
+std::atomic<uint64_t> g_wg_launches{0};
+
+int wfail(int code, const char* fmt, const char* detail = "") {
+  snprintf(g_wg_err, sizeof g_wg_err, fmt, detail);
+  return code;
+}
+
+constexpr int kThreads = 192;
+constexpr int kChunk = 32 * BK * 4;         // bytes of one {32 columns x 32 rows} box
+constexpr int kOnesCols = 16;               // N of the bias-gradient MMA
+
+template <int BN, int STAGES>
+struct Smem {
+  static constexpr int kA = 4 * kChunk, kB = (BN / 32) * kChunk, kStage = kA + kB;
+  static constexpr int kOnes = kChunk;
+  static constexpr int kBars = 1024;
+  static constexpr int kTotal = STAGES * kStage + kOnes + kBars + 1024;
+};
+
+// MN-major 32-bit operand: the tensor core transposes 32-bit elements in 32-byte units, so the tile uses the
+// "128B swizzle with 32B atoms" (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA layout type SWIZZLE_128B_BASE32B = 1;
+// the plain 128B swizzle silently yields zeros for transposed TF32 operands).  Rows are 128 bytes, the swizzle atom is
+// 4 rows (512 bytes = stride byte offset between K atoms), 32-column chunks are `kChunk` bytes apart (leading byte
+// offset); descriptor version 1.
+__device__ __forceinline__ uint64_t mnmajor_sw128_desc(uint32_t smem_addr) {
+  return uint64_t((smem_addr >> 4) & 0x3FFF) | (uint64_t(kChunk >> 4) << 16) | (uint64_t(512 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(1) << 61);
+}
+
+// D = fp32, A = B = TF32, both MN-major (bits 15, 16), N = n, M = 128
+__host__ __device__ constexpr uint32_t tf32_idesc_mn(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | (uint32_t(n >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tma_dz, const __grid_constant__ CUtensorMap tma_x,
+                  float* __restrict__ dw, float* __restrict__ db, int M, int N, int K, int splits, int rows_per_split) {
+  using L = Smem<BN, STAGES>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* ones = reinterpret_cast<float*>(smem + STAGES * L::kStage);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStage + L::kOnes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  constexpr uint32_t kTmemCols = BN == 256 ? 512 : 256;      // BN accumulator columns + 16 for db, power of two
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_tiles = (K + BN - 1) / BN;
+  const int tile = blockIdx.x / splits, split = blockIdx.x % splits;
+  const int n0 = (tile / k_tiles) * BM, k0 = (tile % k_tiles) * BN;
+  const int m_begin = split * rows_per_split;
+  const int m_end = min(M, m_begin + rows_per_split);
+  const int kblocks = m_end > m_begin ? (m_end - m_begin + BK - 1) / BK : 0;
+
+  for (int i = threadIdx.x; i < kChunk / 4; i += kThreads) ones[i] = 1.0f;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_dz) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_x) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (kblocks > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int s = kb % STAGES;
+          const int m = m_begin + kb * BK;
+          mbar_wait(empty + s, ((kb / STAGES) & 1) ^ 1);
+          mbar_expect_tx(full + s, L::kStage);
+          unsigned char* a = smem + s * L::kStage;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_load_2d(a + c * kChunk, &tma_dz, n0 + 32 * c, m, full + s);
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c) tma_load_2d(a + L::kA + c * kChunk, &tma_x, k0 + 32 * c, m, full + s);
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        constexpr uint32_t idesc = tf32_idesc_mn(BN), idesc1 = tf32_idesc_mn(kOnesCols);
+        const uint64_t od = mnmajor_sw128_desc(smem_u32(ones));
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int s = kb % STAGES;
+          mbar_wait(full + s, (kb / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a = smem_u32(smem + s * L::kStage);
+          const uint64_t ad = mnmajor_sw128_desc(a), bd = mnmajor_sw128_desc(a + L::kA);
+#pragma unroll
+          for (int j = 0; j < BK / UMMA_K; ++j) {             // next 8 rows = +1024 bytes = +64 in the address field
+            umma_tf32(tmem_d, ad + uint64_t(j * 64), bd + uint64_t(j * 64), idesc, (kb | j) != 0);
+            umma_tf32(tmem_d + BN, ad + uint64_t(j * 64), od, idesc1, (kb | j) != 0);
+          }
+          umma_commit(empty + s);
+        }
+        umma_commit(acc_full);
+      }
+    } else {
+      const int lane_base = (warp & 3) * 32;
+      const int n = n0 + lane_base + lane;                    // row of dW owned by this thread
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+      const uint32_t t0 = tmem_d + (uint32_t(lane_base) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(t0 + uint32_t(c), v);
+        if (n < N) {
+          float* row = dw + (size_t)n * K + k0 + c;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            if (k0 + c + j + 4 <= K)
+              red_add4(row + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        }
+      }
+      if (db != nullptr && k0 == 0) {                         // one K tile per dW row block carries the bias gradient
+        uint32_t v[32];
+        tmem_ld32(t0 + uint32_t(BN), v);
+        if (n < N) atomicAdd(db + n, __uint_as_float(v[0]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_d, kTmemCols);
+}
+
+int make_map(CUtensorMap* map, const float* base, int rows, int cols) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return wfail(DATR_LINEAR_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable%s");
+  const cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  const cuuint64_t gstride[1] = {cuuint64_t(cols) * 4};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_wg_err, sizeof g_wg_err, "cuTensorMapEncodeTiled failed (CUresult %d)", int(r));
+    return DATR_LINEAR_ERR_CUDA;
+  }
+  return DATR_LINEAR_OK;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& mdz, const CUtensorMap& mx, float* dw, float* db, int M, int N, int K, cudaStream_t stream) {
+  using L = Smem<BN, STAGES>;
+  static std::atomic<uint64_t> opted{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(opted.load(std::memory_order_acquire) & bit)) {
+    const cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    opted.fetch_or(bit, std::memory_order_release);
+  }
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  const int tiles = ((N + BM - 1) / BM) * ((K + BN - 1) / BN);
+  int splits = (2 * sms + tiles - 1) / tiles;                 // about two CTAs' worth of tiles per SM in total
+  const int max_splits = (M + 4 * BK - 1) / (4 * BK);         // at least 128 rows per slab
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  int rows_per_split = ((M + splits - 1) / splits + BK - 1) / BK * BK;
+  splits = (M + rows_per_split - 1) / rows_per_split;
+  wgrad_tf32_kernel<BN, STAGES><<<unsigned(tiles * splits), kThreads, L::kTotal, stream>>>(mdz, mx, dw, db, M, N, K, splits,
+                                                                                          rows_per_split);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "wgrad_tf32_kernel launch: %s", cudaGetErrorString(e));
+  g_wg_launches.fetch_add(1, std::memory_order_relaxed);
+  return DATR_LINEAR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int datr_linear_wgrad_tf32(const float* dz, const float* x, float* dw, float* db, int M, int N, int K, void* stream_) {
+  if (!dz || !x || !dw) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "null pointer argument%s");
+  if (M <= 0 || N <= 0 || K <= 0) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "all dimensions must be positive%s");
+  if (N % 4 != 0 || K % 4 != 0) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "N and K must be multiples of 4%s");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(dz) || !al16(x) || !al16(dw)) return wfail(DATR_LINEAR_ERR_ALIGNMENT, "buffers must be 16-byte aligned%s");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, stream);
+  if (e == cudaSuccess && db) e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, stream);
+  if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  CUtensorMap mdz, mx;
+  if (int rc = make_map(&mdz, dz, M, N)) return rc;
+  if (int rc = make_map(&mx, x, M, K)) return rc;
+  return K > 128 ? launch<256, 4>(mdz, mx, dw, db, M, N, K, stream) : launch<128, 6>(mdz, mx, dw, db, M, N, K, stream);
+}
+
+const char* datr_linear_wgrad_last_error(void) { return g_wg_err; }
+uint64_t datr_linear_wgrad_launch_count(void) { return g_wg_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

@@ -21,6 +21,7 @@ import torch.nn.functional as F
 from . import native
 
 _MODE = "fp32"
+_WGRAD = True          # weight/bias gradients on the tcgen05 kernel (False: cuBLAS GEMM + column-sum kernels)
 
 # Optional launch timers: bench.py sets this to a list and each launch appends
 # ("linear", (M, N, K, has_residual), start_event, end_event) recorded on the launching stream.
@@ -90,6 +91,21 @@ def _colsum(g2, y_act=None):
     return dz, db
 
 
+def _wgrad(g2, x2, want_db):
+    """dW = g2^T x2 (and db = column sums of g2) on the tcgen05 weight-gradient kernel (csrc/wgrad_tf32.cu)."""
+    M, N = g2.shape
+    K = x2.shape[1]
+    lib = native.lib()
+    dw = torch.empty((N, K), dtype=torch.float32, device=g2.device)
+    db = torch.empty(N, dtype=torch.float32, device=g2.device) if want_db else None
+    with torch.cuda.device(g2.device):
+        rc = lib.datr_linear_wgrad_tf32(g2.data_ptr(), x2.data_ptr(), dw.data_ptr(), db.data_ptr() if want_db else None,
+                                        M, N, K, torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"datr_linear_wgrad_tf32 failed (code {rc}): {lib.datr_linear_wgrad_last_error().decode()}")
+    return dw, db
+
+
 class _LinearTF32(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, residual, relu):
@@ -111,26 +127,31 @@ class _LinearTF32(torch.autograd.Function):
         N, K = w.shape
         g2 = _c(gy.reshape(-1, N))
         want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        want_gw = ctx.needs_input_grad[1]
+        fused = _WGRAD and want_gw and N % 4 == 0 and K % 4 == 0      # dW and db from one tensor-core kernel
         gb = None
         if ctx.relu == 2:     # ReLU after the residual add: the mask applies to both branches
-            if want_gb:
+            if want_gb and not fused:
                 g2, gb = _colsum(g2, y)
             else:
                 g2 = torch.ops.aten.threshold_backward(g2, y, 0.0)
         gres = g2.view(ctx.rshape) if ctx.has_res else None
         if ctx.relu == 1:     # ReLU mask (+ bias gradient) in one pass
             act = y if r2 is None else y - r2
-            if want_gb:
+            if want_gb and not fused:
                 g2, gb = _colsum(g2, act)
             else:
                 g2 = torch.ops.aten.threshold_backward(g2, act, 0.0)
-        if want_gb and gb is None:
-            gb = _colsum(g2)[1]
         gx = gw = None
         if ctx.needs_input_grad[0]:
             gx = _launch(g2, _c(w.t()), None, None, False).view(ctx.xshape) if N % 32 == 0 and K % 4 == 0 else (g2 @ w).view(ctx.xshape)
-        if ctx.needs_input_grad[1]:
-            gw = g2.t() @ x2
+        if fused:
+            gw, gb = _wgrad(g2, x2, want_gb)
+        else:
+            if want_gb and gb is None:
+                gb = _colsum(g2)[1]
+            if want_gw:
+                gw = g2.t() @ x2
         return gx, gw, gb, gres, None
 
 

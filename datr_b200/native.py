@@ -15,7 +15,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SOURCES = [os.path.join(_PKG, "csrc", "msda.cu"), os.path.join(_PKG, "csrc", "linear_tf32.cu"),
            os.path.join(_PKG, "csrc", "layernorm.cu"), os.path.join(_PKG, "csrc", "colsum.cu"),
-           os.path.join(_PKG, "csrc", "conv3x3_tf32.cu")]
+           os.path.join(_PKG, "csrc", "conv3x3_tf32.cu"), os.path.join(_PKG, "csrc", "wgrad_tf32.cu")]
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -25,7 +25,8 @@ EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_last_error", "datr_a
            "datr_launch_count", "datr_linear_tf32", "datr_linear_last_error", "datr_linear_launch_count",
            "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count",
            "datr_colsum", "datr_relu_bwd_colsum", "datr_colsum_last_error", "datr_colsum_launch_count",
-           "datr_conv3x3_nhwc_tf32", "datr_conv_last_error", "datr_conv_launch_count")
+           "datr_conv3x3_nhwc_tf32", "datr_conv_last_error", "datr_conv_launch_count",
+           "datr_linear_wgrad_tf32", "datr_linear_wgrad_last_error", "datr_linear_wgrad_launch_count")
 
 _lock = threading.Lock()
 _lib = None
@@ -103,6 +104,10 @@ def lib() -> ctypes.CDLL:
         L.datr_conv3x3_nhwc_tf32.argtypes = [vp, vp, vp, vp, i, i, i, i, i, i, i, vp]
         L.datr_conv_last_error.restype = ctypes.c_char_p
         L.datr_conv_launch_count.restype = ctypes.c_uint64
+        L.datr_linear_wgrad_tf32.restype = i
+        L.datr_linear_wgrad_tf32.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+        L.datr_linear_wgrad_last_error.restype = ctypes.c_char_p
+        L.datr_linear_wgrad_launch_count.restype = ctypes.c_uint64
         if L.datr_abi_version() != 1:
             raise NativeLibraryError("libdatr_b200.so ABI version mismatch; rebuild")
         _lib = L
@@ -122,7 +127,12 @@ def colsum_launch_count() -> int:
 def all_launch_count() -> int:
     """Every hand-written kernel launch issued through the library by this process."""
     return (launch_count() + linear_launch_count() + layernorm_launch_count() + colsum_launch_count()
-            + conv_launch_count())
+            + conv_launch_count() + wgrad_launch_count())
+
+
+def wgrad_launch_count() -> int:
+    """tcgen05 weight-gradient kernel launches issued through the library by this process."""
+    return int(lib().datr_linear_wgrad_launch_count())
 
 
 def conv_launch_count() -> int:

@@ -39,6 +39,17 @@ enum {
 int datr_linear_tf32(const float* x, const float* w, const float* bias, const float* residual, float* y,
                      int M, int N, int K, int relu, void* stream);
 
+/*
+ * Weight / bias gradient of the same layer:  dw[N,K] = dz[M,N]^T . x[M,K],  db[N] = sum_m dz[m,n]  (db may be NULL).
+ * Replaces the `grad_output.t().mm(input)` and `grad_output.sum(0)` of torch.nn.functional.linear's autograd.
+ * Both operands are read as they lie in memory (transposed-operand MMA); the M rows are split over CTAs and the
+ * partial tiles are reduced with vector atomics into dw / db, which the library zero-fills on `stream` first
+ * (summation order, hence the last bits, vary from run to run).  N % 4 == 0, K % 4 == 0.
+ */
+int datr_linear_wgrad_tf32(const float* dz, const float* x, float* dw, float* db, int M, int N, int K, void* stream);
+const char* datr_linear_wgrad_last_error(void);
+uint64_t datr_linear_wgrad_launch_count(void);
+
 const char* datr_linear_last_error(void);
 
 /* Number of tensor-core linear kernels launched by this process (bench accounting). */

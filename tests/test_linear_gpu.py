@@ -153,3 +153,20 @@ def test_resnet_bottleneck_pointwise_path_matches_cudnn():
     l2 = [float((a.double() - b.double()).norm() / b.double().norm()) for a, b in zip(got[1:], want[1:])]
     assert max(l2) < 3e-2, (l2, errs)
     assert max(errs[1:]) < 0.15, errs
+
+
+@pytest.mark.parametrize("M,N,K", [(44446, 256, 256), (5000, 2048, 256), (3001, 256, 2048), (130, 128, 128), (31, 64, 32),
+                                   (1000, 384, 512), (267200, 64, 256), (2200, 4, 256)])
+def test_weight_and_bias_gradient_kernel(M, N, K):
+    """datr_linear_wgrad_tf32: dW = dz^T x, db = column sums of dz (split over row slabs, transposed-operand MMA)."""
+    from datr_b200 import native
+    from datr_b200.linear import _wgrad
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    dz = torch.randn(M, N, generator=g).cuda()
+    x = torch.randn(M, K, generator=g).cuda()
+    n0 = native.wgrad_launch_count()
+    dw, db = _wgrad(dz, x, True)
+    torch.cuda.synchronize()
+    assert native.wgrad_launch_count() == n0 + 1
+    assert rel(dw, dz.double().t() @ x.double()) < REL_TF32
+    assert rel(db, dz.double().sum(0)) < REL_TF32
