@@ -198,14 +198,19 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_const
             t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
             if (relu == 1) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
             const size_t off = (size_t)row * N + col;
-            if (vec) {
+            if (vec && relu == 3) {          // ReLU-backward mask taken from the `residual` tensor (the saved activation)
+              t.x = res[j].x > 0.f ? t.x : 0.f; t.y = res[j].y > 0.f ? t.y : 0.f;
+              t.z = res[j].z > 0.f ? t.z : 0.f; t.w = res[j].w > 0.f ? t.w : 0.f;
+              *reinterpret_cast<float4*>(y + off) = t;
+            } else if (vec) {
               t.x += res[j].x; t.y += res[j].y; t.z += res[j].z; t.w += res[j].w;
               if (relu == 2) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
               *reinterpret_cast<float4*>(y + off) = t;
             } else {
               const float ov[4] = {t.x, t.y, t.z, t.w};
               for (int e = 0; e < 4 && col + e < N; ++e) {
-                const float o1 = ov[e] + (residual ? __ldg(residual + off + e) : 0.f);
+                const float r1 = residual ? __ldg(residual + off + e) : 0.f;
+                const float o1 = relu == 3 ? (r1 > 0.f ? ov[e] : 0.f) : ov[e] + r1;
                 y[off + e] = relu == 2 ? fmaxf(o1, 0.f) : o1;
               }
             }

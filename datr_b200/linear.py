@@ -155,6 +155,46 @@ class _LinearTF32(torch.autograd.Function):
         return gx, gw, gb, gres, None
 
 
+class _FFNTF32(torch.autograd.Function):
+    """y = relu(x W1^T + b1) W2^T + b2 + x, the transformer FFN with its residual (reference
+    deformable_transformer.py:801-805, :941-947), as ONE autograd node so that the backward fuses what autograd would
+    run as separate passes over the [M, d_ffn] activation:
+        dW2, db2 = wgrad(gy, h)                      dz1 = (gy W2) * (h > 0)      ReLU mask in the dgrad epilogue
+        dW1, db1 = wgrad(dz1, x)                     dx  = dz1 W1 + gy            residual-branch add in the dgrad epilogue"""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        K = w1.shape[1]
+        x2 = _c(x.reshape(-1, K))
+        w1c, w2c = _c(w1), _c(w2)
+        h = _launch(x2, w1c, _c(b1), None, 1)
+        y = _launch(h, w2c, _c(b2), x2, 0)
+        ctx.xshape = x.shape
+        ctx.save_for_backward(x2, w1c, w2c, h)
+        return y.view(x.shape)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        x2, w1, w2, h = ctx.saved_tensors
+        g2 = _c(gy.reshape(-1, w2.shape[0]))
+        gw2, gb2 = _wgrad(g2, h, True)
+        dz1 = _launch(g2, _c(w2.t()), None, h, 3)
+        gw1, gb1 = _wgrad(dz1, x2, True)
+        gx = _launch(dz1, _c(w1.t()), None, g2, 0).view(ctx.xshape)
+        return gx, gw1, gb1, gw2, gb2
+
+
+def ffn(x, w1, b1, w2, b2):
+    """relu(x @ w1.T + b1) @ w2.T + b2 + x  (pre-norm output of the transformer FFN block)."""
+    d_ffn, d = w1.shape
+    if (_MODE == "tf32" and x.is_cuda and x.dtype == torch.float32 and w1.dtype == torch.float32 and b1 is not None
+            and b2 is not None and tuple(w2.shape) == (d, d_ffn) and d % 32 == 0 and d_ffn % 32 == 0
+            and torch.is_grad_enabled()):
+        return _FFNTF32.apply(x, w1, b1, w2, b2)
+    return linear(linear(x, w1, b1, relu=True), w2, b2, residual=x)
+
+
 def linear(x, weight, bias=None, relu=False, residual=None):
     """relu False/0: x @ weight.T + bias + residual;  True/1: relu(x @ weight.T + bias) + residual;
     2: relu(x @ weight.T + bias + residual).  Tensor-core kernel in 'tf32' mode for eligible shapes, else torch."""

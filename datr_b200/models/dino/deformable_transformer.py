@@ -102,8 +102,7 @@ class DeformableTransformerEncoderLayer(nn.Module):
     def forward_ffn(self, src):
         if _fusable(self, self.dropout2, self.dropout3):
             # linear1 + bias + ReLU and linear2 + bias + residual are one kernel each (datr_b200.linear)
-            hidden = dl.linear(src, self.linear1.weight, self.linear1.bias, relu=True)
-            return ln(self.norm2, dl.linear(hidden, self.linear2.weight, self.linear2.bias, residual=src))
+            return ln(self.norm2, dl.ffn(src, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias))
         return ln(self.norm2, src + self.dropout3(self.linear2(self.dropout2(self.activation(self.linear1(src))))))
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask=None):
@@ -189,8 +188,7 @@ class DeformableTransformerDecoderLayer(nn.Module):
 
     def forward_ffn(self, tgt):
         if _fusable(self, self.dropout3, self.dropout4):
-            hidden = dl.linear(tgt, self.linear1.weight, self.linear1.bias, relu=True)
-            return ln(self.norm3, dl.linear(hidden, self.linear2.weight, self.linear2.bias, residual=tgt))
+            return ln(self.norm3, dl.ffn(tgt, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias))
         return ln(self.norm3, tgt + self.dropout4(self.linear2(self.dropout3(self.activation(self.linear1(tgt))))))
 
     def forward_sa(self, tgt, tgt_query_pos=None, self_attn_mask=None):

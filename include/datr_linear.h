@@ -13,6 +13,8 @@
  *   relu == 0:  y[M,N] =        x[M,K] . w[N,K]^T + bias[N]   + residual[M,N]
  *   relu == 1:  y[M,N] = max(0, x[M,K] . w[N,K]^T + bias[N] ) + residual[M,N]      (FFN linear1)
  *   relu == 2:  y[M,N] = max(0, x[M,K] . w[N,K]^T + bias[N]   + residual[M,N] )    (ResNet bottleneck output)
+ *   relu == 3:  y[M,N] = residual[M,N] > 0 ? x[M,K] . w[N,K]^T + bias[N] : 0            (input gradient through a ReLU:
+ *                                                                                        `residual` is the saved activation)
  *
  * All buffers are fp32 device memory, row-major, contiguous, 16-byte aligned, owned by the caller; `bias` and
  * `residual` may be NULL.  Requirements: K % 32 == 0, N % 4 == 0.

@@ -170,3 +170,30 @@ def test_weight_and_bias_gradient_kernel(M, N, K):
     assert native.wgrad_launch_count() == n0 + 1
     assert rel(dw, dz.double().t() @ x.double()) < REL_TF32
     assert rel(db, dz.double().sum(0)) < REL_TF32
+
+
+@pytest.mark.parametrize("M,d,dff", [(3000, 256, 2048), (257, 256, 512)])
+def test_fused_ffn_block(M, d, dff):
+    """ffn(x) = relu(x W1^T + b1) W2^T + b2 + x as one autograd node (ReLU mask and residual add fused into the
+    input-gradient GEMM epilogues) against fp64 autograd."""
+    from datr_b200 import linear as dl
+    g = torch.Generator(device="cpu").manual_seed(M + dff)
+    x = torch.randn(M, d, generator=g).cuda()
+    w1 = (torch.randn(dff, d, generator=g) / d ** 0.5).cuda(); b1 = torch.randn(dff, generator=g).cuda()
+    w2 = (torch.randn(d, dff, generator=g) / dff ** 0.5).cuda(); b2 = torch.randn(d, generator=g).cuda()
+    gy = torch.randn(M, d, generator=g).cuda()
+    leaves = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    dl.set_mode("tf32")
+    try:
+        y = dl.ffn(*leaves)
+        y.backward(gy)
+        with torch.no_grad():                      # the same kernel on the same operands: the block's own active set
+            active = dl.linear(x, w1, b1, relu=True) > 0
+    finally:
+        dl.set_mode("fp32")
+    ref = [t.double().clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    yr = ((ref[0] @ ref[1].t() + ref[2]) * active) @ ref[3].t() + ref[4] + ref[0]
+    yr.backward(gy.double())
+    assert rel(y.detach(), yr.detach()) < REL_TF32
+    for got, want in zip(leaves, ref):
+        assert rel(got.grad, want.grad) < REL_TF32
