@@ -50,5 +50,22 @@ def main():
               f"   cuBLAS-tf32 {t_tf32*1e3:8.1f} us   cuBLAS-fp32 {t_fp32*1e3:8.1f} us", flush=True)
 
 
+def wgrad():
+    """Weight + bias gradient kernel vs cuBLAS TF32 (dz^T @ x) + ATen column sum."""
+    from datr_b200.linear import _wgrad
+    M = 44446
+    for name, N, K in [("value/out/offsets proj", 256, 256), ("attn_weights", 128, 256), ("linear1", 2048, 256), ("linear2", 256, 2048)]:
+        dz = torch.randn(M, N, device="cuda"); x = torch.randn(M, K, device="cuda")
+        flops = 2.0 * M * N * K
+        bytes_ = 4.0 * (M * N + M * K + N * K)
+        t_ours = timeit(lambda: _wgrad(dz, x, True))
+        torch.backends.cuda.matmul.allow_tf32 = True
+        t_lib = timeit(lambda: (dz.t() @ x, dz.sum(0)))
+        torch.backends.cuda.matmul.allow_tf32 = False
+        print(f"wgrad {name:24s} M={M} N={N:5d} K={K:5d}  ours {t_ours*1e3:8.1f} us ({flops/t_ours/1e9:7.1f} TF/s, {bytes_/t_ours/1e6:7.1f} GB/s = {bytes_/t_ours/1e6/HBM:5.3f} of HBM)"
+              f"   cuBLAS-tf32 + sum {t_lib*1e3:8.1f} us", flush=True)
+
+
 if __name__ == "__main__":
     main()
+    wgrad()
