@@ -323,6 +323,7 @@ def main():
     device = torch.device("cuda", local)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version)
         dist.init_process_group("nccl", device_id=device)
 
     def barrier():
