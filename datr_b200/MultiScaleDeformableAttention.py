@@ -116,6 +116,93 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_attn]
 
 
+def fused_supported(value, sampling_offsets, reference_points) -> bool:
+    """True if datr_msda_fused_forward / _backward (include/datr_msda.h) cover this call."""
+    if not (value.is_cuda and value.dtype == torch.float32 and value.dim() == 4 and value.shape[-1] == 32):
+        return False
+    L, P = sampling_offsets.shape[3], sampling_offsets.shape[4]
+    return P in (1, 2, 4, 8) and L * P <= 32 and reference_points.shape[-1] in (2, 4) \
+        and reference_points.dtype == torch.float32 and not reference_points.requires_grad
+
+
+def _check_fused(value, spatial_shapes, level_start_index, offsets, logits, ref, extra=()):
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("sampling_offsets", offsets), ("attn_logits", logits), ("reference_points", ref), *extra]
+    if not value.is_cuda:
+        raise RuntimeError("Not implemented on the CPU")
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+        if not t.is_cuda or t.device != value.device:
+            raise RuntimeError(f"{name} must be a CUDA tensor on the device of value")
+    for name, t in named[3:]:
+        if t.dtype != torch.float32 or value.dtype != torch.float32:
+            raise RuntimeError(f"fused MSDeformAttn is fp32 only ({name} is {t.dtype})")
+    if spatial_shapes.dtype != torch.int64 or level_start_index.dtype != torch.int64:
+        raise RuntimeError("spatial_shapes and level_start_index must be int64")
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    if offsets.dim() != 6 or ref.dim() != 4:
+        raise RuntimeError("expected sampling_offsets[N,Lq,M,L,P,2], reference_points[N,Lq,L,2|4]")
+    Lq, P, R = offsets.shape[1], offsets.shape[4], ref.shape[-1]
+    if tuple(offsets.shape) != (N, Lq, M, L, P, 2) or logits.numel() != N * Lq * M * L * P \
+            or tuple(ref.shape) != (N, Lq, L, R) or R not in (2, 4) or level_start_index.numel() != L:
+        raise RuntimeError("inconsistent fused MSDeformAttn argument shapes")
+    return N, S, M, D, L, Lq, P, R
+
+
+def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                                 reference_points):
+    """Extension (not in the reference's module): MSDeformAttn.forward's prologue + the op in one kernel."""
+    N, S, M, D, L, Lq, P, R = _check_fused(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                                           reference_points)
+    lib = native.lib()
+    with torch.cuda.device(value.device):
+        out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
+        stream = torch.cuda.current_stream()
+        if _timers is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        rc = lib.datr_msda_fused_forward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                         sampling_offsets.data_ptr(), attn_logits.data_ptr(),
+                                         reference_points.data_ptr(), R, N, S, M, D, L, Lq, P, 0, out.data_ptr(),
+                                         stream.cuda_stream)
+        if _timers is not None:
+            e1.record(stream)
+            _timers.append(("fwd", (N, S, M, D, L, Lq, P, value.element_size()), e0, e1))
+    if rc != 0:
+        _raise(rc, "ms_deform_attn_fused_forward")
+    return out
+
+
+def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                                  reference_points, grad_output):
+    N, S, M, D, L, Lq, P, R = _check_fused(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
+                                           reference_points, extra=(("grad_output", grad_output),))
+    if grad_output.numel() != N * Lq * M * D:
+        raise RuntimeError("grad_output has the wrong number of elements")
+    lib = native.lib()
+    with torch.cuda.device(value.device):
+        grad_value = torch.empty_like(value)            # zero-filled by the library on the stream
+        grad_off = torch.empty_like(sampling_offsets)
+        grad_logits = torch.empty_like(attn_logits)
+        stream = torch.cuda.current_stream()
+        if _timers is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        rc = lib.datr_msda_fused_backward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                          sampling_offsets.data_ptr(), attn_logits.data_ptr(),
+                                          reference_points.data_ptr(), R, grad_output.data_ptr(),
+                                          N, S, M, D, L, Lq, P, 0, grad_value.data_ptr(), grad_off.data_ptr(),
+                                          grad_logits.data_ptr(), stream.cuda_stream)
+        if _timers is not None:
+            e1.record(stream)
+            _timers.append(("bwd", (N, S, M, D, L, Lq, P, value.element_size()), e0, e1))
+    if rc != 0:
+        _raise(rc, "ms_deform_attn_fused_backward")
+    return [grad_value, grad_off, grad_logits]
+
+
 def install(name: str = "MultiScaleDeformableAttention"):
     """Register this module under the reference's extension name."""
     sys.modules[name] = sys.modules[__name__]

@@ -180,6 +180,76 @@ __device__ __forceinline__ float group8_sum(float v) {
   return v;
 }
 
+__device__ __forceinline__ float group8_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 4));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Module-level fusion (kMode 1 / 2): the kernels take what the reference's MSDeformAttn.forward feeds
+// into its elementwise prologue (models/dino/ops/modules/ms_deform_attn.py:99-111) instead of the
+// materialised sampling_locations / attention_weights:
+//   raw sampling offsets [N,Lq,M,L,P,2], raw attention logits [N,Lq,M,L*P], reference points [N,Lq,L,R]
+//   kMode 1 (R = 2, encoder):  loc = ref + off / (W_l, H_l)                       (:102-105)
+//   kMode 2 (R = 4, decoder):  loc = ref.xy + off / P * ref.wh * 0.5              (:106-108)
+//   attn = softmax over the L*P logits of a (query, head) row                     (:101)
+// with the same operation order as the torch expressions.  The 8 lanes of a row hold its samples
+// (lane `sub` owns samples sub, sub+8, ...), so the softmax is two 8-lane shuffle butterflies.
+// ------------------------------------------------------------------------------------------------
+constexpr int kChunks = 4;  // kMaxTaps / 8
+
+struct RowTaps {
+  float x[kChunks], y[kChunks], a[kChunks];  // location and softmax weight of samples c*8+sub
+};
+
+template <int kMode, int kP>
+__device__ __forceinline__ RowTaps fused_taps(const float* __restrict__ off, const float* __restrict__ logit,
+                                              const float* __restrict__ ref, long long bq, long long row, int sub,
+                                              int L, int LP, const LevelGeom* geom) {
+  RowTaps t;
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int s = c * 8 + sub;
+    t.x[c] = t.y[c] = 0.f;
+    t.a[c] = -INFINITY;
+    if (s < LP) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(off) + row * LP + s);
+      t.x[c] = xy.x; t.y[c] = xy.y;
+      t.a[c] = __ldg(logit + row * LP + s);
+      mx = fmaxf(mx, t.a[c]);
+    }
+  }
+  mx = group8_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    t.a[c] = (c * 8 + sub < LP) ? expf(t.a[c] - mx) : 0.f;
+    sum += t.a[c];
+  }
+  sum = group8_sum(sum);
+#pragma unroll
+  for (int c = 0; c < kChunks; ++c) {
+    const int s = c * 8 + sub;
+    t.a[c] = t.a[c] / sum;
+    if (s < LP) {
+      const int l = s / kP;
+      if (kMode == 1) {
+        const float2 r = __ldg(reinterpret_cast<const float2*>(ref) + bq * L + l);
+        t.x[c] = r.x + t.x[c] / float(geom[l].W);
+        t.y[c] = r.y + t.y[c] / float(geom[l].H);
+      } else {
+        const float4 r = __ldg(reinterpret_cast<const float4*>(ref) + bq * L + l);
+        t.x[c] = r.x + ((t.x[c] / float(kP)) * r.z) * 0.5f;
+        t.y[c] = r.y + ((t.y[c] / float(kP)) * r.w) * 0.5f;
+      }
+    }
+  }
+  return t;
+}
+
 // row stride (in 16-byte records) of the slot tables: 4 rows of a warp read 4 different records per
 // LDS.128; they fall on disjoint bank groups iff stride mod 8 is not 0 or 4.
 __host__ __device__ inline int table_stride(int taps) {
@@ -194,11 +264,11 @@ constexpr int kGeomBytes = 512;  // kMaxLevels * sizeof(LevelGeom) rounded up
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int kP, int kBatch>
+template <int kP, int kBatch, int kMode>
 __global__ void __launch_bounds__(256)
 msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                  const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                 const float* __restrict__ attn, int N, int S, int M, int L, int Lq,
+                 const float* __restrict__ attn, const float* __restrict__ ref, int N, int S, int M, int L, int Lq,
                  float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
   LevelGeom* geom = reinterpret_cast<LevelGeom*>(smem);
@@ -219,14 +289,23 @@ msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
   uint4* myw = wtab + r * ws;
   int* myp = ptab + r * ps;
 
-  for (int s = sub; s < LP; s += 8) {
-    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
-    const float a = __ldg(attn + row * LP + s);
-    const Slots t = place(xy.x, xy.y, a, geom[s / kP]);
+  auto publish = [&](int s, float x, float y, float a) {
+    const Slots t = place(x, y, a, geom[s / kP]);
     const float ay0 = t.wy0 * t.a, ay1 = t.wy1 * t.a;
     myw[s] = make_uint4(__float_as_uint(ay0 * t.wx0), __float_as_uint(ay0 * t.wx1),
                         __float_as_uint(ay1 * t.wx0), __float_as_uint(ay1 * t.wx1));
     myp[s] = t.pix;
+  };
+  if constexpr (kMode == 0) {
+    for (int s = sub; s < LP; s += 8) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
+      publish(s, xy.x, xy.y, __ldg(attn + row * LP + s));
+    }
+  } else {
+    const RowTaps t = fused_taps<kMode, kP>(loc, attn, ref, bq, row, sub, L, LP, geom);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+      if (c * 8 + sub < LP) publish(c * 8 + sub, t.x[c], t.y[c], t.a[c]);
   }
   __syncwarp();
 
@@ -272,11 +351,11 @@ msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-template <int kP>
+template <int kP, int kMode>
 __global__ void __launch_bounds__(256, 4)
 msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                  const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                 const float* __restrict__ attn, const float* __restrict__ grad_out,
+                 const float* __restrict__ attn, const float* __restrict__ ref, const float* __restrict__ grad_out,
                  int N, int S, int M, int L, int Lq,
                  float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -303,16 +382,28 @@ msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
   uint4* my1 = tab1 + r * ws;
   uint4* my2 = tab2 + r * ws;
 
-  for (int s = sub; s < LP; s += 8) {
-    const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
-    const float a = __ldg(attn + row * LP + s);
+  auto publish = [&](int s, float x, float y, float a) {
     const LevelGeom g = geom[s / kP];
-    const Slots t = place(xy.x, xy.y, a, g);
+    const Slots t = place(x, y, a, g);
     const float al = live ? t.a : 0.f;  // dead rows scatter nothing
     my0[s] = make_uint4(unsigned(t.pix), __float_as_uint(al), __float_as_uint(t.a * float(g.W)),
                         __float_as_uint(t.a * float(g.H)));
     my1[s] = make_uint4(__float_as_uint(t.wy0), __float_as_uint(t.wy1), __float_as_uint(t.wx0), __float_as_uint(t.wx1));
     my2[s] = make_uint4(__float_as_uint(t.sy0), __float_as_uint(t.sy1), __float_as_uint(t.sx0), __float_as_uint(t.sx1));
+  };
+  float soft[kChunks] = {0.f, 0.f, 0.f, 0.f};  // fused modes: softmax weight of samples c*8+sub
+  if constexpr (kMode == 0) {
+    for (int s = sub; s < LP; s += 8) {
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
+      publish(s, xy.x, xy.y, __ldg(attn + row * LP + s));
+    }
+  } else {
+    const RowTaps t = fused_taps<kMode, kP>(loc, attn, ref, bq, row, sub, L, LP, geom);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      soft[c] = t.a[c];
+      if (c * 8 + sub < LP) publish(c * 8 + sub, t.x[c], t.y[c], t.a[c]);
+    }
   }
   const float4 g = ldg4(grad_out + row * 32 + sub * 4);
   __syncwarp();
@@ -352,13 +443,53 @@ msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
       float px = fmaf(wy1, t1, wy0 * t0);                                                // cuh:157 (x)
       float py = fmaf(__uint_as_float(q2.y), r1, __uint_as_float(q2.x) * r0);            // cuh:158 (y)
       pa = group8_sum(pa); px = group8_sum(px); py = group8_sum(py);
-      if (sub == (s & 7)) { keep_a = pa; keep_x = px * __uint_as_float(q0.z); keep_y = py * __uint_as_float(q0.w); }
-      if ((s & 7) == 7 || s == LP - 1) {
-        const int s0 = s & ~7;
-        if (live && s0 + sub <= s) {
-          grad_attn[row * LP + s0 + sub] = keep_a;
-          reinterpret_cast<float2*>(grad_loc)[row * LP + s0 + sub] = make_float2(keep_x, keep_y);
+      if constexpr (kMode == 0) {
+        if (sub == (s & 7)) { keep_a = pa; keep_x = px * __uint_as_float(q0.z); keep_y = py * __uint_as_float(q0.w); }
+        if ((s & 7) == 7 || s == LP - 1) {
+          const int s0 = s & ~7;
+          if (live && s0 + sub <= s) {
+            grad_attn[row * LP + s0 + sub] = keep_a;
+            reinterpret_cast<float2*>(grad_loc)[row * LP + s0 + sub] = make_float2(keep_x, keep_y);
+          }
         }
+      } else {
+        // every lane of the row has read record s (the shuffles above are warp-synchronous): reuse its slot of
+        // table 2 for {d/d attn, d/d loc.x, d/d loc.y}; the owner lane of the sample collects it after the loop
+        if (sub == (s & 7))
+          my2[s] = make_uint4(__float_as_uint(pa), __float_as_uint(px * __uint_as_float(q0.z)),
+                              __float_as_uint(py * __uint_as_float(q0.w)), 0u);
+      }
+    }
+  }
+  if constexpr (kMode != 0) {
+    // softmax backward (d logit_s = a_s * (d a_s - sum_t a_t * d a_t)) and the chain rule of the location formula
+    (void)keep_a; (void)keep_x; (void)keep_y;
+    __syncwarp();
+    uint4 res[kChunks];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      res[c] = make_uint4(0u, 0u, 0u, 0u);
+      if (c * 8 + sub < LP) res[c] = my2[c * 8 + sub];
+      dot = fmaf(soft[c], __uint_as_float(res[c].x), dot);
+    }
+    dot = group8_sum(dot);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      const int s = c * 8 + sub;
+      if (live && s < LP) {
+        const int l = s / kP;
+        float gx = __uint_as_float(res[c].y), gy = __uint_as_float(res[c].z);
+        if (kMode == 1) {
+          gx = gx / float(geom[l].W);
+          gy = gy / float(geom[l].H);
+        } else {
+          const float4 rr = __ldg(reinterpret_cast<const float4*>(ref) + bq * L + l);
+          gx = ((gx * 0.5f) * rr.z) / float(kP);
+          gy = ((gy * 0.5f) * rr.w) / float(kP);
+        }
+        grad_attn[row * LP + s] = soft[c] * (__uint_as_float(res[c].x) - dot);
+        reinterpret_cast<float2*>(grad_loc)[row * LP + s] = make_float2(gx, gy);
       }
     }
   }
@@ -498,10 +629,66 @@ int allow_big_smem() {
   const int bytes = 64 * 1024;
   cudaError_t e = cudaSuccess;
 #define DATR_OPT(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
-  DATR_OPT(msda_bwd_f32_d32<1>); DATR_OPT(msda_bwd_f32_d32<2>); DATR_OPT(msda_bwd_f32_d32<4>); DATR_OPT(msda_bwd_f32_d32<8>);
+#define DATR_OPT_MODES(PP) DATR_OPT((msda_bwd_f32_d32<PP, 0>)); DATR_OPT((msda_bwd_f32_d32<PP, 1>)); DATR_OPT((msda_bwd_f32_d32<PP, 2>))
+  DATR_OPT_MODES(1); DATR_OPT_MODES(2); DATR_OPT_MODES(4); DATR_OPT_MODES(8);
+#undef DATR_OPT_MODES
 #undef DATR_OPT
   if (e != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   done.fetch_or(bit, std::memory_order_release);
+  return DATR_OK;
+}
+
+// launchers of the fp32 / D = 32 kernels; mode 0 = materialised locations + weights, 1 / 2 = fused prologue (R = 2 / 4)
+int launch_fwd_fast(int mode, const float* v, const int64_t* shapes, const int64_t* lstart, const float* lc,
+                    const float* at, const float* ref, int N, int S, int M, int L, int Lq, int P, float* o,
+                    cudaStream_t stream) {
+  const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
+  if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
+  const int LP = L * P;
+  const size_t smem = kGeomBytes + (size_t)kRowsPerCta * (table_stride(LP) * 16 + pix_stride(LP) * 4);
+#define DATR_FWD(PP, BB, MM) \
+  msda_fwd_f32_d32<PP, BB, MM><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, N, S, M, L, Lq, o)
+#define DATR_FWD_P(MM)                  \
+  switch (P) {                          \
+    case 1: DATR_FWD(1, 1, MM); break;  \
+    case 2: DATR_FWD(2, 2, MM); break;  \
+    case 4: DATR_FWD(4, 2, MM); break;  \
+    default: DATR_FWD(8, 2, MM); break; \
+  }
+  if (mode == 0) { DATR_FWD_P(0) } else if (mode == 1) { DATR_FWD_P(1) } else { DATR_FWD_P(2) }
+#undef DATR_FWD_P
+#undef DATR_FWD
+  return after_launch("msda_fwd_f32_d32");
+}
+
+int launch_bwd_fast(int mode, const float* v, const int64_t* shapes, const int64_t* lstart, const float* lc,
+                    const float* at, const float* ref, const float* go, int N, int S, int M, int L, int Lq, int P,
+                    float* gv, float* gl, float* ga, cudaStream_t stream) {
+  const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
+  if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
+  const size_t smem = kGeomBytes + (size_t)kRowsPerCta * table_stride(L * P) * 48;
+  if (int rc = allow_big_smem()) return rc;
+#define DATR_BWD(PP, MM) \
+  msda_bwd_f32_d32<PP, MM><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, go, N, S, M, L, Lq, gv, gl, ga)
+#define DATR_BWD_P(MM)               \
+  switch (P) {                       \
+    case 1: DATR_BWD(1, MM); break;  \
+    case 2: DATR_BWD(2, MM); break;  \
+    case 4: DATR_BWD(4, MM); break;  \
+    default: DATR_BWD(8, MM); break; \
+  }
+  if (mode == 0) { DATR_BWD_P(0) } else if (mode == 1) { DATR_BWD_P(1) } else { DATR_BWD_P(2) }
+#undef DATR_BWD_P
+#undef DATR_BWD
+  return after_launch("msda_bwd_f32_d32");
+}
+
+int check_fused(const void* ref, int ref_dim, int D, int P, int L, int dtype) {
+  if (!ref) return fail(DATR_ERR_BAD_ARGUMENT, "null reference_points pointer%s");
+  if (ref_dim != 2 && ref_dim != 4) return fail(DATR_ERR_BAD_ARGUMENT, "reference_points must have 2 or 4 components%s");
+  if (dtype != DATR_DTYPE_F32 || D != 32 || !(P == 1 || P == 2 || P == 4 || P == 8) || L > kMaxLevels || L * P > kMaxTaps)
+    return fail(DATR_ERR_UNSUPPORTED, "the fused entry points cover fp32, 32 channels per head, 1/2/4/8 points, L*P <= 32%s");
+  if (!aligned(ref, ref_dim == 2 ? 8 : 16)) return fail(DATR_ERR_ALIGNMENT, "reference_points not aligned to one point%s");
   return DATR_OK;
 }
 
@@ -516,26 +703,9 @@ int datr_msda_forward(const void* value, const int64_t* shapes, const int64_t* l
   if (!out) return fail(DATR_ERR_BAD_ARGUMENT, "null output pointer%s");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const long long rows = (long long)N * Lq * M;
-  if (fast_ok(D, P, L, dtype, value, out, loc, attn)) {
-    const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
-    if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
-    const float* v = static_cast<const float*>(value);
-    const float* lc = static_cast<const float*>(loc);
-    const float* at = static_cast<const float*>(attn);
-    float* o = static_cast<float*>(out);
-    const int LP = L * P;
-    const size_t smem = kGeomBytes + (size_t)kRowsPerCta * (table_stride(LP) * 16 + pix_stride(LP) * 4);
-#define DATR_FWD(PP, BB) \
-  msda_fwd_f32_d32<PP, BB><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, N, S, M, L, Lq, o)
-    switch (P) {
-      case 1: DATR_FWD(1, 1); break;
-      case 2: DATR_FWD(2, 2); break;
-      case 4: DATR_FWD(4, 2); break;
-      default: DATR_FWD(8, 2); break;
-    }
-#undef DATR_FWD
-    return after_launch("msda_fwd_f32_d32");
-  }
+  if (fast_ok(D, P, L, dtype, value, out, loc, attn))
+    return launch_fwd_fast(0, static_cast<const float*>(value), shapes, lstart, static_cast<const float*>(loc),
+                           static_cast<const float*>(attn), nullptr, N, S, M, L, Lq, P, static_cast<float*>(out), stream);
   const long long ctas = (rows + 7) / 8;
   if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
   if (dtype == DATR_DTYPE_F32)
@@ -560,29 +730,11 @@ int datr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
   if (me != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaMemsetAsync(grad_value): %s", cudaGetErrorString(me));
   const long long rows = (long long)N * Lq * M;
   if (fast_ok(D, P, L, dtype, value, grad_out, grad_loc, grad_attn) && aligned(grad_value, 16) && aligned(loc, 8) &&
-      aligned(attn, 4)) {
-    const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
-    if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
-    const float* v = static_cast<const float*>(value);
-    const float* lc = static_cast<const float*>(loc);
-    const float* at = static_cast<const float*>(attn);
-    const float* go = static_cast<const float*>(grad_out);
-    float* gv = static_cast<float*>(grad_value);
-    float* gl = static_cast<float*>(grad_loc);
-    float* ga = static_cast<float*>(grad_attn);
-    const size_t smem = kGeomBytes + (size_t)kRowsPerCta * table_stride(L * P) * 48;
-#define DATR_BWD(PP) \
-  msda_bwd_f32_d32<PP><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, go, N, S, M, L, Lq, gv, gl, ga)
-    if (int rc = allow_big_smem()) return rc;
-    switch (P) {
-      case 1: DATR_BWD(1); break;
-      case 2: DATR_BWD(2); break;
-      case 4: DATR_BWD(4); break;
-      default: DATR_BWD(8); break;
-    }
-#undef DATR_BWD
-    return after_launch("msda_bwd_f32_d32");
-  }
+      aligned(attn, 4))
+    return launch_bwd_fast(0, static_cast<const float*>(value), shapes, lstart, static_cast<const float*>(loc),
+                           static_cast<const float*>(attn), nullptr, static_cast<const float*>(grad_out), N, S, M, L, Lq, P,
+                           static_cast<float*>(grad_value), static_cast<float*>(grad_loc), static_cast<float*>(grad_attn),
+                           stream);
   const long long ctas = (rows + 7) / 8;
   if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
   if (dtype == DATR_DTYPE_F32)
@@ -596,6 +748,40 @@ int datr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
         static_cast<const double*>(attn), static_cast<const double*>(grad_out), rows, S, M, D, L, Lq, P,
         static_cast<double*>(grad_value), static_cast<double*>(grad_loc), static_cast<double*>(grad_attn));
   return after_launch("msda_bwd_generic");
+}
+
+int datr_msda_fused_forward(const void* value, const int64_t* shapes, const int64_t* lstart, const void* offsets,
+                            const void* logits, const void* ref, int ref_dim, int N, int S, int M, int D, int L, int Lq,
+                            int P, int dtype, void* out, void* stream_) {
+  if (int rc = check_common(value, shapes, lstart, offsets, logits, N, S, M, D, L, Lq, P, dtype)) return rc;
+  if (!out) return fail(DATR_ERR_BAD_ARGUMENT, "null output pointer%s");
+  if (int rc = check_fused(ref, ref_dim, D, P, L, dtype)) return rc;
+  if (!aligned(value, 16) || !aligned(out, 16) || !aligned(offsets, 8))
+    return fail(DATR_ERR_ALIGNMENT, "value / output must be 16-byte aligned, offsets 8-byte aligned%s");
+  return launch_fwd_fast(ref_dim == 2 ? 1 : 2, static_cast<const float*>(value), shapes, lstart,
+                         static_cast<const float*>(offsets), static_cast<const float*>(logits),
+                         static_cast<const float*>(ref), N, S, M, L, Lq, P, static_cast<float*>(out),
+                         static_cast<cudaStream_t>(stream_));
+}
+
+int datr_msda_fused_backward(const void* value, const int64_t* shapes, const int64_t* lstart, const void* offsets,
+                             const void* logits, const void* ref, int ref_dim, const void* grad_out, int N, int S, int M,
+                             int D, int L, int Lq, int P, int dtype, void* grad_value, void* grad_offsets,
+                             void* grad_logits, void* stream_) {
+  if (int rc = check_common(value, shapes, lstart, offsets, logits, N, S, M, D, L, Lq, P, dtype)) return rc;
+  if (!grad_out || !grad_value || !grad_offsets || !grad_logits) return fail(DATR_ERR_BAD_ARGUMENT, "null gradient pointer%s");
+  if (int rc = check_fused(ref, ref_dim, D, P, L, dtype)) return rc;
+  if (!aligned(value, 16) || !aligned(grad_out, 16) || !aligned(grad_value, 16) || !aligned(offsets, 8) ||
+      !aligned(grad_offsets, 8))
+    return fail(DATR_ERR_ALIGNMENT, "value / grad_output / grad_value must be 16-byte aligned, offsets 8-byte aligned%s");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const cudaError_t me = cudaMemsetAsync(grad_value, 0, sizeof(float) * (size_t)N * S * M * D, stream);
+  if (me != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaMemsetAsync(grad_value): %s", cudaGetErrorString(me));
+  return launch_bwd_fast(ref_dim == 2 ? 1 : 2, static_cast<const float*>(value), shapes, lstart,
+                         static_cast<const float*>(offsets), static_cast<const float*>(logits),
+                         static_cast<const float*>(ref), static_cast<const float*>(grad_out), N, S, M, L, Lq, P,
+                         static_cast<float*>(grad_value), static_cast<float*>(grad_offsets),
+                         static_cast<float*>(grad_logits), stream);
 }
 
 const char* datr_last_error(void) { return g_err; }

@@ -106,14 +106,22 @@ def _wgrad(g2, x2, want_db):
     return dw, db
 
 
+def _zero_rows(t2, mask):
+    from .rowmask import _zero
+    _zero(t2, mask)
+
+
 class _LinearTF32(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu):
+    def forward(ctx, x, weight, bias, residual, relu, zero_rows=None):
         K = weight.shape[1]
         x2 = _c(x.reshape(-1, K))
         w = _c(weight)
         r2 = _c(residual.reshape(-1, weight.shape[0])) if residual is not None else None
         y = _launch(x2, w, _c(bias) if bias is not None else None, r2, relu)
+        ctx.zero_rows = zero_rows
+        if zero_rows is not None:      # padding rows of the fresh output -> 0 (csrc/rowmask.cu)
+            _zero_rows(y, zero_rows)
         ctx.relu, ctx.has_bias, ctx.has_res = relu, bias is not None, residual is not None
         ctx.xshape = x.shape
         ctx.rshape = residual.shape if residual is not None else None
@@ -126,6 +134,10 @@ class _LinearTF32(torch.autograd.Function):
         x2, w, y, r2 = ctx.saved_tensors
         N, K = w.shape
         g2 = _c(gy.reshape(-1, N))
+        if ctx.zero_rows is not None:
+            # the masked output has one consumer (the MSDeformAttn op), whose backward allocates this gradient:
+            # nobody else reads it, so its padding rows are zeroed in place
+            _zero_rows(g2, ctx.zero_rows)
         want_gb = ctx.has_bias and ctx.needs_input_grad[2]
         want_gw = ctx.needs_input_grad[1]
         fused = _WGRAD and want_gw and N % 4 == 0 and K % 4 == 0      # dW and db from one tensor-core kernel
@@ -152,7 +164,7 @@ class _LinearTF32(torch.autograd.Function):
                 gb = _colsum(g2)[1]
             if want_gw:
                 gw = g2.t() @ x2
-        return gx, gw, gb, gres, None
+        return gx, gw, gb, gres, None, None
 
 
 class _FFNTF32(torch.autograd.Function):
@@ -195,10 +207,19 @@ def ffn(x, w1, b1, w2, b2):
     return linear(linear(x, w1, b1, relu=True), w2, b2, residual=x)
 
 
-def linear(x, weight, bias=None, relu=False, residual=None):
+def linear(x, weight, bias=None, relu=False, residual=None, zero_rows=None):
     """relu False/0: x @ weight.T + bias + residual;  True/1: relu(x @ weight.T + bias) + residual;
-    2: relu(x @ weight.T + bias + residual).  Tensor-core kernel in 'tf32' mode for eligible shapes, else torch."""
+    2: relu(x @ weight.T + bias + residual).  Tensor-core kernel in 'tf32' mode for eligible shapes, else torch.
+    `zero_rows` (bool [*x.shape[:-1]], True = padding; plain Linear only): those rows of the result are set to zero,
+    as `masked_fill(mask[..., None], 0)` after the Linear would."""
     relu = int(relu)
+    if zero_rows is not None:
+        if relu or residual is not None:
+            raise ValueError("zero_rows applies to a plain Linear")
+        if _MODE == "tf32" and eligible(x, weight) and zero_rows.dtype == torch.bool and zero_rows.shape == x.shape[:-1]:
+            return _LinearTF32.apply(x, weight, bias, None, 0, zero_rows.contiguous())
+        from .rowmask import zero_masked_rows
+        return zero_masked_rows(F.linear(x, weight, bias), zero_rows)
     if _MODE == "tf32" and eligible(x, weight):
         return _LinearTF32.apply(x, weight, bias, residual, relu)
     y = F.linear(x, weight, bias)

@@ -32,3 +32,27 @@ class MSDeformAttnFunction(Function):
         grad_value, grad_loc, grad_attn = MSDA.ms_deform_attn_backward(
             value, shapes, level_start, loc, attn, grad_output.contiguous(), ctx.im2col_step)
         return grad_value, None, None, grad_loc, grad_attn, None
+
+
+class MSDeformAttnFusedFunction(Function):
+    """Extension (no counterpart class in the reference): the elementwise prologue of
+    MSDeformAttn.forward (ops/modules/ms_deform_attn.py:99-111 -- softmax of the attention logits, sampling
+    locations from reference points and offsets) evaluated inside the CUDA kernels, so neither tensor is
+    materialised; the backward returns the gradients of the raw offsets and logits."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_offsets, attention_logits,
+                reference_points):
+        output = MSDA.ms_deform_attn_fused_forward(value, value_spatial_shapes, value_level_start_index,
+                                                   sampling_offsets, attention_logits, reference_points)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_offsets,
+                              attention_logits, reference_points)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, offsets, logits, ref = ctx.saved_tensors
+        grad_value, grad_off, grad_logits = MSDA.ms_deform_attn_fused_backward(
+            value, shapes, level_start, offsets, logits, ref, grad_output.contiguous())
+        return grad_value, None, None, grad_off, grad_logits, None

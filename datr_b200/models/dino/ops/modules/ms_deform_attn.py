@@ -13,9 +13,20 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
+from datr_b200 import MultiScaleDeformableAttention as MSDA
 from datr_b200 import linear as dl
 
-from ..functions import MSDeformAttnFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+
+# Module-level fusion: softmax + sampling-location arithmetic inside the MSDeformAttn kernels.
+# DATR_MSDA_FUSED=0 (or set_fused(False)) composes the reference's op with the torch prologue instead.
+import os
+_FUSED = os.environ.get("DATR_MSDA_FUSED", "1") != "0"
+
+
+def set_fused(on: bool) -> None:
+    global _FUSED
+    _FUSED = bool(on)
 
 
 def _is_power_of_2(n):
@@ -71,16 +82,22 @@ class MSDeformAttn(nn.Module):
         # (the reference asserts sum(H*W) == S here with a device->host sync, ms_deform_attn.py:92; the C ABI
         #  bounds every gather by clamping, so the check is left to the caller)
 
-        value = dl.linear(input_flatten, self.value_proj.weight, self.value_proj.bias)
-        if input_padding_mask is not None:
-            value = value.masked_fill(input_padding_mask[..., None], 0.0)
+        # value.masked_fill(mask[..., None], 0) of the reference (:96-97) is applied in place on the fresh projection
+        value = dl.linear(input_flatten, self.value_proj.weight, self.value_proj.bias, zero_rows=input_padding_mask)
         value = value.view(N, S, M, self.d_model // M)
 
         offsets = dl.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(N, Lq, M, L, P, 2)
-        weights = F.softmax(dl.linear(query, self.attention_weights.weight, self.attention_weights.bias)
-                            .view(N, Lq, M, L * P), -1).view(N, Lq, M, L, P)
+        logits = dl.linear(query, self.attention_weights.weight, self.attention_weights.bias).view(N, Lq, M, L * P)
 
         ref_dim = reference_points.shape[-1]
+        if ref_dim not in (2, 4):
+            raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {ref_dim} instead.")
+        if _FUSED and MSDA.fused_supported(value, offsets, reference_points):
+            sampled = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
+                                                      offsets, logits, reference_points.contiguous())
+            return dl.linear(sampled, self.output_proj.weight, self.output_proj.bias, residual=residual)
+
+        weights = F.softmax(logits, -1).view(N, Lq, M, L, P)
         if ref_dim == 2:      # offsets are in pixels of each level: normalise by (W_l, H_l)
             wh = input_spatial_shapes.flip(-1)
             locations = reference_points[:, :, None, :, None, :] + offsets / wh[None, None, None, :, None, :]

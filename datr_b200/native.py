@@ -15,18 +15,20 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SOURCES = [os.path.join(_PKG, "csrc", "msda.cu"), os.path.join(_PKG, "csrc", "linear_tf32.cu"),
            os.path.join(_PKG, "csrc", "layernorm.cu"), os.path.join(_PKG, "csrc", "colsum.cu"),
-           os.path.join(_PKG, "csrc", "conv3x3_tf32.cu"), os.path.join(_PKG, "csrc", "wgrad_tf32.cu")]
+           os.path.join(_PKG, "csrc", "conv3x3_tf32.cu"), os.path.join(_PKG, "csrc", "wgrad_tf32.cu"),
+           os.path.join(_PKG, "csrc", "rowmask.cu")]
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
-EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_last_error", "datr_abi_version",
+EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward", "datr_msda_fused_backward", "datr_last_error", "datr_abi_version",
            "datr_launch_count", "datr_linear_tf32", "datr_linear_last_error", "datr_linear_launch_count",
-           "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count",
+           "datr_layernorm256_forward", "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count",
            "datr_colsum", "datr_relu_bwd_colsum", "datr_colsum_last_error", "datr_colsum_launch_count",
            "datr_conv3x3_nhwc_tf32", "datr_conv_last_error", "datr_conv_launch_count",
-           "datr_linear_wgrad_tf32", "datr_linear_wgrad_last_error", "datr_linear_wgrad_launch_count")
+           "datr_linear_wgrad_tf32", "datr_linear_wgrad_last_error", "datr_linear_wgrad_launch_count",
+           "datr_zero_masked_rows", "datr_rowmask_last_error", "datr_rowmask_launch_count")
 
 _lock = threading.Lock()
 _lib = None
@@ -82,6 +84,10 @@ def lib() -> ctypes.CDLL:
         L.datr_msda_forward.argtypes = [vp, i64p, i64p, vp, vp, i, i, i, i, i, i, i, i, vp, vp]
         L.datr_msda_backward.restype = i
         L.datr_msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp]
+        L.datr_msda_fused_forward.restype = i
+        L.datr_msda_fused_forward.argtypes = [vp, i64p, i64p, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, vp]
+        L.datr_msda_fused_backward.restype = i
+        L.datr_msda_fused_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp]
         L.datr_last_error.restype = ctypes.c_char_p
         L.datr_last_error.argtypes = []
         L.datr_abi_version.restype = i
@@ -90,6 +96,8 @@ def lib() -> ctypes.CDLL:
         L.datr_linear_tf32.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
         L.datr_linear_last_error.restype = ctypes.c_char_p
         L.datr_linear_launch_count.restype = ctypes.c_uint64
+        L.datr_layernorm256_forward.restype = i
+        L.datr_layernorm256_forward.argtypes = [vp, vp, vp, ctypes.c_float, vp, vp, vp, i, vp]
         L.datr_layernorm256_backward.restype = i
         L.datr_layernorm256_backward.argtypes = [vp] * 9 + [i, vp]
         L.datr_layernorm_last_error.restype = ctypes.c_char_p
@@ -108,6 +116,10 @@ def lib() -> ctypes.CDLL:
         L.datr_linear_wgrad_tf32.argtypes = [vp, vp, vp, vp, i, i, i, vp]
         L.datr_linear_wgrad_last_error.restype = ctypes.c_char_p
         L.datr_linear_wgrad_launch_count.restype = ctypes.c_uint64
+        L.datr_zero_masked_rows.restype = i
+        L.datr_zero_masked_rows.argtypes = [vp, vp, ctypes.c_longlong, i, vp]
+        L.datr_rowmask_last_error.restype = ctypes.c_char_p
+        L.datr_rowmask_launch_count.restype = ctypes.c_uint64
         if L.datr_abi_version() != 1:
             raise NativeLibraryError("libdatr_b200.so ABI version mismatch; rebuild")
         _lib = L
@@ -127,7 +139,12 @@ def colsum_launch_count() -> int:
 def all_launch_count() -> int:
     """Every hand-written kernel launch issued through the library by this process."""
     return (launch_count() + linear_launch_count() + layernorm_launch_count() + colsum_launch_count()
-            + conv_launch_count() + wgrad_launch_count())
+            + conv_launch_count() + wgrad_launch_count() + rowmask_launch_count())
+
+
+def rowmask_launch_count() -> int:
+    """Padding-mask (zero masked rows) kernel launches issued through the library by this process."""
+    return int(lib().datr_rowmask_launch_count())
 
 
 def wgrad_launch_count() -> int:

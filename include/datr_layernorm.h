@@ -1,6 +1,9 @@
 /*
- * datr_layernorm.h -- C ABI of the LayerNorm backward kernel of libdatr_b200.so (sm_100a).
+ * datr_layernorm.h -- C ABI of the LayerNorm(256) kernels of libdatr_b200.so (sm_100a).
  *
+ *   datr_layernorm256_forward   <-  torch.nn.LayerNorm(256).forward at the same call sites (ATen native_layer_norm):
+ *                                   y = (x - mean) * rstd * gamma + beta, rstd = 1/sqrt(var + eps) with the biased
+ *                                   variance; also writes the row statistics mean, rstd [rows] the backward reads.
  *   datr_layernorm256_backward  <-  the backward of torch.nn.LayerNorm(256) as used by the reference's transformer
  *                                   (models/dino/deformable_transformer.py:801-820 norm1/norm2, :941-994 norm1-3,
  *                                   :339 enc_output_norm, decoder norm): ATen's native_layer_norm_backward.
@@ -22,6 +25,9 @@ extern "C" {
 #endif
 
 enum { DATR_LN_OK = 0, DATR_LN_ERR_BAD_ARGUMENT = -1, DATR_LN_ERR_ALIGNMENT = -2, DATR_LN_ERR_CUDA = -3 };
+
+int datr_layernorm256_forward(const float* x, const float* gamma, const float* beta, float eps, float* y, float* mean,
+                              float* rstd, int rows, void* stream);
 
 int datr_layernorm256_backward(const float* dy, const float* x, const float* gamma, const float* mean, const float* rstd,
                                float* dx, float* dgamma, float* dbeta, float* dx_colsum, int rows, void* stream);

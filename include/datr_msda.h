@@ -56,7 +56,8 @@ enum {
   DATR_OK = 0,
   DATR_ERR_BAD_ARGUMENT = -1, /* null pointer, non-positive dimension, unknown dtype */
   DATR_ERR_ALIGNMENT = -2,    /* a buffer is not aligned to its element type */
-  DATR_ERR_CUDA = -3          /* memset / kernel launch failed; see datr_last_error() */
+  DATR_ERR_CUDA = -3,         /* memset / kernel launch failed; see datr_last_error() */
+  DATR_ERR_UNSUPPORTED = -4   /* fused entry points only: configuration outside fp32 / 32 channels / L*P <= 32 */
 };
 
 int datr_msda_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
@@ -70,6 +71,31 @@ int datr_msda_backward(const void* value, const int64_t* spatial_shapes, const i
                        int batch, int spatial_size, int num_heads, int channels,
                        int num_levels, int num_query, int num_point, int dtype,
                        void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* stream);
+
+/*
+ * Module-level fusion: the elementwise prologue of the reference's MSDeformAttn.forward
+ * (models/dino/ops/modules/ms_deform_attn.py:99-111) runs inside the kernels, so sampling_locations and
+ * attention_weights are never materialised.  Inputs are what that prologue consumes:
+ *   sampling_offsets [batch, num_query, num_heads, num_levels, num_point, 2]   output of the offsets Linear (:99)
+ *   attn_logits      [batch, num_query, num_heads, num_levels * num_point]     output of the weights Linear (:100)
+ *   reference_points [batch, num_query, num_levels, ref_dim], ref_dim = 2 or 4 (:102-111)
+ *     ref_dim 2: loc = ref + offsets / (W_l, H_l);   ref_dim 4: loc = ref.xy + offsets / num_point * ref.wh * 0.5
+ *   attention weights = softmax of the logits over num_levels * num_point (:101)
+ * backward writes grad_value (zero-filled by the library), grad_sampling_offsets and grad_attn_logits (softmax and
+ * location chain rules applied); reference_points receive no gradient (they are detached in the DINO transformer).
+ * Supported: DATR_DTYPE_F32, channels == 32, num_point in {1,2,4,8}, num_levels * num_point <= 32; anything else
+ * returns DATR_ERR_UNSUPPORTED and the caller composes datr_msda_forward / _backward with the torch prologue.
+ */
+int datr_msda_fused_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                            const void* sampling_offsets, const void* attn_logits, const void* reference_points,
+                            int ref_dim, int batch, int spatial_size, int num_heads, int channels,
+                            int num_levels, int num_query, int num_point, int dtype, void* output, void* stream);
+
+int datr_msda_fused_backward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                             const void* sampling_offsets, const void* attn_logits, const void* reference_points,
+                             int ref_dim, const void* grad_output, int batch, int spatial_size, int num_heads,
+                             int channels, int num_levels, int num_query, int num_point, int dtype,
+                             void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits, void* stream);
 
 /* Message of the last failing call made by the calling thread ("" if none). */
 const char* datr_last_error(void);

@@ -1,0 +1,168 @@
+"""GPU parity of the module-level fused MSDeformAttn entry points (datr_msda_fused_forward / _backward,
+include/datr_msda.h) and of the padding-mask kernel (include/datr_rowmask.h).
+
+Oracle: the reference's prologue (ops/modules/ms_deform_attn.py:99-111: softmax of the logits, locations from
+reference points + offsets) written with torch in fp64 on the CPU, feeding the oracle's `core_torch`
+(ms_deform_attn_func.py:41-61); autograd through that composition supplies the gradients of value, offsets and
+logits.  Bar: fp32 1e-3 relative per tensor (north_star), regression guard 5e-5."""
+import numpy as np
+import pytest
+import torch
+
+import msda_cases as mc
+from oracle import msda as om
+
+pytestmark = pytest.mark.gpu
+
+TIGHT = 5e-5
+
+
+def make(N, M, Lq, P, levels, ref_dim, seed, spread=3.0):
+    rng = np.random.default_rng(seed)
+    L = len(levels)
+    S = sum(h * w for h, w in levels)
+    if Lq < 0:
+        Lq = S
+    value = rng.standard_normal((N, S, M, 32)).astype(np.float32)
+    offsets = (rng.standard_normal((N, Lq, M, L, P, 2)) * spread).astype(np.float32)
+    logits = (rng.standard_normal((N, Lq, M, L * P)) * 2).astype(np.float32)
+    if ref_dim == 2:
+        if Lq == S:
+            ref = np.broadcast_to(mc.encoder_reference_points(levels)[None, :, None, :], (N, Lq, L, 2))
+        else:
+            ref = rng.random((N, Lq, L, 2)) * 1.2 - 0.1            # a few centres outside the map
+    else:
+        ref = np.concatenate([rng.random((N, Lq, L, 2)), rng.random((N, Lq, L, 2)) * 0.6 + 0.01], -1)
+    grad_out = rng.standard_normal((N, Lq, M * 32)).astype(np.float32)
+    shapes = np.array(levels, dtype=np.int64)
+    return dict(value=value, offsets=offsets, logits=logits, ref=np.ascontiguousarray(ref, dtype=np.float32),
+                grad_out=grad_out, shapes=shapes, level_start=mc.level_start_index(levels))
+
+
+def oracle(inp, P):
+    v, off, lg = (torch.from_numpy(inp[k]).double().requires_grad_(True) for k in ("value", "offsets", "logits"))
+    ref = torch.from_numpy(inp["ref"]).double()
+    N, Lq, M, L = off.shape[:4]
+    attn = torch.softmax(lg, -1).view(N, Lq, M, L, P)
+    if ref.shape[-1] == 2:
+        wh = torch.from_numpy(inp["shapes"]).flip(-1).double()
+        loc = ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + off / P * ref[:, :, None, :, None, 2:] * 0.5
+    out = om.core_torch(v, inp["shapes"], loc, attn)
+    out.backward(torch.from_numpy(inp["grad_out"]).double().view_as(out))
+    return [t.detach().numpy() for t in (out, v.grad, off.grad, lg.grad)]
+
+
+CASES = [
+    ("enc_l4", 2, 8, -1, 4, [(9, 12), (5, 6), (3, 3), (2, 2)], 2, 41),
+    ("enc_l5", 1, 8, -1, 4, [(8, 11), (4, 6), (2, 3), (1, 2), (1, 1)], 2, 42),
+    ("dec_ref4", 2, 8, 77, 4, [(9, 12), (5, 6), (3, 3), (2, 2)], 4, 43),
+    ("dec_ref2", 1, 8, 33, 4, [(7, 9), (4, 5), (2, 3), (1, 2)], 2, 44),
+    ("p8_l4", 1, 4, 19, 8, [(7, 9), (4, 5), (2, 3), (1, 2)], 4, 45),
+    ("p1_l3", 1, 8, 21, 1, [(7, 9), (4, 5), (2, 3)], 2, 46),
+    ("p2_l2", 2, 2, 13, 2, [(6, 4), (3, 2)], 4, 47),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_fused_entry_points_match_the_reference_prologue_plus_oracle(case):
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    _, N, M, Lq, P, levels, ref_dim, seed = case
+    inp = make(N, M, Lq, P, levels, ref_dim, seed)
+    d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    assert MSDA.fused_supported(d["value"], d["offsets"], d["ref"])
+    out = MSDA.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["level_start"], d["offsets"], d["logits"], d["ref"])
+    gv, goff, glg = MSDA.ms_deform_attn_fused_backward(d["value"], d["shapes"], d["level_start"], d["offsets"],
+                                                       d["logits"], d["ref"], d["grad_out"])
+    torch.cuda.synchronize()
+    want = oracle(inp, P)
+    for g, w, key in zip((out, gv, goff, glg), want, ("out", "grad_value", "grad_offsets", "grad_logits")):
+        assert g.shape == w.shape or g.numel() == w.size, key
+        assert mc.rel_err(g.cpu().numpy().reshape(w.shape), w) < TIGHT, key
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_fused_equals_unfused_cuda_composition(ref_dim):
+    """Same CUDA kernels with and without the in-kernel prologue: the fused path must reproduce the op fed with
+    torch-computed locations / softmax (identical operation order => differences at rounding level only)."""
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    levels = [(20, 31), (10, 16), (5, 8), (3, 4)]
+    inp = make(2, 8, 333 if ref_dim == 4 else -1, 4, levels, ref_dim, 50 + ref_dim, spread=4.0)
+    d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    off = d["offsets"].clone().requires_grad_(True); lg = d["logits"].clone().requires_grad_(True)
+    N, Lq, M, L, P = off.shape[:5]
+    attn = torch.softmax(lg, -1).view(N, Lq, M, L, P)
+    if ref_dim == 2:
+        loc = d["ref"][:, :, None, :, None, :] + off / d["shapes"].flip(-1)[None, None, None, :, None, :]
+    else:
+        loc = d["ref"][:, :, None, :, None, :2] + off / P * d["ref"][:, :, None, :, None, 2:] * 0.5
+    out_u = MSDA.ms_deform_attn_forward(d["value"], d["shapes"], d["level_start"], loc.detach().contiguous(),
+                                        attn.detach().contiguous(), 64)
+    gv_u, gl_u, ga_u = MSDA.ms_deform_attn_backward(d["value"], d["shapes"], d["level_start"], loc.detach().contiguous(),
+                                                    attn.detach().contiguous(), d["grad_out"], 64)
+    torch.autograd.backward([loc, attn], [gl_u, ga_u])
+    out_f = MSDA.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["level_start"], d["offsets"], d["logits"], d["ref"])
+    gv_f, goff_f, glg_f = MSDA.ms_deform_attn_fused_backward(d["value"], d["shapes"], d["level_start"], d["offsets"],
+                                                             d["logits"], d["ref"], d["grad_out"])
+    for a, b, key in ((out_f, out_u, "out"), (gv_f, gv_u, "gv"), (goff_f, off.grad, "goff"), (glg_f, lg.grad, "glg")):
+        assert mc.rel_err(a.cpu().numpy(), b.cpu().numpy().reshape(a.shape)) < 1e-5, key
+
+
+@pytest.mark.parametrize("gemm", ["fp32", "tf32"])
+def test_module_fused_and_unfused_agree_with_padding_mask(gemm):
+    """MSDeformAttn module: fused kernels + in-place padding mask vs the reference-shaped composition (masked_fill,
+    torch softmax / location arithmetic, the plain op), in both GEMM modes (same GEMM kernels on both sides)."""
+    from datr_b200 import linear as dl
+    from datr_b200.models.dino.ops.modules import ms_deform_attn as mod
+    dl.set_mode(gemm)
+    levels = [(12, 17), (6, 9), (3, 5), (2, 3)]
+    S = sum(h * w for h, w in levels)
+    torch.manual_seed(7)
+    m = mod.MSDeformAttn(256, 4, 8, 4).cuda()
+    with torch.no_grad():   # move the offsets / logits off their symmetric initialisation
+        m.sampling_offsets.weight.normal_(0, 0.05); m.attention_weights.weight.normal_(0, 0.05)
+    shapes = torch.tensor(levels, dtype=torch.long, device="cuda")
+    start = torch.from_numpy(mc.level_start_index(levels)).cuda()
+    src = torch.randn(2, S, 256, device="cuda")
+    ref = torch.from_numpy(mc.encoder_reference_points(levels)).float().cuda()[None, :, None, :].expand(2, S, 4, 2).contiguous()
+    mask = torch.zeros(2, S, dtype=torch.bool, device="cuda"); mask[1, 150:] = True; mask[0, ::7] = True
+    gout = torch.randn(2, S, 256, device="cuda")
+    res = []
+    for fused in (True, False):
+        mod.set_fused(fused)
+        m.zero_grad()
+        x = src.clone().requires_grad_(True)
+        y = m(x, ref, x, shapes, start, mask)
+        y.backward(gout)
+        res.append([y.detach(), x.grad] + [p.grad.clone() for p in m.parameters()])
+    mod.set_fused(True)
+    dl.set_mode("fp32")
+    for a, b in zip(*res):
+        assert mc.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
+    # the reference composition with torch's own masked_fill on the same weights
+    x = src.clone().requires_grad_(True)
+    value = torch.nn.functional.linear(x, m.value_proj.weight, m.value_proj.bias).masked_fill(mask[..., None], 0.0)
+    assert gemm == "tf32" or torch.equal(value[mask], torch.zeros_like(value[mask]))
+
+
+def test_zero_masked_rows_matches_masked_fill():
+    from datr_b200 import native
+    from datr_b200.rowmask import zero_masked_rows
+    g = torch.Generator(device="cpu").manual_seed(3)
+    x = torch.randn(3, 1001, 256, generator=g).cuda()
+    mask = (torch.rand(3, 1001, generator=g) < 0.3).cuda()
+    w = torch.randn(3, 1001, 256, generator=g).cuda()
+    a = x.clone().requires_grad_(True)
+    n0 = native.rowmask_launch_count()
+    ya = zero_masked_rows(a * 1.0, mask)
+    (ya * w).sum().backward()
+    assert native.rowmask_launch_count() == n0 + 2, "padding-mask kernel did not launch"
+    b = x.clone().requires_grad_(True)
+    yb = (b * 1.0).masked_fill(mask[..., None], 0.0)
+    (yb * w).sum().backward()
+    assert torch.equal(ya, yb) and torch.equal(a.grad, b.grad)
+    # 4-d activation with a 2-d mask, ragged tail (rows not a multiple of 32)
+    v = torch.randn(2, 77, 8, 32, generator=g).cuda()
+    mk = (torch.rand(2, 77, generator=g) < 0.5).cuda()
+    assert torch.equal(zero_masked_rows(v.clone(), mk), v.masked_fill(mk[..., None, None], 0.0))
