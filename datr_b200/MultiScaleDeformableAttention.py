@@ -125,13 +125,25 @@ def fused_supported(value, sampling_offsets, reference_points) -> bool:
         and reference_points.dtype == torch.float32 and not reference_points.requires_grad
 
 
+def _row_stride(name, t):
+    """Elements between consecutive queries of a [N, Lq, ...] tensor whose per-query block is contiguous (the tensor
+    may be a column slice of a wider [N, Lq, R] GEMM output)."""
+    inner, want = 1, []
+    for d in reversed(t.shape[2:]):
+        want.append(inner)
+        inner *= d
+    if list(t.stride()[2:]) != want[::-1] or t.stride(1) < inner or (t.shape[0] > 1 and t.stride(0) != t.shape[1] * t.stride(1)):
+        raise RuntimeError(f"{name}: each query's block must be contiguous and the rows uniformly strided")
+    return t.stride(1)
+
+
 def _check_fused(value, spatial_shapes, level_start_index, offsets, logits, ref, extra=()):
     named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
              ("sampling_offsets", offsets), ("attn_logits", logits), ("reference_points", ref), *extra]
     if not value.is_cuda:
         raise RuntimeError("Not implemented on the CPU")
     for name, t in named:
-        if not t.is_contiguous():
+        if name not in ("sampling_offsets", "attn_logits") and not t.is_contiguous():
             raise RuntimeError(f"{name} tensor has to be contiguous")
         if not t.is_cuda or t.device != value.device:
             raise RuntimeError(f"{name} must be a CUDA tensor on the device of value")
@@ -142,20 +154,22 @@ def _check_fused(value, spatial_shapes, level_start_index, offsets, logits, ref,
         raise RuntimeError("spatial_shapes and level_start_index must be int64")
     N, S, M, D = value.shape
     L = spatial_shapes.shape[0]
-    if offsets.dim() != 6 or ref.dim() != 4:
-        raise RuntimeError("expected sampling_offsets[N,Lq,M,L,P,2], reference_points[N,Lq,L,2|4]")
+    if offsets.dim() != 6 or ref.dim() != 4 or logits.dim() < 3:
+        raise RuntimeError("expected sampling_offsets[N,Lq,M,L,P,2], attn_logits[N,Lq,M,L*P], reference_points[N,Lq,L,2|4]")
     Lq, P, R = offsets.shape[1], offsets.shape[4], ref.shape[-1]
     if tuple(offsets.shape) != (N, Lq, M, L, P, 2) or logits.numel() != N * Lq * M * L * P \
             or tuple(ref.shape) != (N, Lq, L, R) or R not in (2, 4) or level_start_index.numel() != L:
         raise RuntimeError("inconsistent fused MSDeformAttn argument shapes")
-    return N, S, M, D, L, Lq, P, R
+    if tuple(logits.shape[:2]) != (N, Lq):
+        raise RuntimeError("attn_logits must be [N, Lq, ...]")
+    return N, S, M, D, L, Lq, P, R, _row_stride("sampling_offsets", offsets), _row_stride("attn_logits", logits)
 
 
 def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
                                  reference_points):
     """Extension (not in the reference's module): MSDeformAttn.forward's prologue + the op in one kernel."""
-    N, S, M, D, L, Lq, P, R = _check_fused(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
-                                           reference_points)
+    N, S, M, D, L, Lq, P, R, so, sl = _check_fused(value, spatial_shapes, level_start_index, sampling_offsets,
+                                                   attn_logits, reference_points)
     lib = native.lib()
     with torch.cuda.device(value.device):
         out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
@@ -164,7 +178,7 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampl
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
         rc = lib.datr_msda_fused_forward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-                                         sampling_offsets.data_ptr(), attn_logits.data_ptr(),
+                                         sampling_offsets.data_ptr(), so, attn_logits.data_ptr(), sl,
                                          reference_points.data_ptr(), R, N, S, M, D, L, Lq, P, 0, out.data_ptr(),
                                          stream.cuda_stream)
         if _timers is not None:
@@ -176,22 +190,35 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampl
 
 
 def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
-                                  reference_points, grad_output):
-    N, S, M, D, L, Lq, P, R = _check_fused(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
-                                           reference_points, extra=(("grad_output", grad_output),))
+                                  reference_points, grad_output, merged_grad=None):
+    """Returns [grad_value, grad_sampling_offsets, grad_attn_logits].  The two last gradients mirror the memory layout
+    of their inputs; `merged_grad` (optional, [N, Lq, R] with R = the common row stride) is the buffer they are
+    carved from when offsets and logits are column slices [0, 2T) and [2T, 3T) of one [N, Lq, R] GEMM output."""
+    N, S, M, D, L, Lq, P, R, so, sl = _check_fused(value, spatial_shapes, level_start_index, sampling_offsets,
+                                                   attn_logits, reference_points, extra=(("grad_output", grad_output),))
     if grad_output.numel() != N * Lq * M * D:
         raise RuntimeError("grad_output has the wrong number of elements")
     lib = native.lib()
     with torch.cuda.device(value.device):
         grad_value = torch.empty_like(value)            # zero-filled by the library on the stream
-        grad_off = torch.empty_like(sampling_offsets)
-        grad_logits = torch.empty_like(attn_logits)
+        T = M * L * P
+        if merged_grad is not None:
+            if so != sl or tuple(merged_grad.shape) != (N, Lq, so) or not merged_grad.is_contiguous() or so < 3 * T:
+                raise RuntimeError("merged_grad must be a contiguous [N, Lq, row_stride] buffer")
+            grad_off = merged_grad[..., :2 * T].view(sampling_offsets.shape)
+            grad_logits = merged_grad[..., 2 * T:3 * T].view(attn_logits.shape)
+        else:
+            grad_off = torch.empty(sampling_offsets.shape, dtype=value.dtype, device=value.device)
+            grad_logits = torch.empty(attn_logits.shape, dtype=value.dtype, device=value.device)
+        go, gl = _row_stride("grad_offsets", grad_off), _row_stride("grad_logits", grad_logits)
+        if merged_grad is None and (so != go or sl != gl):   # strided inputs, dense gradients: not expressible
+            raise RuntimeError("strided sampling_offsets / attn_logits need merged_grad")
         stream = torch.cuda.current_stream()
         if _timers is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
         rc = lib.datr_msda_fused_backward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-                                          sampling_offsets.data_ptr(), attn_logits.data_ptr(),
+                                          sampling_offsets.data_ptr(), so, attn_logits.data_ptr(), sl,
                                           reference_points.data_ptr(), R, grad_output.data_ptr(),
                                           N, S, M, D, L, Lq, P, 0, grad_value.data_ptr(), grad_off.data_ptr(),
                                           grad_logits.data_ptr(), stream.cuda_stream)

@@ -290,7 +290,8 @@ int datr_linear_tf32(const float* x, const float* w, const float* bias, const fl
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   CUtensorMap mx, mw;
   static const int force_bn = getenv("DATR_LINEAR_BN") ? atoi(getenv("DATR_LINEAR_BN")) : 0;   // tuning hook
-  const bool wide = force_bn ? force_bn == 256 : N > 256;   // 128-wide tiles fill the 148 SMs better at N <= 256
+  // 128-wide tiles fill the 148 SMs better at N <= 256 and waste no MMA columns when N mod 256 is in (0, 128]
+  const bool wide = force_bn ? force_bn == 256 : (N > 256 && (N % 256 == 0 || N % 256 > 128));
   if (int rc = make_map(&mx, x, M, K, BM)) return rc;
   if (int rc = make_map(&mw, w, N, K, wide ? 256 : 128)) return rc;
   return wide ? launch<256, 3>(mx, mw, bias, residual, y, M, N, K, relu, stream)

@@ -204,9 +204,10 @@ struct RowTaps {
   float x[kChunks], y[kChunks], a[kChunks];  // location and softmax weight of samples c*8+sub
 };
 
+// `off` / `logit` point at the (query, head) row: offsets[bq][m][0][0][0], logits[bq][m][0]
 template <int kMode, int kP>
 __device__ __forceinline__ RowTaps fused_taps(const float* __restrict__ off, const float* __restrict__ logit,
-                                              const float* __restrict__ ref, long long bq, long long row, int sub,
+                                              const float* __restrict__ ref, long long bq, int sub,
                                               int L, int LP, const LevelGeom* geom) {
   RowTaps t;
   float mx = -INFINITY;
@@ -216,9 +217,9 @@ __device__ __forceinline__ RowTaps fused_taps(const float* __restrict__ off, con
     t.x[c] = t.y[c] = 0.f;
     t.a[c] = -INFINITY;
     if (s < LP) {
-      const float2 xy = __ldg(reinterpret_cast<const float2*>(off) + row * LP + s);
+      const float2 xy = __ldg(reinterpret_cast<const float2*>(off) + s);
       t.x[c] = xy.x; t.y[c] = xy.y;
-      t.a[c] = __ldg(logit + row * LP + s);
+      t.a[c] = __ldg(logit + s);
       mx = fmaxf(mx, t.a[c]);
     }
   }
@@ -268,8 +269,8 @@ template <int kP, int kBatch, int kMode>
 __global__ void __launch_bounds__(256)
 msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                  const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                 const float* __restrict__ attn, const float* __restrict__ ref, int N, int S, int M, int L, int Lq,
-                 float* __restrict__ out) {
+                 const float* __restrict__ attn, const float* __restrict__ ref, long long ostride, long long lstride,
+                 int N, int S, int M, int L, int Lq, float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem[];
   LevelGeom* geom = reinterpret_cast<LevelGeom*>(smem);
   const int LP = L * kP, ws = table_stride(LP), ps = pix_stride(LP);
@@ -302,7 +303,9 @@ msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
       publish(s, xy.x, xy.y, __ldg(attn + row * LP + s));
     }
   } else {
-    const RowTaps t = fused_taps<kMode, kP>(loc, attn, ref, bq, row, sub, L, LP, geom);
+    // fused modes: rows of the offsets / logits tensors may be strided (both can live in one merged GEMM output)
+    const RowTaps t = fused_taps<kMode, kP>(loc + bq * ostride + (long long)m * LP * 2, attn + bq * lstride + (long long)m * LP,
+                                            ref, bq, sub, L, LP, geom);
 #pragma unroll
     for (int c = 0; c < kChunks; ++c)
       if (c * 8 + sub < LP) publish(c * 8 + sub, t.x[c], t.y[c], t.a[c]);
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(256, 4)
 msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                  const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                  const float* __restrict__ attn, const float* __restrict__ ref, const float* __restrict__ grad_out,
-                 int N, int S, int M, int L, int Lq,
+                 long long ostride, long long lstride, int N, int S, int M, int L, int Lq,
                  float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
   extern __shared__ __align__(16) unsigned char smem[];
   LevelGeom* geom = reinterpret_cast<LevelGeom*>(smem);
@@ -398,7 +401,8 @@ msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
       publish(s, xy.x, xy.y, __ldg(attn + row * LP + s));
     }
   } else {
-    const RowTaps t = fused_taps<kMode, kP>(loc, attn, ref, bq, row, sub, L, LP, geom);
+    const RowTaps t = fused_taps<kMode, kP>(loc + bq * ostride + (long long)m * LP * 2, attn + bq * lstride + (long long)m * LP,
+                                            ref, bq, sub, L, LP, geom);
 #pragma unroll
     for (int c = 0; c < kChunks; ++c) {
       soft[c] = t.a[c];
@@ -488,8 +492,9 @@ msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
           gx = ((gx * 0.5f) * rr.z) / float(kP);
           gy = ((gy * 0.5f) * rr.w) / float(kP);
         }
-        grad_attn[row * LP + s] = soft[c] * (__uint_as_float(res[c].x) - dot);
-        reinterpret_cast<float2*>(grad_loc)[row * LP + s] = make_float2(gx, gy);
+        // gradients use the row strides of their inputs (a merged offsets+logits gradient is one GEMM operand)
+        grad_attn[bq * lstride + (long long)m * LP + s] = soft[c] * (__uint_as_float(res[c].x) - dot);
+        *reinterpret_cast<float2*>(grad_loc + bq * ostride + ((long long)m * LP + s) * 2) = make_float2(gx, gy);
       }
     }
   }
@@ -640,14 +645,14 @@ int allow_big_smem() {
 
 // launchers of the fp32 / D = 32 kernels; mode 0 = materialised locations + weights, 1 / 2 = fused prologue (R = 2 / 4)
 int launch_fwd_fast(int mode, const float* v, const int64_t* shapes, const int64_t* lstart, const float* lc,
-                    const float* at, const float* ref, int N, int S, int M, int L, int Lq, int P, float* o,
-                    cudaStream_t stream) {
+                    const float* at, const float* ref, long long ostride, long long lstride, int N, int S, int M, int L,
+                    int Lq, int P, float* o, cudaStream_t stream) {
   const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
   if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
   const int LP = L * P;
   const size_t smem = kGeomBytes + (size_t)kRowsPerCta * (table_stride(LP) * 16 + pix_stride(LP) * 4);
 #define DATR_FWD(PP, BB, MM) \
-  msda_fwd_f32_d32<PP, BB, MM><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, N, S, M, L, Lq, o)
+  msda_fwd_f32_d32<PP, BB, MM><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, ostride, lstride, N, S, M, L, Lq, o)
 #define DATR_FWD_P(MM)                  \
   switch (P) {                          \
     case 1: DATR_FWD(1, 1, MM); break;  \
@@ -662,14 +667,14 @@ int launch_fwd_fast(int mode, const float* v, const int64_t* shapes, const int64
 }
 
 int launch_bwd_fast(int mode, const float* v, const int64_t* shapes, const int64_t* lstart, const float* lc,
-                    const float* at, const float* ref, const float* go, int N, int S, int M, int L, int Lq, int P,
-                    float* gv, float* gl, float* ga, cudaStream_t stream) {
+                    const float* at, const float* ref, const float* go, long long ostride, long long lstride, int N, int S,
+                    int M, int L, int Lq, int P, float* gv, float* gl, float* ga, cudaStream_t stream) {
   const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
   if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
   const size_t smem = kGeomBytes + (size_t)kRowsPerCta * table_stride(L * P) * 48;
   if (int rc = allow_big_smem()) return rc;
 #define DATR_BWD(PP, MM) \
-  msda_bwd_f32_d32<PP, MM><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, go, N, S, M, L, Lq, gv, gl, ga)
+  msda_bwd_f32_d32<PP, MM><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, go, ostride, lstride, N, S, M, L, Lq, gv, gl, ga)
 #define DATR_BWD_P(MM)               \
   switch (P) {                       \
     case 1: DATR_BWD(1, MM); break;  \
@@ -692,6 +697,16 @@ int check_fused(const void* ref, int ref_dim, int D, int P, int L, int dtype) {
   return DATR_OK;
 }
 
+// row strides (elements between consecutive queries) of the offsets / logits tensors; 0 = densely packed
+int check_strides(long long* ostride, long long* lstride, int M, int L, int P) {
+  const long long taps = (long long)M * L * P;
+  if (*ostride == 0) *ostride = taps * 2;
+  if (*lstride == 0) *lstride = taps;
+  if (*ostride < taps * 2 || *lstride < taps || (*ostride & 1))
+    return fail(DATR_ERR_BAD_ARGUMENT, "row strides must cover one row (and the offsets stride must be even)%s");
+  return DATR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -705,7 +720,7 @@ int datr_msda_forward(const void* value, const int64_t* shapes, const int64_t* l
   const long long rows = (long long)N * Lq * M;
   if (fast_ok(D, P, L, dtype, value, out, loc, attn))
     return launch_fwd_fast(0, static_cast<const float*>(value), shapes, lstart, static_cast<const float*>(loc),
-                           static_cast<const float*>(attn), nullptr, N, S, M, L, Lq, P, static_cast<float*>(out), stream);
+                           static_cast<const float*>(attn), nullptr, 0, 0, N, S, M, L, Lq, P, static_cast<float*>(out), stream);
   const long long ctas = (rows + 7) / 8;
   if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
   if (dtype == DATR_DTYPE_F32)
@@ -732,7 +747,7 @@ int datr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
   if (fast_ok(D, P, L, dtype, value, grad_out, grad_loc, grad_attn) && aligned(grad_value, 16) && aligned(loc, 8) &&
       aligned(attn, 4))
     return launch_bwd_fast(0, static_cast<const float*>(value), shapes, lstart, static_cast<const float*>(loc),
-                           static_cast<const float*>(attn), nullptr, static_cast<const float*>(grad_out), N, S, M, L, Lq, P,
+                           static_cast<const float*>(attn), nullptr, static_cast<const float*>(grad_out), 0, 0, N, S, M, L, Lq, P,
                            static_cast<float*>(grad_value), static_cast<float*>(grad_loc), static_cast<float*>(grad_attn),
                            stream);
   const long long ctas = (rows + 7) / 8;
@@ -751,26 +766,28 @@ int datr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
 }
 
 int datr_msda_fused_forward(const void* value, const int64_t* shapes, const int64_t* lstart, const void* offsets,
-                            const void* logits, const void* ref, int ref_dim, int N, int S, int M, int D, int L, int Lq,
-                            int P, int dtype, void* out, void* stream_) {
+                            long long ostride, const void* logits, long long lstride, const void* ref, int ref_dim, int N,
+                            int S, int M, int D, int L, int Lq, int P, int dtype, void* out, void* stream_) {
   if (int rc = check_common(value, shapes, lstart, offsets, logits, N, S, M, D, L, Lq, P, dtype)) return rc;
   if (!out) return fail(DATR_ERR_BAD_ARGUMENT, "null output pointer%s");
   if (int rc = check_fused(ref, ref_dim, D, P, L, dtype)) return rc;
+  if (int rc = check_strides(&ostride, &lstride, M, L, P)) return rc;
   if (!aligned(value, 16) || !aligned(out, 16) || !aligned(offsets, 8))
     return fail(DATR_ERR_ALIGNMENT, "value / output must be 16-byte aligned, offsets 8-byte aligned%s");
   return launch_fwd_fast(ref_dim == 2 ? 1 : 2, static_cast<const float*>(value), shapes, lstart,
                          static_cast<const float*>(offsets), static_cast<const float*>(logits),
-                         static_cast<const float*>(ref), N, S, M, L, Lq, P, static_cast<float*>(out),
+                         static_cast<const float*>(ref), ostride, lstride, N, S, M, L, Lq, P, static_cast<float*>(out),
                          static_cast<cudaStream_t>(stream_));
 }
 
 int datr_msda_fused_backward(const void* value, const int64_t* shapes, const int64_t* lstart, const void* offsets,
-                             const void* logits, const void* ref, int ref_dim, const void* grad_out, int N, int S, int M,
-                             int D, int L, int Lq, int P, int dtype, void* grad_value, void* grad_offsets,
-                             void* grad_logits, void* stream_) {
+                             long long ostride, const void* logits, long long lstride, const void* ref, int ref_dim,
+                             const void* grad_out, int N, int S, int M, int D, int L, int Lq, int P, int dtype,
+                             void* grad_value, void* grad_offsets, void* grad_logits, void* stream_) {
   if (int rc = check_common(value, shapes, lstart, offsets, logits, N, S, M, D, L, Lq, P, dtype)) return rc;
   if (!grad_out || !grad_value || !grad_offsets || !grad_logits) return fail(DATR_ERR_BAD_ARGUMENT, "null gradient pointer%s");
   if (int rc = check_fused(ref, ref_dim, D, P, L, dtype)) return rc;
+  if (int rc = check_strides(&ostride, &lstride, M, L, P)) return rc;
   if (!aligned(value, 16) || !aligned(grad_out, 16) || !aligned(grad_value, 16) || !aligned(offsets, 8) ||
       !aligned(grad_offsets, 8))
     return fail(DATR_ERR_ALIGNMENT, "value / grad_output / grad_value must be 16-byte aligned, offsets 8-byte aligned%s");
@@ -779,8 +796,8 @@ int datr_msda_fused_backward(const void* value, const int64_t* shapes, const int
   if (me != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaMemsetAsync(grad_value): %s", cudaGetErrorString(me));
   return launch_bwd_fast(ref_dim == 2 ? 1 : 2, static_cast<const float*>(value), shapes, lstart,
                          static_cast<const float*>(offsets), static_cast<const float*>(logits),
-                         static_cast<const float*>(ref), static_cast<const float*>(grad_out), N, S, M, L, Lq, P,
-                         static_cast<float*>(grad_value), static_cast<float*>(grad_offsets),
+                         static_cast<const float*>(ref), static_cast<const float*>(grad_out), ostride, lstride, N, S, M, L,
+                         Lq, P, static_cast<float*>(grad_value), static_cast<float*>(grad_offsets),
                          static_cast<float*>(grad_logits), stream);
 }
 

@@ -56,3 +56,35 @@ class MSDeformAttnFusedFunction(Function):
         grad_value, grad_off, grad_logits = MSDA.ms_deform_attn_fused_backward(
             value, shapes, level_start, offsets, logits, ref, grad_output.contiguous())
         return grad_value, None, None, grad_off, grad_logits, None
+
+
+class MSDeformAttnMergedFunction(Function):
+    """MSDeformAttnFusedFunction fed by ONE Linear: `merged` [N, Lq, 3*M*L*P] holds the sampling offsets in columns
+    [0, 2*M*L*P) and the attention logits in [2*M*L*P, 3*M*L*P) (the rows of `sampling_offsets.weight` and
+    `attention_weights.weight` stacked), and the backward returns one gradient of the same layout, so the two
+    projections of the query cost one GEMM forward and one dgrad + one wgrad backward."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, merged, reference_points, M, L, P):
+        N, Lq = merged.shape[:2]
+        T = M * L * P
+        ctx.dims = (M, L, P)
+        offsets = merged[..., :2 * T].view(N, Lq, M, L, P, 2)
+        logits = merged[..., 2 * T:].view(N, Lq, M, L * P)
+        output = MSDA.ms_deform_attn_fused_forward(value, value_spatial_shapes, value_level_start_index,
+                                                   offsets, logits, reference_points)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, merged, reference_points)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, merged, ref = ctx.saved_tensors
+        M, L, P = ctx.dims
+        N, Lq = merged.shape[:2]
+        T = M * L * P
+        grad_merged = torch.empty_like(merged)
+        grad_value, _, _ = MSDA.ms_deform_attn_fused_backward(
+            value, shapes, level_start, merged[..., :2 * T].view(N, Lq, M, L, P, 2),
+            merged[..., 2 * T:].view(N, Lq, M, L * P), ref, grad_output.contiguous(), merged_grad=grad_merged)
+        return grad_value, None, None, grad_merged, None, None, None, None

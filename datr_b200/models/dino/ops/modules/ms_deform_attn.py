@@ -16,7 +16,7 @@ from torch import nn
 from datr_b200 import MultiScaleDeformableAttention as MSDA
 from datr_b200 import linear as dl
 
-from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction
+from ..functions import MSDeformAttnFunction, MSDeformAttnFusedFunction, MSDeformAttnMergedFunction
 
 # Module-level fusion: softmax + sampling-location arithmetic inside the MSDeformAttn kernels.
 # DATR_MSDA_FUSED=0 (or set_fused(False)) composes the reference's op with the torch prologue instead.
@@ -86,12 +86,21 @@ class MSDeformAttn(nn.Module):
         value = dl.linear(input_flatten, self.value_proj.weight, self.value_proj.bias, zero_rows=input_padding_mask)
         value = value.view(N, S, M, self.d_model // M)
 
-        offsets = dl.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(N, Lq, M, L, P, 2)
-        logits = dl.linear(query, self.attention_weights.weight, self.attention_weights.bias).view(N, Lq, M, L * P)
-
         ref_dim = reference_points.shape[-1]
         if ref_dim not in (2, 4):
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {ref_dim} instead.")
+        if (_FUSED and P in (1, 2, 4, 8) and L * P <= 32 and query.dtype == torch.float32
+                and MSDA.fused_supported(value, query.new_empty((0, 0, M, L, P, 2)), reference_points)):
+            # the two projections of the query (sampling_offsets :99, attention_weights :100) as ONE GEMM over the
+            # stacked weights; the kernels read offsets and logits as column slices of its output
+            merged = dl.linear(query, torch.cat((self.sampling_offsets.weight, self.attention_weights.weight), 0),
+                               torch.cat((self.sampling_offsets.bias, self.attention_weights.bias), 0))
+            sampled = MSDeformAttnMergedFunction.apply(value, input_spatial_shapes, input_level_start_index, merged,
+                                                       reference_points.contiguous(), M, L, P)
+            return dl.linear(sampled, self.output_proj.weight, self.output_proj.bias, residual=residual)
+
+        offsets = dl.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(N, Lq, M, L, P, 2)
+        logits = dl.linear(query, self.attention_weights.weight, self.attention_weights.bias).view(N, Lq, M, L * P)
         if _FUSED and MSDA.fused_supported(value, offsets, reference_points):
             sampled = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                                       offsets, logits, reference_points.contiguous())

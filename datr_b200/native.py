@@ -85,9 +85,10 @@ def lib() -> ctypes.CDLL:
         L.datr_msda_backward.restype = i
         L.datr_msda_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp]
         L.datr_msda_fused_forward.restype = i
-        L.datr_msda_fused_forward.argtypes = [vp, i64p, i64p, vp, vp, vp, i, i, i, i, i, i, i, i, i, vp, vp]
+        ll = ctypes.c_longlong
+        L.datr_msda_fused_forward.argtypes = [vp, i64p, i64p, vp, ll, vp, ll, vp, i, i, i, i, i, i, i, i, i, vp, vp]
         L.datr_msda_fused_backward.restype = i
-        L.datr_msda_fused_backward.argtypes = [vp, i64p, i64p, vp, vp, vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp]
+        L.datr_msda_fused_backward.argtypes = [vp, i64p, i64p, vp, ll, vp, ll, vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp]
         L.datr_last_error.restype = ctypes.c_char_p
         L.datr_last_error.argtypes = []
         L.datr_abi_version.restype = i

@@ -81,18 +81,24 @@ int datr_msda_backward(const void* value, const int64_t* spatial_shapes, const i
  *   reference_points [batch, num_query, num_levels, ref_dim], ref_dim = 2 or 4 (:102-111)
  *     ref_dim 2: loc = ref + offsets / (W_l, H_l);   ref_dim 4: loc = ref.xy + offsets / num_point * ref.wh * 0.5
  *   attention weights = softmax of the logits over num_levels * num_point (:101)
+ * sampling_offsets and attn_logits may be row-strided views (`*_row_stride` = elements between consecutive
+ * queries, 0 = densely packed; everything inside one query's row is contiguous), so both can live in ONE GEMM output
+ * [batch * num_query, 3 * heads * levels * points]; the two gradients are written with the same strides and form one
+ * GEMM operand for the merged Linear's backward.
  * backward writes grad_value (zero-filled by the library), grad_sampling_offsets and grad_attn_logits (softmax and
  * location chain rules applied); reference_points receive no gradient (they are detached in the DINO transformer).
  * Supported: DATR_DTYPE_F32, channels == 32, num_point in {1,2,4,8}, num_levels * num_point <= 32; anything else
  * returns DATR_ERR_UNSUPPORTED and the caller composes datr_msda_forward / _backward with the torch prologue.
  */
 int datr_msda_fused_forward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                            const void* sampling_offsets, const void* attn_logits, const void* reference_points,
+                            const void* sampling_offsets, long long offsets_row_stride,
+                            const void* attn_logits, long long logits_row_stride, const void* reference_points,
                             int ref_dim, int batch, int spatial_size, int num_heads, int channels,
                             int num_levels, int num_query, int num_point, int dtype, void* output, void* stream);
 
 int datr_msda_fused_backward(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
-                             const void* sampling_offsets, const void* attn_logits, const void* reference_points,
+                             const void* sampling_offsets, long long offsets_row_stride,
+                             const void* attn_logits, long long logits_row_stride, const void* reference_points,
                              int ref_dim, const void* grad_output, int batch, int spatial_size, int num_heads,
                              int channels, int num_levels, int num_query, int num_point, int dtype,
                              void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits, void* stream);

@@ -109,6 +109,28 @@ def test_fused_equals_unfused_cuda_composition(ref_dim):
         assert mc.rel_err(a.cpu().numpy(), b.cpu().numpy().reshape(a.shape)) < 1e-5, key
 
 
+def test_merged_projection_layout_matches_separate_tensors():
+    """Offsets and logits as column slices of one [N, Lq, 3*M*L*P] GEMM output (row-strided views) and their gradients
+    carved from one merged buffer: bit-identical to the densely packed call (same kernels, same arithmetic)."""
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    from datr_b200.models.dino.ops.functions import MSDeformAttnMergedFunction
+    levels = [(9, 12), (5, 6), (3, 3), (2, 2)]
+    inp = make(2, 8, 77, 4, levels, 4, 61)
+    d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    N, Lq, M, L, P = d["offsets"].shape[:5]
+    T = M * L * P
+    merged = torch.cat((d["offsets"].reshape(N, Lq, 2 * T), d["logits"].reshape(N, Lq, T)), -1).contiguous()
+    out_d = MSDA.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["level_start"], d["offsets"], d["logits"], d["ref"])
+    gv_d, go_d, gl_d = MSDA.ms_deform_attn_fused_backward(d["value"], d["shapes"], d["level_start"], d["offsets"],
+                                                          d["logits"], d["ref"], d["grad_out"])
+    v = d["value"].clone().requires_grad_(True); mg = merged.clone().requires_grad_(True)
+    out_m = MSDeformAttnMergedFunction.apply(v, d["shapes"], d["level_start"], mg, d["ref"], M, L, P)
+    out_m.backward(d["grad_out"])
+    assert torch.equal(out_m, out_d)
+    assert torch.equal(mg.grad[..., :2 * T].reshape(go_d.shape), go_d) and torch.equal(mg.grad[..., 2 * T:].reshape(gl_d.shape), gl_d)
+    assert mc.rel_err(v.grad.cpu().numpy(), gv_d.cpu().numpy()) < 1e-5        # atomics: order-dependent rounding
+
+
 @pytest.mark.parametrize("gemm", ["fp32", "tf32"])
 def test_module_fused_and_unfused_agree_with_padding_mask(gemm):
     """MSDeformAttn module: fused kernels + in-place padding mask vs the reference-shaped composition (masked_fill,
@@ -138,8 +160,10 @@ def test_module_fused_and_unfused_agree_with_padding_mask(gemm):
         res.append([y.detach(), x.grad] + [p.grad.clone() for p in m.parameters()])
     mod.set_fused(True)
     dl.set_mode("fp32")
+    # fp32: the same arithmetic on both sides; tf32: the merged offsets+logits GEMM sums its K blocks in another order
+    # than the two separate GEMMs, and the sampling positions amplify that rounding (bar for this mode: 1e-2)
     for a, b in zip(*res):
-        assert mc.rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-4
+        assert mc.rel_err(a.cpu().numpy(), b.cpu().numpy()) < (1e-4 if gemm == "fp32" else 2e-3)
     # the reference composition with torch's own masked_fill on the same weights
     x = src.clone().requires_grad_(True)
     value = torch.nn.functional.linear(x, m.value_proj.weight, m.value_proj.bias).masked_fill(mask[..., None], 0.0)
