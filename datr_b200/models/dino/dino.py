@@ -30,7 +30,7 @@ from .backbone import build_backbone
 from .DA_utils import FCDiscriminator_img, decompose_features, get_prototype_class_wise, grad_reverse
 from .deformable_transformer import build_deformable_transformer
 from .dn_components import dn_post_process, prepare_for_cdn
-from .matcher import build_matcher, match_many
+from .matcher import BatchedMatch, batchable, build_matcher, match_many, matching_sets, prefetch, take_prefetched
 from .utils import MLP, sigmoid_focal_loss
 
 
@@ -271,6 +271,10 @@ class DINO(nn.Module):
             out = self._outputs_from(tuple(hs), tuple(reference), outputs_class, interm_class, ref_enc, init_box_proposal, dn_meta)
         if not self.training:
             return out
+        if targets is not None and torch.is_grad_enabled():
+            # the criterion's Hungarian matchings only need the source-domain predictions: start them now so that the
+            # host part overlaps the target-domain pass below (matcher.prefetch)
+            prefetch(getattr(self, "_prefetch_matcher", None), out, targets)
 
         # ---- domain adaptation -----------------------------------------------------------------
         da = {}
@@ -493,22 +497,32 @@ class SetCriterion(nn.Module):
 
         key_aux = "aux_outputs_target" if target_domain_flag else "aux_outputs"
         key_interm = "interm_outputs_target" if target_domain_flag else "interm_outputs"
-        pre = None
+        pre = nb = None
         if len(targets) > 0:
-            # all matchings of the step (final, auxiliary decoder layers, intermediate) in one batched pass
+            # all matchings of the step (final, auxiliary decoder layers, intermediate) in one batched pass; the
+            # num_boxes all-reduce (reference :767-770) rides along with it
             sets = [outputs_without_aux] + list(outputs.get(key_aux, [])) + ([outputs[key_interm]] if key_interm in outputs else [])
-            pre = match_many(self.matcher, sets, targets)
+            handle = None if target_domain_flag else take_prefetched(outputs, sets, targets)
+            if handle is None and batchable(self.matcher, sets):
+                handle = BatchedMatch(self.matcher, sets, targets)
+            if handle is not None:
+                pre, nb = handle.result()
+            else:
+                pre = match_many(self.matcher, sets, targets)
             indices = pre[0]
-            num_boxes = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=device)
             indices0, indices_list = indices, []
         else:       # no pseudo labels on this rank: still take part in the collective below
             indices = None
-            num_boxes = torch.as_tensor([1], dtype=torch.float, device=outputs["pred_logits"].device)
-        if is_dist_avail_and_initialized():
-            torch.distributed.all_reduce(num_boxes)
-        if indices is None:
-            num_boxes = num_boxes - 1
-        num_boxes = torch.clamp(num_boxes / get_world_size(), min=1).item()
+        if nb is not None:
+            num_boxes = nb      # counted (and all-reduced) by BatchedMatch without a host->device copy or a sync here
+        else:
+            n_local = sum(len(t["labels"]) for t in targets) if indices is not None else 1
+            num_boxes = torch.as_tensor([n_local], dtype=torch.float, device=outputs["pred_logits"].device)
+            if is_dist_avail_and_initialized():
+                torch.distributed.all_reduce(num_boxes)
+            if indices is None:
+                num_boxes = num_boxes - 1
+            num_boxes = torch.clamp(num_boxes / get_world_size(), min=1).item()
         if indices is None:
             return {}
 
@@ -576,6 +590,9 @@ def build_dino(args):
         dn_box_noise_scale=args.dn_box_noise_scale, dn_label_noise_ratio=args.dn_label_noise_ratio,
         dn_labelbook_size=getattr(args, "dn_labelbook_size", num_classes))
     matcher = build_matcher(args)
+    # lets DINO.forward start the criterion's matchings early (matcher.prefetch); a plain attribute, not a sub-module:
+    # module list and state_dict stay the reference's
+    object.__setattr__(model, "_prefetch_matcher", matcher)
 
     weight_dict = {"loss_ce": args.cls_loss_coef, "loss_bbox": args.bbox_loss_coef, "loss_giou": args.giou_loss_coef}
     plain = copy.deepcopy(weight_dict)

@@ -30,10 +30,18 @@ def box_iou(boxes1, boxes2):
     return inter / (union + 1e-6), union
 
 
-def generalized_box_iou(boxes1, boxes2):
-    """Pairwise GIoU [N,M] of xyxy boxes (degenerate boxes are a caller bug, as in the reference)."""
-    assert (boxes1[:, 2:] >= boxes1[:, :2]).all()
-    assert (boxes2[:, 2:] >= boxes2[:, :2]).all()
+def boxes_well_formed(boxes1, boxes2):
+    """Device-side bool scalar of the reference's degenerate-box asserts (util/box_ops.py:48-49), for callers that
+    check it later on the host instead of synchronising here."""
+    return (boxes1[:, 2:] >= boxes1[:, :2]).all() & (boxes2[:, 2:] >= boxes2[:, :2]).all()
+
+
+def generalized_box_iou(boxes1, boxes2, check=True):
+    """Pairwise GIoU [N,M] of xyxy boxes (degenerate boxes are a caller bug, as in the reference).
+    check=False skips the two asserts (each is a device synchronisation); pair it with boxes_well_formed()."""
+    if check:
+        assert (boxes1[:, 2:] >= boxes1[:, :2]).all()
+        assert (boxes2[:, 2:] >= boxes2[:, :2]).all()
     iou, union = box_iou(boxes1, boxes2)
     hull_wh = (torch.max(boxes1[:, None, 2:], boxes2[None, :, 2:])
                - torch.min(boxes1[:, None, :2], boxes2[None, :, :2])).clamp(min=0)
