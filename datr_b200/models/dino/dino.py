@@ -14,6 +14,7 @@ Hot-path differences that keep the numbers:
   * segmentation heads (DETRsegm) are outside the hot path (`masks=False` in every DINO/DATR config).
 """
 import copy
+import os
 import math
 from typing import List
 
@@ -319,6 +320,7 @@ class SetCriterion(nn.Module):
         super().__init__()
         self.num_classes, self.matcher, self.weight_dict = num_classes, matcher, weight_dict
         self.losses, self.focal_alpha = losses, focal_alpha
+        self.batched = os.environ.get("DATR_BATCHED_LOSSES", "1") != "0"    # False: one pass per prediction set, like the reference
 
     # ---- individual losses -------------------------------------------------------------------------
     def loss_labels(self, outputs, targets, indices, num_boxes, log=True):
@@ -401,6 +403,131 @@ class SetCriterion(nn.Module):
         return F.cross_entropy(F.normalize(q_s, dim=1) @ proto, eye * mask_s) \
             + F.cross_entropy(F.normalize(q_t, dim=1) @ proto, eye * mask_t)
 
+    # ---- batched loss groups ------------------------------------------------------------
+    # The step scores 13 prediction sets of identical shape against the same targets (final + 5 auxiliary decoder
+    # layers + intermediate, and the 6 de-noising sets).  The reference runs loss_labels / loss_boxes /
+    # loss_cardinality once per set (dino.py:723-933), ~40 tiny kernels each and as many again in the backward; here a
+    # FAMILY of sets is stacked along a leading group axis and scored in one pass, per-group sums taken at the end.
+    def _family_helpers(self, fam, counts, lens, groups, device):
+        """Constant index vectors of a family, cached by signature: for every matched pair (ordered group-major, then
+        image) the flattened (group, image) row and the image's offset into the concatenated targets."""
+        key = (fam, tuple(counts), tuple(lens), groups, str(device))
+        cache = self.__dict__.setdefault("_family_cache", {})
+        if key not in cache:
+            import numpy as np
+            bs = len(counts)
+            offs = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+            gb = np.concatenate([np.full(lens[i], g * bs + i, dtype=np.int64) for g in range(groups) for i in range(bs)])
+            toff = np.concatenate([np.full(lens[i], offs[i], dtype=np.int64) for g in range(groups) for i in range(bs)])
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = (torch.as_tensor(gb, device=device), torch.as_tensor(toff, device=device))
+        return cache[key]
+
+    def _batched_helpers(self, outputs, targets, pre):
+        """Everything the batched loss path needs that is a function of the target counts only (host-known), built
+        outside the captured segment: index helpers of both families and the per-image target counts."""
+        if list(self.losses) != ["labels", "boxes", "cardinality"] or "enc_outputs" in outputs:
+            return None
+        sets = [outputs] + list(outputs.get("aux_outputs", [])) + ([outputs["interm_outputs"]] if "interm_outputs" in outputs else [])
+        shape = outputs["pred_logits"].shape
+        if len(sets) != len(pre) or any(o["pred_logits"].shape != shape for o in sets):
+            return None
+        device = outputs["pred_logits"].device
+        counts = [len(t["labels"]) for t in targets]
+        lens = [int(src.numel()) for src, _ in pre[0]]
+        if sum(lens) == 0 or any([int(src.numel()) for src, _ in ind] != lens for ind in pre):
+            return None
+        helpers = {"m": self._family_helpers("m", counts, lens, len(sets), device)}
+        cached = getattr(self, "_n_tgt", None)
+        if cached is None or cached[0] != counts or cached[1].device != device:
+            self._n_tgt = cached = (counts, torch.as_tensor(counts, device=device))
+        helpers["n_tgt"] = cached[1]
+        dn_meta = outputs.get("dn_meta")
+        if self.training and dn_meta and "output_known_lbs_bboxes" in dn_meta:
+            known = dn_meta["output_known_lbs_bboxes"]
+            scalar, pad = dn_meta["num_dn_group"], dn_meta["pad_size"]
+            dsets = [known] + list(known.get("aux_outputs", []))
+            if any(o["pred_logits"].shape != known["pred_logits"].shape for o in dsets):
+                return None
+            key = ("dn_idx", tuple(counts), scalar, pad, len(dsets), str(device))
+            cache = self.__dict__.setdefault("_family_cache", {})
+            if key not in cache:
+                pos = self._dn_indices(targets, pad // scalar, scalar, device)
+                cache[key] = (torch.cat([o for o, _ in pos]).repeat(len(dsets)), torch.cat([t for _, t in pos]).repeat(len(dsets)))
+            dlens = [scalar * n for n in counts]
+            helpers["d"] = self._family_helpers("d", counts, dlens, len(dsets), device) + cache[key]
+        return helpers
+
+    def _family_losses(self, sets, targets, src, tgt, gb, toff, n_tgt, num_boxes, suffixes, log_group=None):
+        """loss_labels + loss_boxes + loss_cardinality of `sets` (same shapes) in one pass.  src / tgt: query and
+        target index of every matched pair, group-major; gb / toff: see _family_helpers."""
+        G = len(sets)
+        logits = torch.stack([o["pred_logits"] for o in sets]).flatten(0, 1)        # [G*bs, nq, nc]
+        boxes = torch.stack([o["pred_boxes"] for o in sets]).flatten(0, 1)          # [G*bs, nq, 4]
+        labels_all = torch.cat([t["labels"] for t in targets])
+        boxes_all = torch.cat([t["boxes"] for t in targets])
+        tsel = tgt + toff
+        matched = labels_all[tsel]
+        onehot = torch.zeros_like(logits)
+        onehot.index_put_((gb, src, matched), onehot.new_ones(()))
+        p = logits.sigmoid()
+        ce = F.binary_cross_entropy_with_logits(logits, onehot, reduction="none")
+        p_t = p * onehot + (1 - p) * (1 - onehot)
+        focal = ce * (1 - p_t) ** 2
+        if self.focal_alpha >= 0:
+            focal = (self.focal_alpha * onehot + (1 - self.focal_alpha) * (1 - onehot)) * focal
+        # sigmoid_focal_loss(...) * num_queries of the reference (= sum over the set / num_boxes)
+        loss_ce = focal.view(G, -1).sum(1) / num_boxes
+        sb = boxes[gb, src]
+        tb = boxes_all[tsel]
+        l1 = F.l1_loss(sb, tb, reduction="none")
+        giou = box_ops.paired_giou(box_ops.box_cxcywh_to_xyxy(sb), box_ops.box_cxcywh_to_xyxy(tb))
+        K = src.numel() // G
+        loss_bbox = l1.view(G, -1).sum(1) / num_boxes
+        loss_giou = (1 - giou).view(G, K).sum(1) / num_boxes
+        with torch.no_grad():
+            l1d = l1.detach().view(G, K, 4)
+            loss_xy = l1d[..., :2].sum((1, 2)) / num_boxes
+            loss_hw = l1d[..., 2:].sum((1, 2)) / num_boxes
+            n_pred = (logits.argmax(-1) != logits.shape[-1] - 1).sum(1).view(G, -1)
+            card = (n_pred.float() - n_tgt.float()[None]).abs().mean(1)
+        out = {}
+        for g, sfx in enumerate(suffixes):
+            out["loss_ce" + sfx] = loss_ce[g]
+            out["loss_bbox" + sfx], out["loss_giou" + sfx] = loss_bbox[g], loss_giou[g]
+            out["loss_xy" + sfx], out["loss_hw" + sfx] = loss_xy[g], loss_hw[g]
+            out["cardinality_error" + sfx] = card[g]
+        if log_group is not None:
+            with torch.no_grad():
+                sel = slice(log_group * K, (log_group + 1) * K)
+                out["class_error"] = 100 - accuracy(logits[gb[sel], src[sel]], matched[sel])[0]
+        return out
+
+    def _losses_batched(self, outputs, targets, pre, num_boxes, helpers):
+        aux = list(outputs.get("aux_outputs", []))
+        sets = [outputs] + aux + ([outputs["interm_outputs"]] if "interm_outputs" in outputs else [])
+        suffixes = [""] + [f"_{i}" for i in range(len(aux))] + (["_interm"] if "interm_outputs" in outputs else [])
+        src = torch.cat([s_ for ind in pre for s_, _ in ind])
+        tgt = torch.cat([t_ for ind in pre for _, t_ in ind])
+        losses = {}
+        dn_zero = ("loss_bbox_dn", "loss_giou_dn", "loss_ce_dn", "loss_xy_dn", "loss_hw_dn", "cardinality_error_dn")
+        if "d" in helpers:
+            dn_meta = outputs["dn_meta"]
+            known = dn_meta["output_known_lbs_bboxes"]
+            dsets = [known] + list(known.get("aux_outputs", []))
+            dsfx = ["_dn"] + [f"_dn_{i}" for i in range(len(dsets) - 1)]
+            gb, toff, dsrc, dtgt = helpers["d"]
+            losses.update(self._family_losses(dsets, targets, dsrc, dtgt, gb, toff, helpers["n_tgt"],
+                                              num_boxes * dn_meta["num_dn_group"], dsfx))
+        else:
+            device = outputs["pred_logits"].device
+            losses.update({k: torch.zeros((), device=device) for k in dn_zero})
+            losses.update({f"{k}_{i}": torch.zeros((), device=device) for k in dn_zero for i in range(len(aux))})
+        gb, toff = helpers["m"]
+        losses.update(self._family_losses(sets, targets, src, tgt, gb, toff, helpers["n_tgt"], num_boxes, suffixes, log_group=0))
+        return losses
+
     # ---- driver ------------------------------------------------------------------------------------
     def _dn_indices(self, targets, single_pad, scalar, device):
         pos = []
@@ -421,8 +548,17 @@ class SetCriterion(nn.Module):
             out.update({k + suffix: v for k, v in self.get_loss(loss, outputs, targets, indices, num_boxes, **kwargs).items()})
         return out
 
-    def _losses_from(self, outputs, targets, pre, num_boxes, target_domain_flag, training, return_indices):
-        """All losses given the matchings `pre` (device index tensors): pure device work, no host synchronisation."""
+    def _losses_from(self, outputs, targets, pre, num_boxes, target_domain_flag, training, return_indices, helpers=None):
+        """All losses given the matchings `pre` (device index tensors): pure device work, no host synchronisation.
+        With `helpers` (see _batched_helpers) the 13 set losses run as two batched families."""
+        if helpers is not None:
+            losses = self._losses_batched(outputs, targets, pre, num_boxes, helpers)
+            if "da_output" in outputs:
+                da = outputs["da_output"]
+                losses["loss_backbone_DA"] = self.loss_da(da["backbone_DA"])
+                losses["loss_proto_DA"] = self.loss_proto_da(da["proto_DA"])
+                losses["loss_global_proto_DA"] = self.loss_contrast_da(da["global_proto_DA"])
+            return losses
         device = outputs["pred_logits"].device
         key_aux = "aux_outputs_target" if target_domain_flag else "aux_outputs"
         key_interm = "interm_outputs_target" if target_domain_flag else "interm_outputs"
@@ -526,13 +662,16 @@ class SetCriterion(nn.Module):
         if indices is None:
             return {}
 
+        helpers = None
+        if self.batched and not return_indices and not target_domain_flag and isinstance(pre, list):
+            helpers = self._batched_helpers(outputs, targets, pre)
         if (graphs.ACTIVE is not None and device.type == "cuda" and torch.is_grad_enabled() and not return_indices
                 and not target_domain_flag):
             # every loss of the step as one captured segment: the matched indices, targets and predictions are its
-            # tensor inputs, everything host-side (matching, num_boxes) happened above
+            # tensor inputs, everything host-side (matching, num_boxes, index helpers) happened above
             return graphs.ACTIVE.call("criterion", None, self._losses_from, outputs, targets, pre, num_boxes,
-                                      target_domain_flag, self.training, False)
-        return self._losses_from(outputs, targets, pre, num_boxes, target_domain_flag, self.training, return_indices)
+                                      target_domain_flag, self.training, False, helpers)
+        return self._losses_from(outputs, targets, pre, num_boxes, target_domain_flag, self.training, return_indices, helpers)
 
     def prep_for_dn(self, dn_meta):
         groups, pad = dn_meta["num_dn_group"], dn_meta["pad_size"]
