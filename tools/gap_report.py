@@ -50,6 +50,14 @@ with open(out, "w") as f:
         f.write(f"kernels of {b[0]:>4}-{b[1] if b[1] < 1e9 else 'inf':>5} us: {hist[b][0]:6d}  total {hist[b][1] / 1e3:7.2f} ms\n")
     f.write("kernels shorter than 6 us per 2 ms window (start ms: count, busy ms): " +
             "  ".join(f"{2 * w}: {c[0]}, {c[1] / 1e3:.2f}" for w, c in sorted(win.items())) + "\n")
+    names = {}
+    for e in ev:
+        d = e.time_range.end - e.time_range.start
+        if d < 6:
+            c = names.setdefault(e.name[:110], [0, 0.0]); c[0] += 1; c[1] += d
+    f.write("kernels shorter than 6 us by name:\n")
+    for n, c in sorted(names.items(), key=lambda x: -x[1][0])[:45]:
+        f.write(f"   {c[0]:5d}x {c[1] / 1e3:6.2f} ms  {n}\n")
     for g in gaps[:40]:
         f.write(f"{g[0]:8.1f} us at +{g[1] / 1e3:7.2f} ms   after {g[2][:60]:60s} before {g[3][:60]}\n")
 print(open(out).read()[:5000])
