@@ -15,8 +15,9 @@ Differences that do not change results:
     CUDA tensor, :479-484);
   * in the two-stage block the box head runs on the 900 selected tokens only (it is row-wise, so
     gathering first gives the same numbers as :340-345 for a third of the FLOPs);
-  * decoder self-attention is F.scaled_dot_product_attention on the packed in_proj weights of
-    nn.MultiheadAttention (same parameter names and math).
+  * decoder self-attention runs on the packed in_proj weights of nn.MultiheadAttention (same parameter names and
+    math): batched GEMMs around the masked-softmax kernel of datr_b200.attention on CUDA fp32,
+    F.scaled_dot_product_attention otherwise (DATR_OWN_ATTENTION=0 forces the latter).
 Options the DINO/DATR configs never enable (box attention, layer sharing, dec_layer_number, patterns,
 'ca_label' / 'ca_content' self-attention, key-aware cross-attention) raise NotImplementedError.
 """
@@ -28,12 +29,17 @@ import torch
 import torch.nn.functional as F
 from torch import Tensor, nn
 
+import os
+
 from datr_b200.util.misc import inverse_sigmoid
-from datr_b200 import graphs
+from datr_b200 import attention, graphs
 from datr_b200 import linear as dl
 from datr_b200.layernorm import layer_norm as ln
 from .ops.modules import MSDeformAttn
 from .utils import MLP, _get_activation_fn, gen_encoder_output_proposals, gen_sineembed_for_position, level_sizes
+
+
+_OWN_ATTENTION = os.environ.get("DATR_OWN_ATTENTION", "1") != "0"
 
 
 def _get_clones(module, N, layer_share=False):
@@ -65,10 +71,14 @@ class PackedSelfAttention(nn.Module):
         v = dl.linear(v_in, self.in_proj_weight[2 * C:], self.in_proj_bias[2 * C:])
         q, k = qk.view(N, T, 2, H, C // H).permute(2, 0, 3, 1, 4)
         v = v.view(N, T, H, C // H).transpose(1, 2)
-        if attn_mask is not None and attn_mask.dtype == torch.bool:
-            attn_mask = ~attn_mask                      # SDPA: True = may attend
-        o = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask,
-                                           dropout_p=self.dropout if self.training else 0.0)
+        drop = self.dropout if self.training else 0.0
+        if _OWN_ATTENTION and attention.applicable(q, attn_mask, drop):
+            # score matrix in HBM: two batched GEMMs around the in-place masked-softmax kernel (datr_b200.attention)
+            o = attention.self_attention(q, k, v, attn_mask)
+        else:
+            if attn_mask is not None and attn_mask.dtype == torch.bool:
+                attn_mask = ~attn_mask                      # SDPA: True = may attend
+            o = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask, dropout_p=drop)
         return dl.linear(o.transpose(1, 2).reshape(N, T, C), self.out_proj.weight, self.out_proj.bias)
 
 

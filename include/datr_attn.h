@@ -1,0 +1,39 @@
+/*
+ * datr_attn.h -- C ABI of the decoder self-attention softmax kernels of libdatr_b200.so (sm_100a).
+ *
+ * The reference's decoder layer runs nn.MultiheadAttention over the 900 matching + <=200 de-noising queries with a
+ * boolean attention mask (models/dino/deformable_transformer.py:880-897, mask built in dn_components.py:105-121).
+ * At T <= 1100 tokens, 8 heads x 32 channels the score matrix of a layer is 77 MB, so the attention is run as
+ *   S = Q K^T (library batched GEMM)  ->  P = softmax(scale * S + mask)  ->  O = P V (library batched GEMM)
+ * with these two HBM-bound kernels for the softmax and its backward, both IN PLACE on the score matrix:
+ *
+ *   datr_attn_softmax_forward   s[rows, T] <- softmax_j(scale * s[r, j]  with  -inf where blocked[(r % Tq) * T + j])
+ *                               (`blocked` = the reference's bool attn_mask [Tq, T], True = may NOT attend; NULL = none;
+ *                               rows = batch * heads * Tq).  Replaces the scale / masked_fill / softmax chain of
+ *                               torch.nn.functional.multi_head_attention_forward.
+ *   datr_attn_softmax_backward  dp[rows, T] <- scale * p * (dp - sum_j dp[r, j] * p[r, j])   (dS from dP, in place)
+ *
+ * fp32, contiguous, caller-owned device buffers, T <= 2048.  Algorithmic bytes: forward 8 * rows * T (+ mask),
+ * backward 12 * rows * T.  Returns 0 or a negative code.
+ */
+#ifndef DATR_ATTN_H_
+#define DATR_ATTN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { DATR_ATTN_OK = 0, DATR_ATTN_ERR_BAD_ARGUMENT = -1, DATR_ATTN_ERR_CUDA = -3 };
+
+int datr_attn_softmax_forward(float* s, const uint8_t* blocked, float scale, long long rows, int T, int Tq, void* stream);
+int datr_attn_softmax_backward(const float* p, float* dp, float scale, long long rows, int T, void* stream);
+
+const char* datr_attn_last_error(void);
+uint64_t datr_attn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DATR_ATTN_H_ */
