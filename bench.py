@@ -42,8 +42,10 @@ MSDA_WORKLOAD = ("MSDeformAttn calls of one DINO-4scale DA training step, 1333x8
                  "12 encoder (N=2,Lq=S=22223) + 6 decoder Lq=1100 + 6 decoder Lq=900, forward+backward, fp32")
 FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the config-2/3 encoder call, from the committed
-# `ncu --set full` capture (profiles/r01b_msda_ncu_full.txt)
-TRAFFIC_NCU = {"msda_fwd_f32_d32": 142.6e6, "msda_bwd_f32_d32": 340.9e6}
+# `ncu --set full` capture of the fused-prologue kernels the model runs (profiles/r01o_msda_fused_ln_rowmask_ncu_full.txt:
+# forward 116.2 + 29.4 MB, backward 238.5 + 98.9 MB; the plain-op kernels of profiles/r01b_msda_ncu_full.txt moved
+# 142.6 / 340.9 MB)
+TRAFFIC_NCU = {"msda_fwd_f32_d32": 145.6e6, "msda_bwd_f32_d32": 337.4e6}
 
 
 def hbm_peak():

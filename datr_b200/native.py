@@ -16,7 +16,8 @@ _ROOT = os.path.dirname(_PKG)
 SOURCES = [os.path.join(_PKG, "csrc", "msda.cu"), os.path.join(_PKG, "csrc", "linear_tf32.cu"),
            os.path.join(_PKG, "csrc", "layernorm.cu"), os.path.join(_PKG, "csrc", "colsum.cu"),
            os.path.join(_PKG, "csrc", "conv3x3_tf32.cu"), os.path.join(_PKG, "csrc", "wgrad_tf32.cu"),
-           os.path.join(_PKG, "csrc", "rowmask.cu"), os.path.join(_PKG, "csrc", "attn_softmax.cu")]
+           os.path.join(_PKG, "csrc", "rowmask.cu"), os.path.join(_PKG, "csrc", "attn_softmax.cu"),
+           os.path.join(_PKG, "csrc", "ema.cu")]
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -29,7 +30,8 @@ EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward",
            "datr_conv3x3_nhwc_tf32", "datr_conv_last_error", "datr_conv_launch_count",
            "datr_linear_wgrad_tf32", "datr_linear_wgrad_last_error", "datr_linear_wgrad_launch_count",
            "datr_zero_masked_rows", "datr_rowmask_last_error", "datr_rowmask_launch_count",
-           "datr_attn_softmax_forward", "datr_attn_softmax_backward", "datr_attn_last_error", "datr_attn_launch_count")
+           "datr_attn_softmax_forward", "datr_attn_softmax_backward", "datr_attn_last_error", "datr_attn_launch_count",
+           "datr_ema_update", "datr_ema_last_error", "datr_ema_launch_count")
 
 _lock = threading.Lock()
 _lib = None
@@ -128,6 +130,10 @@ def lib() -> ctypes.CDLL:
         L.datr_attn_softmax_backward.argtypes = [vp, vp, ctypes.c_float, ctypes.c_longlong, i, vp]
         L.datr_attn_last_error.restype = ctypes.c_char_p
         L.datr_attn_launch_count.restype = ctypes.c_uint64
+        L.datr_ema_update.restype = i
+        L.datr_ema_update.argtypes = [vp, vp, i, ctypes.c_float, ctypes.c_float, vp]
+        L.datr_ema_last_error.restype = ctypes.c_char_p
+        L.datr_ema_launch_count.restype = ctypes.c_uint64
         if L.datr_abi_version() != 1:
             raise NativeLibraryError("libdatr_b200.so ABI version mismatch; rebuild")
         _lib = L
@@ -147,7 +153,12 @@ def colsum_launch_count() -> int:
 def all_launch_count() -> int:
     """Every hand-written kernel launch issued through the library by this process."""
     return (launch_count() + linear_launch_count() + layernorm_launch_count() + colsum_launch_count()
-            + conv_launch_count() + wgrad_launch_count() + rowmask_launch_count() + attn_launch_count())
+            + conv_launch_count() + wgrad_launch_count() + rowmask_launch_count() + attn_launch_count() + ema_launch_count())
+
+
+def ema_launch_count() -> int:
+    """Multi-tensor EMA kernel launches issued through the library by this process."""
+    return int(lib().datr_ema_launch_count())
 
 
 def attn_launch_count() -> int:
