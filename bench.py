@@ -283,6 +283,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner with printf) and anything
+    # else that writes to file descriptor 1 is sent to stderr for the whole run; the result goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    emit = lambda obj: (real_stdout.write(json.dumps(obj) + "\n"), real_stdout.flush())
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -301,7 +307,7 @@ def main():
             return
         if args.workload == "dino":
             from datr_b200 import bench_dino
-            print(json.dumps(bench_dino.reference_arm(args, threads)), flush=True)
+            emit(bench_dino.reference_arm(args, threads))
             return
         vals = []
         for _ in range(max(1, min(args.steps, 3))):
@@ -310,14 +316,14 @@ def main():
         ips, step_s = max(vals)
         sample = ("1 encoder + 1 decoder(1100) + 1 decoder(900) call, forward + autograd backward, of the "
                   "reference's grid_sample CPU path (func.py:41-61, port in oracle/msda.py), extrapolated x12/x6/x6")
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": MSDA_WORKLOAD, "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }), flush=True)
+        })
         return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
@@ -438,7 +444,7 @@ def main():
     extra = getattr(wl, "extra", None)
     if extra:
         line.update(extra() if callable(extra) else extra)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
