@@ -54,6 +54,18 @@ def test_bad_arguments_return_error_codes_without_touching_the_gpu():
     assert rc == -1
     rc = lib.datr_msda_forward(p + 2, p, p, p, p, 1, 1, 1, 1, 1, 1, 1, 0, p, None)
     assert rc == -2
+    # fused entry points: reference_points arity, unsupported configuration, row strides
+    rc = lib.datr_msda_fused_forward(p, p, p, p, 0, p, 0, p, 3, 1, 1, 1, 32, 1, 1, 4, 0, p, None)
+    assert rc == -1 and b"2 or 4" in lib.datr_last_error()
+    rc = lib.datr_msda_fused_forward(p, p, p, p, 0, p, 0, p, 2, 1, 1, 1, 16, 1, 1, 4, 0, p, None)
+    assert rc == -4
+    rc = lib.datr_msda_fused_backward(p, p, p, p, 5, p, 0, p, 2, p, 1, 1, 8, 32, 4, 1, 4, 0, p, p, p, None)
+    assert rc == -1 and b"row strides" in lib.datr_last_error()
+    assert lib.datr_attn_softmax_forward(None, None, 1.0, 1, 1, 1, None) == -1
+    assert lib.datr_attn_softmax_forward(p, None, 1.0, 1, 4096, 1, None) == -1
+    assert lib.datr_ema_update(None, None, 1, 0.5, 0.5, None) == -1
+    assert lib.datr_zero_masked_rows(p, p, 4, 3, None) == -1
+    assert lib.datr_layernorm256_forward(p, p, p, 1e-5, p, p, p, 0, None) == -1
 
 
 def test_shim_refuses_cpu_tensors_like_the_reference():

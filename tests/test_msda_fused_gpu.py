@@ -190,3 +190,74 @@ def test_zero_masked_rows_matches_masked_fill():
     v = torch.randn(2, 77, 8, 32, generator=g).cuda()
     mk = (torch.rand(2, 77, generator=g) < 0.5).cuda()
     assert torch.equal(zero_masked_rows(v.clone(), mk), v.masked_fill(mk[..., None, None], 0.0))
+
+
+def _torch_prologue(d, P):
+    """ops/modules/ms_deform_attn.py:99-111 with torch ops on the device."""
+    off, lg, ref = d["offsets"], d["logits"], d["ref"]
+    N, Lq, M, L = off.shape[:4]
+    attn = torch.softmax(lg, -1).view(N, Lq, M, L, P)
+    if ref.shape[-1] == 2:
+        loc = ref[:, :, None, :, None, :] + off / d["shapes"].flip(-1)[None, None, None, :, None, :]
+    else:
+        loc = ref[:, :, None, :, None, :2] + off / P * ref[:, :, None, :, None, 2:] * 0.5
+    return loc.contiguous(), attn.contiguous()
+
+
+@pytest.mark.parametrize("levels,tag", [(mc.CFG2_LEVELS, "config2 N=2 S=22223"), (mc.CFG4_LEVELS, "config4 5-scale N=1 S=89023")])
+def test_full_size_fused_vs_reference_cuda_kernels_and_properties(levels, tag):
+    """BASELINE.json configs[1] / configs[3] encoder calls through the fused entry points: against the reference's
+    own CUDA kernels (oracle/_ref, when built) fed with the torch prologue, plus size-independent properties --
+    linearity in value, zero grad_out -> zero grads, sum(grad_logits) == 0 per (query, head) (softmax), Euler identity
+    <grad_value, value> == <grad_out, out>."""
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    N = 2 if len(levels) == 4 else 1
+    inp = make(N, 8, -1, 4, levels, 2, 71 + len(levels), spread=3.0)
+    d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    f = lambda v: MSDA.ms_deform_attn_fused_forward(v, d["shapes"], d["level_start"], d["offsets"], d["logits"], d["ref"])
+    out = f(d["value"])
+    gv, goff, glg = MSDA.ms_deform_attn_fused_backward(d["value"], d["shapes"], d["level_start"], d["offsets"], d["logits"],
+                                                       d["ref"], d["grad_out"])
+    v2 = torch.randn_like(d["value"])
+    assert mc.rel_err(f(d["value"] + 2 * v2).cpu().numpy(), (out + 2 * f(v2)).cpu().numpy()) < 1e-5
+    rhs = (d["grad_out"].double() * out.double()).sum().item()
+    assert abs((gv.double() * d["value"].double()).sum().item() - rhs) / abs(rhs) < 1e-4
+    assert float(glg.double().sum(-1).abs().max()) < 1e-3 * float(glg.abs().max())
+    zero = MSDA.ms_deform_attn_fused_backward(d["value"], d["shapes"], d["level_start"], d["offsets"], d["logits"], d["ref"],
+                                              torch.zeros_like(d["grad_out"]))
+    assert all(not t.any().item() for t in zero)
+    from oracle import build_ref
+    ref = build_ref.load()
+    if ref is None:
+        return
+    off = d["offsets"].clone().requires_grad_(True); lg = d["logits"].clone().requires_grad_(True)
+    loc, attn = _torch_prologue(dict(d, offsets=off, logits=lg), 4)
+    args = (d["value"], d["shapes"], d["level_start"], loc.detach(), attn.detach())
+    out_ref = ref.ms_deform_attn_forward(*args, 64)
+    gv_ref, gl_ref, ga_ref = ref.ms_deform_attn_backward(*args, d["grad_out"], 64)
+    torch.autograd.backward([loc, attn], [gl_ref, ga_ref])
+    assert mc.rel_err(out.cpu().numpy(), out_ref.cpu().numpy()) < TIGHT
+    for a, b, key in ((gv, gv_ref, "gv"), (goff, off.grad, "goff"), (glg, lg.grad, "glg")):
+        assert mc.rel_err(a.cpu().numpy(), b.cpu().numpy().reshape(a.shape)) < TIGHT * 5, key
+
+
+def test_fused_error_behaviour():
+    from datr_b200 import MultiScaleDeformableAttention as MSDA, native
+    inp = make(1, 8, 9, 4, [(4, 5), (2, 3)], 2, 80)
+    d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        MSDA.ms_deform_attn_fused_forward(d["value"].cpu(), d["shapes"], d["level_start"], d["offsets"], d["logits"], d["ref"])
+    with pytest.raises(RuntimeError, match="uniformly strided|contiguous"):
+        MSDA.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["level_start"], d["offsets"].transpose(2, 3), d["logits"], d["ref"])
+    with pytest.raises(RuntimeError, match="fp32 only"):
+        MSDA.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["level_start"], d["offsets"].double(), d["logits"], d["ref"])
+    assert not MSDA.fused_supported(d["value"].double(), d["offsets"], d["ref"])
+    assert not MSDA.fused_supported(d["value"], d["offsets"], d["ref"].clone().requires_grad_(True))
+    lib = native.lib()
+    p = d["value"].data_ptr()
+    rc = lib.datr_msda_fused_forward(p, p, p, p, 0, p, 0, p, 3, 1, 1, 1, 32, 1, 1, 4, 0, p, None)
+    assert rc == -1 and b"2 or 4" in lib.datr_last_error()
+    rc = lib.datr_msda_fused_forward(p, p, p, p, 0, p, 0, p, 2, 1, 1, 1, 16, 1, 1, 4, 0, p, None)
+    assert rc == -4 and b"fused entry points cover" in lib.datr_last_error()
+    rc = lib.datr_msda_fused_forward(p, p, p, p, 5, p, 0, p, 2, 1, 1, 8, 32, 4, 1, 4, 0, p, None)
+    assert rc == -1 and b"row strides" in lib.datr_last_error()
