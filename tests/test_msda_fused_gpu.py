@@ -248,7 +248,8 @@ def test_fused_error_behaviour():
     with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
         MSDA.ms_deform_attn_fused_forward(d["value"].cpu(), d["shapes"], d["level_start"], d["offsets"], d["logits"], d["ref"])
     with pytest.raises(RuntimeError, match="uniformly strided|contiguous"):
-        MSDA.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["level_start"], d["offsets"].transpose(2, 3), d["logits"], d["ref"])
+        padded = torch.zeros(d["offsets"].shape[:-1] + (3,), device="cuda")[..., :2]      # same shape, gaps inside a row
+        MSDA.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["level_start"], padded, d["logits"], d["ref"])
     with pytest.raises(RuntimeError, match="fp32 only"):
         MSDA.ms_deform_attn_fused_forward(d["value"], d["shapes"], d["level_start"], d["offsets"].double(), d["logits"], d["ref"])
     assert not MSDA.fused_supported(d["value"].double(), d["offsets"], d["ref"])
