@@ -47,6 +47,9 @@ class DinoStep:
         self.dtype = "tf32" if self.matmul == "tf32" and device.type == "cuda" else "f32"
         torch.backends.cuda.matmul.allow_tf32 = self.matmul == "tf32"
         torch.backends.cudnn.allow_tf32 = True
+        # static shapes: let cuDNN time its algorithms once for the layers that stay on it (7x7 stem, convolution
+        # backward); DATR_CUDNN_BENCHMARK=0 keeps its heuristics
+        torch.backends.cudnn.benchmark = os.environ.get("DATR_CUDNN_BENCHMARK", "1") != "0"
         from datr_b200 import linear as dl
         dl.set_mode("tf32" if self.matmul == "tf32" and device.type == "cuda" else "fp32")
         # CUDA graphs for the ResNet body, encoder and decoder (datr_b200/graphs.py); DATR_GRAPHS=0 keeps the step eager

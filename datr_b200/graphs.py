@@ -39,6 +39,8 @@ class StepGraphs:
         self.warmup_iters = warmup_iters
         self.replayed_native_launches = 0      # hand-written kernel launches executed by graph replays
         self.captures = 0
+        self.per_segment = {}                  # (name, index) -> number of signatures captured so far
+        self.max_signatures = 4                # beyond that a segment runs eagerly for unseen signatures
         import os
         self.skip = set(filter(None, os.environ.get("DATR_GRAPH_SKIP", "").split(",")))   # segment names kept eager
 
@@ -59,10 +61,14 @@ class StepGraphs:
         key = (name, idx, torch.is_grad_enabled(), key_extra) + tuple((tuple(a.shape), a.dtype, a.requires_grad) for a in args)
         entry = self.cache.get(key)
         if entry is None:
-            if not torch.is_grad_enabled():
-                module = make_module()                   # inference passes stay eager
+            # inference passes stay eager; so does a segment whose signature keeps changing (e.g. the criterion with
+            # real data: its index tensors are sized by the number of boxes in the batch) -- capturing costs far more
+            # than one eager pass and every capture keeps its private memory pool
+            if not torch.is_grad_enabled() or self.per_segment.get((name, idx), 0) >= self.max_signatures:
+                module = make_module()
                 out = module(*args)
                 return (out, module) if want_module else out
+            self.per_segment[(name, idx)] = self.per_segment.get((name, idx), 0) + 1
             module = make_module()
             sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
             n0 = _native_launches()
