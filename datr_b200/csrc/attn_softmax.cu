@@ -38,24 +38,27 @@ __device__ __forceinline__ float wmax(float v) {
   return v;
 }
 
-template <int PER>   // PER * 32 >= T
+template <int PER, bool kMask>   // PER * 32 >= T
 __global__ void __launch_bounds__(kWarps * 32)
 softmax_fwd(float* __restrict__ s, const uint8_t* __restrict__ blocked, float scale, long long rows, int T, int Tq) {
   const int lane = threadIdx.x & 31;
   const long long r = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (r >= rows) return;
   float* row = s + r * T;
-  const uint8_t* mrow = blocked ? blocked + (r % Tq) * (long long)T : nullptr;
+  const uint8_t* mrow = kMask ? blocked + (r % Tq) * (long long)T : nullptr;
+  // all loads of the row first (clamped index instead of a branch per element: 36 independent loads in flight),
+  // then the arithmetic
   float v[PER];
+  uint8_t b[PER];
+#pragma unroll
+  for (int c = 0; c < PER; ++c) v[c] = row[min(c * 32 + lane, T - 1)];
+#pragma unroll
+  for (int c = 0; c < PER; ++c) b[c] = kMask ? mrow[min(c * 32 + lane, T - 1)] : uint8_t(0);
   float mx = -CUDART_INF_F;
 #pragma unroll
   for (int c = 0; c < PER; ++c) {
-    const int j = c * 32 + lane;
-    v[c] = -CUDART_INF_F;
-    if (j < T) {
-      v[c] = row[j] * scale;
-      if (mrow && mrow[j]) v[c] = -CUDART_INF_F;
-    }
+    const bool live = c * 32 + lane < T && !b[c];
+    v[c] = live ? v[c] * scale : -CUDART_INF_F;
     mx = fmaxf(mx, v[c]);
   }
   mx = wmax(mx);
@@ -65,11 +68,11 @@ softmax_fwd(float* __restrict__ s, const uint8_t* __restrict__ blocked, float sc
     v[c] = (c * 32 + lane < T) ? expf(v[c] - mx) : 0.f;    // a fully blocked row gives NaN, like torch
     sum += v[c];
   }
-  sum = wsum(sum);
+  const float inv = 1.0f / wsum(sum);
 #pragma unroll
   for (int c = 0; c < PER; ++c) {
     const int j = c * 32 + lane;
-    if (j < T) row[j] = v[c] / sum;
+    if (j < T) row[j] = v[c] * inv;
   }
 }
 
@@ -107,8 +110,13 @@ int datr_attn_softmax_forward(float* s, const uint8_t* blocked, float scale, lon
   if (rows <= 0 || T <= 0 || T > 2048 || Tq <= 0) return afail(DATR_ATTN_ERR_BAD_ARGUMENT, "need rows > 0, 0 < T <= 2048, Tq > 0%s");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const unsigned grid = unsigned((rows + kWarps - 1) / kWarps);
-  if (T <= 36 * 32) softmax_fwd<36><<<grid, kWarps * 32, 0, stream>>>(s, blocked, scale, rows, T, Tq);
-  else softmax_fwd<64><<<grid, kWarps * 32, 0, stream>>>(s, blocked, scale, rows, T, Tq);
+  if (T <= 36 * 32) {
+    if (blocked) softmax_fwd<36, true><<<grid, kWarps * 32, 0, stream>>>(s, blocked, scale, rows, T, Tq);
+    else softmax_fwd<36, false><<<grid, kWarps * 32, 0, stream>>>(s, blocked, scale, rows, T, Tq);
+  } else {
+    if (blocked) softmax_fwd<64, true><<<grid, kWarps * 32, 0, stream>>>(s, blocked, scale, rows, T, Tq);
+    else softmax_fwd<64, false><<<grid, kWarps * 32, 0, stream>>>(s, blocked, scale, rows, T, Tq);
+  }
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return afail(DATR_ATTN_ERR_CUDA, "softmax_fwd launch: %s", cudaGetErrorString(e));
   g_at_launches.fetch_add(1, std::memory_order_relaxed);
