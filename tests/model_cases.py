@@ -69,6 +69,29 @@ def targets(seed=5, counts=(3, 5), num_classes=9, device="cpu"):
     return out
 
 
+def pseudo_targets(device="cpu"):
+    """Seeded pseudo labels for the two target-domain images (what engine.py:208-218 distils from the teacher)."""
+    return targets(seed=9, counts=(2, 4), device=device)
+
+
+def split_target_outputs(out, idx=(0, 1)):
+    """The `*_target` half of a self-training output dict restricted to the images `idx` that have pseudo labels:
+    spilt_output (self_training_utils.py:99-107) followed by get_valid_output (:110-146)."""
+    idx = list(idx)
+    pick = lambda d: {"pred_logits": d["pred_logits"][idx, :, :], "pred_boxes": d["pred_boxes"][idx, :, :]}
+    res = {}
+    for k, v in out.items():
+        if "target" not in k:
+            continue
+        if "pred" in k:
+            res[k] = v[idx, :, :]
+        elif "aux_outputs_target" in k:
+            res[k] = [pick(d) for d in v]
+        else:
+            res[k] = pick(v)
+    return res
+
+
 def flatten(tree, prefix=""):
     """dict / list / tensor tree -> {dotted name: tensor} (None and non-tensors skipped)."""
     flat = {}
