@@ -11,6 +11,7 @@ from datr_b200.config import dino_args
 
 SMALL = dict(enc_layers=2, dec_layers=2, dim_feedforward=64, num_queries=30, num_classes=9, dn_labelbook_size=9,
              dn_number=100, num_select=100)
+FIVE_SCALE = dict(return_interm_indices=[0, 1, 2, 3], num_feature_levels=5)       # BASELINE.json configs[3]
 IMAGE_SIZES = [(128, 160), (112, 144), (120, 150), (128, 128)]      # 2 source + 2 target images, ragged
 
 
