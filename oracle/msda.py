@@ -122,3 +122,28 @@ def core_torch(value: torch.Tensor, shapes, loc: torch.Tensor, attn: torch.Tenso
     wts = attn.permute(0, 2, 1, 3, 4).reshape(N * M, 1, Lq, L * P)
     out = (sampled * wts).sum(-1)                                              # [N*M, D, Lq]
     return out.reshape(N, M * D, Lq).transpose(1, 2).contiguous()
+
+
+def module_prologue_torch(offsets: torch.Tensor, logits: torch.Tensor, reference_points: torch.Tensor, shapes, P: int):
+    """The elementwise prologue of the reference's MSDeformAttn.forward (ops/modules/ms_deform_attn.py:99-111):
+    attention weights = softmax of the logits over levels*points (:100-101); sampling locations = reference point +
+    offset / (W_l, H_l) for 2-d reference points (:102-105) or reference centre + offset / n_points * box size * 0.5
+    for 4-d reference boxes (:106-108).  offsets [N,Lq,M,L,P,2], logits [N,Lq,M,L*P], reference_points [N,Lq,L,2|4];
+    returns (sampling_locations [N,Lq,M,L,P,2], attention_weights [N,Lq,M,L,P]).  Oracle of the fused entry points."""
+    N, Lq, M, L = offsets.shape[:4]
+    attn = torch.softmax(logits, -1).view(N, Lq, M, L, P)
+    hw = torch.as_tensor(shapes.tolist() if hasattr(shapes, "tolist") else shapes, device=offsets.device)
+    if reference_points.shape[-1] == 2:
+        normalizer = torch.stack([hw[..., 1], hw[..., 0]], -1).to(offsets.dtype)                # (W_l, H_l), :103
+        loc = reference_points[:, :, None, :, None, :] + offsets / normalizer[None, None, None, :, None, :]
+    elif reference_points.shape[-1] == 4:
+        loc = reference_points[:, :, None, :, None, :2] + offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5
+    else:
+        raise ValueError("Last dim of reference_points must be 2 or 4")                         # :109-111
+    return loc, attn
+
+
+def fused_torch(value, shapes, offsets, logits, reference_points, P):
+    """module_prologue_torch followed by core_torch: what datr_msda_fused_forward computes."""
+    loc, attn = module_prologue_torch(offsets, logits, reference_points, shapes, P)
+    return core_torch(value, shapes, loc, attn)

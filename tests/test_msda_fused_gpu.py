@@ -41,15 +41,7 @@ def make(N, M, Lq, P, levels, ref_dim, seed, spread=3.0):
 
 def oracle(inp, P):
     v, off, lg = (torch.from_numpy(inp[k]).double().requires_grad_(True) for k in ("value", "offsets", "logits"))
-    ref = torch.from_numpy(inp["ref"]).double()
-    N, Lq, M, L = off.shape[:4]
-    attn = torch.softmax(lg, -1).view(N, Lq, M, L, P)
-    if ref.shape[-1] == 2:
-        wh = torch.from_numpy(inp["shapes"]).flip(-1).double()
-        loc = ref[:, :, None, :, None, :] + off / wh[None, None, None, :, None, :]
-    else:
-        loc = ref[:, :, None, :, None, :2] + off / P * ref[:, :, None, :, None, 2:] * 0.5
-    out = om.core_torch(v, inp["shapes"], loc, attn)
+    out = om.fused_torch(v, inp["shapes"], off, lg, torch.from_numpy(inp["ref"]).double(), P)
     out.backward(torch.from_numpy(inp["grad_out"]).double().view_as(out))
     return [t.detach().numpy() for t in (out, v.grad, off.grad, lg.grad)]
 
