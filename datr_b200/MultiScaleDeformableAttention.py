@@ -116,13 +116,18 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_attn]
 
 
-def fused_supported(value, sampling_offsets, reference_points) -> bool:
-    """True if datr_msda_fused_forward / _backward (include/datr_msda.h) cover this call."""
+def fused_config_supported(value, reference_points, L: int, P: int) -> bool:
+    """True if datr_msda_fused_forward / _backward (include/datr_msda.h) cover a call with this value map
+    [N,S,M,D], these reference points and L levels x P points."""
     if not (value.is_cuda and value.dtype == torch.float32 and value.dim() == 4 and value.shape[-1] == 32):
         return False
-    L, P = sampling_offsets.shape[3], sampling_offsets.shape[4]
     return P in (1, 2, 4, 8) and L * P <= 32 and reference_points.shape[-1] in (2, 4) \
         and reference_points.dtype == torch.float32 and not reference_points.requires_grad
+
+
+def fused_supported(value, sampling_offsets, reference_points) -> bool:
+    """fused_config_supported for given sampling offsets [N,Lq,M,L,P,2]."""
+    return fused_config_supported(value, reference_points, sampling_offsets.shape[3], sampling_offsets.shape[4])
 
 
 def _row_stride(name, t):

@@ -89,8 +89,7 @@ class MSDeformAttn(nn.Module):
         ref_dim = reference_points.shape[-1]
         if ref_dim not in (2, 4):
             raise ValueError(f"Last dim of reference_points must be 2 or 4, but get {ref_dim} instead.")
-        if (_FUSED and P in (1, 2, 4, 8) and L * P <= 32 and query.dtype == torch.float32
-                and MSDA.fused_supported(value, query.new_empty((0, 0, M, L, P, 2)), reference_points)):
+        if _FUSED and query.dtype == torch.float32 and MSDA.fused_config_supported(value, reference_points, L, P):
             # the two projections of the query (sampling_offsets :99, attention_weights :100) as ONE GEMM over the
             # stacked weights; the kernels read offsets and logits as column slices of its output
             merged = dl.linear(query, torch.cat((self.sampling_offsets.weight, self.attention_weights.weight), 0),
