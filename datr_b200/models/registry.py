@@ -1,43 +1,43 @@
-"""Model-builder registry -- same surface as the reference's models/registry.py:12-57
-(`MODULE_BUILD_FUNCS.registe_with_name(module_name=...)` decorator, `.get(name)`), which is how
-main.py:79-85 finds `build_dino`."""
-import inspect
-from functools import partial
+"""Model-builder registry: the lookup table main.py:79-85 of the reference uses to find `build_dino`.
+
+API surface kept from the reference's models/registry.py:12-57 because callers rely on it: the module-level
+`MODULE_BUILD_FUNCS`, its `registe_with_name(module_name=...)` decorator factory (the reference's spelling),
+`register(fn, module_name=None, force=False)`, `get(name)` (None when absent), `name`, `module_dict`, `len()`."""
+import types
+from typing import Callable, Dict, Optional
 
 
 class Registry:
-    def __init__(self, name):
-        self._name = name
-        self._module_dict = {}
+    """name -> build function.  Only plain functions can be registered; re-registering a name needs force=True."""
 
-    def __repr__(self):
-        return f"{type(self).__name__}(name={self._name}, items={list(self._module_dict)})"
+    def __init__(self, name: str):
+        self.name = name
+        self.module_dict: Dict[str, Callable] = {}
 
-    def __len__(self):
-        return len(self._module_dict)
-
-    @property
-    def name(self):
-        return self._name
-
-    @property
-    def module_dict(self):
-        return self._module_dict
-
-    def get(self, key):
-        return self._module_dict.get(key)
-
-    def registe_with_name(self, module_name=None, force=False):  # (sic) the reference's spelling
-        return partial(self.register, module_name=module_name, force=force)
-
-    def register(self, module_build_function, module_name=None, force=False):
-        if not inspect.isfunction(module_build_function):
+    def register(self, module_build_function: Callable, module_name: Optional[str] = None, force: bool = False) -> Callable:
+        if not isinstance(module_build_function, types.FunctionType):
             raise TypeError(f"module_build_function must be a function, but got {type(module_build_function)}")
-        key = module_name or module_build_function.__name__
-        if key in self._module_dict and not force:
-            raise KeyError(f"{key} is already registered in {self._name}")
-        self._module_dict[key] = module_build_function
+        key = module_build_function.__name__ if module_name is None else module_name
+        taken = key in self.module_dict
+        if taken and not force:
+            raise KeyError(f"{key} is already registered in {self.name}")
+        self.module_dict[key] = module_build_function
         return module_build_function
+
+    def registe_with_name(self, module_name: Optional[str] = None, force: bool = False) -> Callable[[Callable], Callable]:
+        """Decorator factory: `@MODULE_BUILD_FUNCS.registe_with_name(module_name='dino')`."""
+        def decorate(fn: Callable) -> Callable:
+            return self.register(fn, module_name=module_name, force=force)
+        return decorate
+
+    def get(self, key: str) -> Optional[Callable]:
+        return self.module_dict[key] if key in self.module_dict else None
+
+    def __len__(self) -> int:
+        return len(self.module_dict)
+
+    def __repr__(self) -> str:
+        return f"{type(self).__name__}(name={self.name}, items={list(self.module_dict)})"
 
 
 MODULE_BUILD_FUNCS = Registry("model build functions")
