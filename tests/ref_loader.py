@@ -66,6 +66,10 @@ def load():
         ns.backbone = importlib.import_module("models.dino.backbone")
         ns.dino = importlib.import_module("models.dino.dino")
         ns.registry = importlib.import_module("models.registry")
+        try:        # needs cv2 and torchvision (present in the build container)
+            ns.selftrain = importlib.import_module("models.dino.self_training_utils")
+        except ImportError:
+            ns.selftrain = None
         core = ns.func.ms_deform_attn_core_pytorch
 
         class _CpuMSDA:
