@@ -2,7 +2,9 @@
 
 API surface kept from the reference's models/registry.py:12-57 because callers rely on it: the module-level
 `MODULE_BUILD_FUNCS`, its `registe_with_name(module_name=...)` decorator factory (the reference's spelling),
-`register(fn, module_name=None, force=False)`, `get(name)` (None when absent), `name`, `module_dict`, `len()`."""
+`register(fn, module_name=None, force=False)`, `get(name)` (None when absent), `name`, `module_dict`, `len()` -- and
+the underscore spellings `_module_dict` / `_name`, which main.py:82 reads directly
+(`assert args.modelname in MODULE_BUILD_FUNCS._module_dict`)."""
 import types
 from typing import Callable, Dict, Optional
 
@@ -29,6 +31,14 @@ class Registry:
         def decorate(fn: Callable) -> Callable:
             return self.register(fn, module_name=module_name, force=force)
         return decorate
+
+    @property
+    def _module_dict(self) -> Dict[str, Callable]:     # main.py:82 / main_teacher.py:82 of the reference
+        return self.module_dict
+
+    @property
+    def _name(self) -> str:
+        return self.name
 
     def get(self, key: str) -> Optional[Callable]:
         return self.module_dict[key] if key in self.module_dict else None

@@ -93,3 +93,19 @@ def test_dropin_module_name():
     assert MSDA.ms_deform_attn_forward is shim.ms_deform_attn_forward
     assert MSDA.ms_deform_attn_backward is shim.ms_deform_attn_backward
     del sys.modules["MultiScaleDeformableAttention"]
+
+
+def test_registry_serves_the_reference_entry_point_the_way_main_py_uses_it():
+    """main.py:79-85 (build_model_main): membership test on the private dict, then .get(modelname)(args)."""
+    import datr_b200
+    datr_b200.install_dropin()
+    from models.registry import MODULE_BUILD_FUNCS
+    import models  # noqa: F401  (importing the package registers 'dino', like the reference's models/__init__.py:8)
+    assert "dino" in MODULE_BUILD_FUNCS._module_dict and MODULE_BUILD_FUNCS._name == MODULE_BUILD_FUNCS.name
+    assert MODULE_BUILD_FUNCS.get("dino").__name__ == "build_dino" and MODULE_BUILD_FUNCS.get("missing") is None
+    assert len(MODULE_BUILD_FUNCS) >= 1 and "dino" in repr(MODULE_BUILD_FUNCS)
+    import pytest as _pytest
+    with _pytest.raises(KeyError):
+        MODULE_BUILD_FUNCS.register(MODULE_BUILD_FUNCS.get("dino"), module_name="dino")
+    with _pytest.raises(TypeError):
+        MODULE_BUILD_FUNCS.register(object())
