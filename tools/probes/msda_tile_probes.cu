@@ -146,6 +146,87 @@ __global__ void __launch_bounds__(256, 2) probe_gather_window(const float* __res
   }
 }
 
+
+// ---- probe E (written after A-D were measured; NOT yet run): per-tile pixel sort.  CTA = 16x8 query tile of one head.
+// The tile's 2 048 samples are binned by anchor pixel with native integer shared atomics (count -> scan -> scatter of
+// {query, 4 corner weights} records); then every 8-lane group OWNS window pixels and sums, in registers, the
+// contributions of the four bins whose 2x2 block covers the pixel: one broadcast record read + one LDS.128 of the
+// query's grad_out per contribution, no read-modify-write; one red.global per window line at the end.
+constexpr int TQY = 8, WINX = TQ + 2 * HALO, WINY = TQY + 2 * HALO, NPIX = WINX * WINY;      // 26 x 18 = 468 pixels
+constexpr int TILE_Q = TQ * TQY, TILE_S = TILE_Q * TAPS;                                       // 128 queries, 2 048 samples
+constexpr int TILES_Y8 = (H + TQY - 1) / TQY;
+
+__global__ void __launch_bounds__(256, 3) probe_pixel_sort(float* __restrict__ grad, const float* __restrict__ go) {
+  extern __shared__ __align__(16) unsigned char raw[];
+  float4* gos = reinterpret_cast<float4*>(raw);                         // [TILE_Q][8] grad_out of the tile's queries
+  float4* rw = gos + TILE_Q * 8;                                        // [TILE_S] corner weights of a record
+  int* rq = reinterpret_cast<int*>(rw + TILE_S);                        // [TILE_S] query of a record
+  int* cnt = rq + TILE_S;                                               // [NPIX + 1] bin counts, then exclusive offsets
+  const int m = blockIdx.x % M, tile = (blockIdx.x / M) % (TILES_Y8 * TILES_X), b = blockIdx.x / (M * TILES_Y8 * TILES_X);
+  const int y0 = (tile / TILES_X) * TQY, x0 = (tile % TILES_X) * TQ, oy = y0 - HALO, ox = x0 - HALO;
+  for (int i = threadIdx.x; i < TILE_Q * 8; i += blockDim.x) {
+    const int qi = i >> 3, y = min(y0 + qi / TQ, H - 1), x = min(x0 + qi % TQ, W - 1);
+    gos[i] = *reinterpret_cast<const float4*>(go + ((((long long)b * S + y * W + x) * M + m) * 32) + (i & 7) * 4);
+  }
+  for (int i = threadIdx.x; i <= NPIX; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  int bin[TILE_S / 256], rank[TILE_S / 256];
+#pragma unroll
+  for (int k = 0; k < TILE_S / 256; ++k) {                              // sample id -> (query, tap)
+    const int sid = threadIdx.x + 256 * k, qi = sid / TAPS, y = y0 + qi / TQ, x = x0 + qi % TQ;
+    bin[k] = -1;
+    if (y < H && x < W) {
+      int by, bx; anchor(y, x, sid % TAPS, m, by, bx);
+      bin[k] = (by - oy) * WINX + (bx - ox);
+      rank[k] = atomicAdd(cnt + bin[k], 1);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {                                               // exclusive scan of NPIX counts by one warp
+    int carry = 0;
+    for (int base = 0; base < NPIX; base += 32) {
+      const int i = base + threadIdx.x, v = i < NPIX ? cnt[i] : 0;
+      int inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, d); if ((threadIdx.x & 31) >= d) inc += t; }
+      if (i < NPIX) cnt[i] = carry + inc - v;
+      carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (threadIdx.x == 0) cnt[NPIX] = carry;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < TILE_S / 256; ++k)
+    if (bin[k] >= 0) {
+      const int pos = cnt[bin[k]] + rank[k];
+      rq[pos] = (threadIdx.x + 256 * k) / TAPS;
+      rw[pos] = make_float4(1.f, 1.f, 1.f, 1.f);                        // (a real kernel stores attn * bilinear weights)
+    }
+  __syncthreads();
+  const int grp = threadIdx.x >> 3, sub = threadIdx.x & 7;
+  for (int pix = grp; pix < NPIX; pix += 32) {
+    const int wy = pix / WINX, wx = pix % WINX;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool any = false;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {                                       // the bin whose corner c lands on this pixel
+      const int ay = wy - (c >> 1), ax = wx - (c & 1);
+      if (ay < 0 || ax < 0) continue;
+      const int bb = ay * WINX + ax;
+      for (int i = cnt[bb]; i < cnt[bb + 1]; ++i) {
+        const float4 w4 = rw[i];
+        const float w = c == 0 ? w4.x : c == 1 ? w4.y : c == 2 ? w4.z : w4.w;
+        const float4 g = gos[rq[i] * 8 + sub];
+        acc.x = fmaf(w, g.x, acc.x); acc.y = fmaf(w, g.y, acc.y); acc.z = fmaf(w, g.z, acc.z); acc.w = fmaf(w, g.w, acc.w);
+        any = true;
+      }
+    }
+    const int gy = oy + wy, gx = ox + wx;
+    if (any && gy >= 0 && gy < H && gx >= 0 && gx < W)
+      red4(grad + (((long long)b * S + gy * W + gx) * M + m) * 32 + sub * 4, acc);
+  }
+}
+
 template <typename F>
 float time_us(F launch, int iters = 20) {
   cudaEvent_t e0, e1;
@@ -176,10 +257,14 @@ int main() {
   const float b = time_us([&] { probe_cas_window<<<tile_ctas, 256, smem>>>(grad, go); });
   const float c = time_us([&] { probe_gather_ldg<<<rows_ctas, 256>>>(value, out); });
   const float d = time_us([&] { probe_gather_window<<<tile_ctas, 256, smem>>>(value, out); });
+  const int smem_e = TILE_Q * 8 * 16 + TILE_S * 16 + TILE_S * 4 + (NPIX + 1) * 4;
+  CK(cudaFuncSetAttribute(probe_pixel_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_e));
+  const float e = time_us([&] { probe_pixel_sort<<<NB * M * TILES_Y8 * TILES_X, 256, smem_e>>>(grad, go); });
   CK(cudaGetLastError());
   printf("A red.global per corner line          %8.1f us  (%.2f cycles/line/SM at 1.965 GHz, 148 SMs)\n", a, a * 1965.0 * 148 / lines);
   printf("B shared-memory window (CAS) + flush  %8.1f us\n", b);
   printf("C LDG.128 gathers from global         %8.1f us  (%.2f cycles/line/SM)\n", c, c * 1965.0 * 148 / lines);
   printf("D cp.async window + LDS.128 gathers   %8.1f us\n", d);
+  printf("E per-tile pixel sort + owned pixels  %8.1f us  (%d bytes of shared memory per CTA)\n", e, smem_e);
   return 0;
 }
