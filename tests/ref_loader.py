@@ -1,5 +1,6 @@
-"""TEST INFRASTRUCTURE: import the reference's own Python modules from /root/reference (build container
-only) so that tests and the golden generators can run the reference model on CPU.
+"""TEST INFRASTRUCTURE: import the reference's own Python modules -- from /root/reference in the build container,
+from the staged copy `baseline/_ref/` (oracle/stage_ref.py, git-ignored, travels with gpurun) on the GPU box -- so
+that tests, the golden generators and the baseline tools can run the reference model itself.
 
 Nothing is copied: the reference packages are imported under a private alias (`_ref_models`, `_ref_util`)
 with stubs for the packages missing from this image (timm, the native MultiScaleDeformableAttention
@@ -15,7 +16,9 @@ import types
 
 import torch
 
-REF = "/root/reference"
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = ("/root/reference", os.path.join(_ROOT, "baseline", "_ref"))
+REF = next((p for p in _CANDIDATES if os.path.isdir(os.path.join(p, "models", "dino"))), _CANDIDATES[0])
 
 
 def available():
@@ -32,13 +35,26 @@ def _stub(name, **attrs):
 _loaded = None
 
 
-def load():
+def load(cuda_ext=False):
     """Returns a namespace with the reference modules: .dino, .transformer, .backbone, .utils, .dn, .matcher,
-    .da, .misc, .box_ops, .func, .msda_module."""
+    .da, .misc, .box_ops, .func, .msda_module.
+
+    cuda_ext=False: MSDeformAttnFunction.apply is routed to the reference's pure-PyTorch op (CPU runs).
+    cuda_ext=True : the reference's own autograd Function is left in place and its native module
+                    `MultiScaleDeformableAttention` is the reference CUDA extension built unmodified by
+                    oracle/build_ref.py (oracle/_ref/*.so) -- the stock GPU path of the reference."""
     global _loaded
     if _loaded is not None:
+        assert _loaded.cuda_ext == cuda_ext, "the reference is already loaded in the other mode"
         return _loaded
-    assert available(), "/root/reference is not present"
+    assert available(), "neither /root/reference nor baseline/_ref is present"
+    ext = None
+    if cuda_ext:
+        if _ROOT not in sys.path:
+            sys.path.insert(0, _ROOT)
+        from oracle import build_ref
+        ext = build_ref.load()
+        assert ext is not None, "oracle/_ref/*.so (the reference CUDA extension) is not built"
     saved = {k: sys.modules.get(k) for k in ("models", "util", "MultiScaleDeformableAttention", "timm", "timm.models",
                                                "timm.models.layers")}
     saved_path = list(sys.path)
@@ -47,7 +63,10 @@ def load():
         if k == "models" or k.startswith("models.") or k == "util" or k.startswith("util."):
             del sys.modules[k]
     sys.path.insert(0, REF)
-    _stub("MultiScaleDeformableAttention")
+    if ext is not None:
+        sys.modules["MultiScaleDeformableAttention"] = ext
+    else:
+        _stub("MultiScaleDeformableAttention")
     ident = lambda *a, **k: None
     _stub("timm"); _stub("timm.models")
     _stub("timm.models.layers", DropPath=torch.nn.Identity, to_2tuple=lambda x: (x, x), trunc_normal_=ident)
@@ -76,7 +95,9 @@ def load():
             @staticmethod
             def apply(value, shapes, level_start, loc, attn, im2col_step):
                 return core(value, shapes, loc, attn)
-        ns.msda_module.MSDeformAttnFunction = _CpuMSDA
+        if not cuda_ext:
+            ns.msda_module.MSDeformAttnFunction = _CpuMSDA
+        ns.cuda_ext = cuda_ext
         ns.backbone.is_main_process = lambda: False          # no pretrained-weight download
     finally:
         # keep the reference modules alive under private names, give `models` / `util` back to the caller

@@ -31,21 +31,33 @@ def timeit(fn, iters=20, flush=None):
 
 
 def main():
-    ref = build_ref.load()
+    """Location distributions: `encoder` = pixel centres + N(0, (2 px)^2) per sample (no coherence between neighbouring
+    queries: worst case of the run kernels); `init` = the offset pattern of MSDeformAttn._reset_parameters (what a
+    freshly built model, and bench.py's dino workload, samples); `init+0.3px` = that pattern with per-sample jitter
+    (smooth learned offsets); `uniform` = locations anywhere in the map."""
+    from test_msda_runs_gpu import coherent_inputs
+    ref = None if "--no-ref" in sys.argv else build_ref.load()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    cases = [("cfg2_enc", 2, mc.CFG2_LEVELS, -1, "encoder"), ("cfg2_enc_uniform", 2, mc.CFG2_LEVELS, -1, "uniform"),
+    cases = [("cfg2_enc", 2, mc.CFG2_LEVELS, -1, "encoder"), ("cfg2_enc_init", 2, mc.CFG2_LEVELS, -1, ("coherent", 0.0)),
+             ("cfg2_enc_init+0.3px", 2, mc.CFG2_LEVELS, -1, ("coherent", 0.3)),
+             ("cfg2_enc_uniform", 2, mc.CFG2_LEVELS, -1, "uniform"),
              ("cfg2_dec1100", 2, mc.CFG2_LEVELS, 1100, "uniform"), ("cfg1_enc", 1, mc.CFG1_LEVELS, -1, "encoder"),
-             ("cfg4_enc", 1, mc.CFG4_LEVELS, -1, "encoder")]
+             ("cfg4_enc", 1, mc.CFG4_LEVELS, -1, "encoder"), ("cfg4_enc_init+0.3px", 1, mc.CFG4_LEVELS, -1, ("coherent", 0.3))]
     for name, N, levels, Lq, mode in cases:
-        inp = mc.make_inputs(N, 8, 32, Lq, 4, levels, mode, 1, np.float32)
+        if isinstance(mode, tuple):
+            inp = coherent_inputs(N, 8, 4, levels, mode[1], 1)
+        else:
+            inp = mc.make_inputs(N, 8, 32, Lq, 4, levels, mode, 1, np.float32)
         d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
         args = (d["value"], d["shapes"], d["level_start"], d["loc"], d["attn"])
         S = d["value"].shape[1]; LQ = d["loc"].shape[1]
         fb, bb = algo_bytes(N, S, 8, 32, len(levels), LQ, 4)
-        for impl, mod in (("ours", MSDA), ("ref", ref)):
+        for impl, mod in (("rows", MSDA), ("runs", MSDA), ("ref", ref)):
             if mod is None:
                 continue
-            for flushed, fl in (("cold", flush), ("warm", None)):
+            if impl != "ref":
+                MSDA.set_strategy(1 if impl == "rows" else 2)
+            for flushed, fl in (("cold", flush),):
                 tf, tfm = timeit(lambda: mod.ms_deform_attn_forward(*args, 64), flush=fl)
                 tb, tbm = timeit(lambda: mod.ms_deform_attn_backward(*args, d["grad_out"], 64), flush=fl)
                 print(f"{name:18s} {impl:5s} {flushed} fwd {tf*1e3:8.1f} us ({fb/tf/1e6:7.1f} GB/s, {fb/tf/1e6/PEAK:5.3f}) "
