@@ -238,8 +238,9 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, samp
 def set_strategy(strategy: int) -> None:
     """Kernel family of the fp32 / 32-channel path (include/datr_msda.h): 0 auto (run kernels for encoder
     self-attention, num_query == spatial_size), 1 row kernels, 2 run kernels wherever they exist."""
-    lib = native.lib()
-    _raise(lib.datr_msda_set_strategy(int(strategy)), "datr_msda_set_strategy")
+    rc = native.lib().datr_msda_set_strategy(int(strategy))
+    if rc != 0:
+        _raise(rc, "datr_msda_set_strategy")
 
 
 def get_strategy() -> int:

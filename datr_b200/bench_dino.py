@@ -58,6 +58,7 @@ class DinoStep:
             from datr_b200 import graphs
             self.graphs = graphs.StepGraphs()
         self.set_graphs(True)
+        os.environ.setdefault("DATR_BACKBONE_WEIGHTS", "none")  # synthetic benchmark: random-init weights by design
         torch.manual_seed(42)                                   # identical initial weights on every rank
         args = dino_args(device=str(device), **over)
         self.args = args

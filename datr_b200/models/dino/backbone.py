@@ -19,7 +19,7 @@ from torch import nn
 from datr_b200 import conv as dconv
 from datr_b200 import linear as dl
 
-from datr_b200.util.misc import NestedTensor
+from datr_b200.util.misc import NestedTensor, is_main_process
 from .position_encoding import build_position_encoding
 
 
@@ -185,10 +185,33 @@ class BackboneBase(nn.Module):
         return out
 
 
+_TV_FILES = {"resnet50": "resnet50-0676ba61.pth", "resnet101": "resnet101-63fe2227.pth"}   # torchvision IMAGENET1K_V1
+
+
+def _pretrained_state_dict(name: str):
+    """ImageNet weights for the ResNet body without touching the network: a path given through
+    DATR_BACKBONE_WEIGHTS, else the file torchvision's `resnet50(pretrained=True)` (reference backbone.py:118-120)
+    would have downloaded into the torch hub cache.  None if neither exists."""
+    import os
+    cands = [os.environ.get("DATR_BACKBONE_WEIGHTS")]
+    try:
+        cands.append(os.path.join(torch.hub.get_dir(), "checkpoints", _TV_FILES.get(name, "")))
+    except Exception:
+        pass
+    for path in cands:
+        if path and os.path.isfile(path):
+            sd = torch.load(path, map_location="cpu", weights_only=True)
+            return sd.get("state_dict", sd.get("model", sd)) if isinstance(sd, dict) else sd
+    return None
+
+
 class Backbone(BackboneBase):
-    """ResNet-50/101 with FrozenBatchNorm2d.  Weights are random-initialised here: the reference downloads
-    ImageNet weights on the main process (:118-120); there is no network on the benchmark box, and a
-    checkpoint load overwrites them anyway."""
+    """ResNet-50/101 with FrozenBatchNorm2d.  The reference builds `torchvision.models.resnet50(pretrained=
+    is_main_process())` (:118-120), i.e. downloads ImageNet weights.  Parameter names here are torchvision's, so the
+    same file is loaded when it is already on disk (DATR_BACKBONE_WEIGHTS or the torch hub cache); nothing is ever
+    downloaded.  Without it the body is randomly initialised -- with a FROZEN stem / layer1 and identity FrozenBN
+    statistics that is only meaningful when a checkpoint is loaded afterwards (resume / finetune / the synthetic
+    benchmark), so a warning says so (DATR_BACKBONE_WEIGHTS=none silences it)."""
 
     def __init__(self, name: str, train_backbone: bool, dilation: bool, return_interm_indices: list,
                  batch_norm=FrozenBatchNorm2d):
@@ -196,6 +219,18 @@ class Backbone(BackboneBase):
             raise NotImplementedError(f"Why you can get here with name {name}")
         assert return_interm_indices in [[0, 1, 2, 3], [1, 2, 3], [3]]
         net = ResNet(_RESNETS[name], (False, False, dilation), norm_layer=batch_norm)
+        import os
+        if os.environ.get("DATR_BACKBONE_WEIGHTS", "").lower() != "none":
+            sd = _pretrained_state_dict(name) if is_main_process() else None
+            if sd is not None:
+                missing, unexpected = net.load_state_dict({k: v for k, v in sd.items() if not k.startswith("fc.")}, strict=False)
+                assert not [k for k in missing if "num_batches_tracked" not in k], f"backbone weights incomplete: {missing[:5]}"
+            elif is_main_process():
+                import warnings
+                warnings.warn("datr_b200 backbone: no ImageNet weights found (DATR_BACKBONE_WEIGHTS or torch hub cache); the "
+                              "ResNet body is RANDOMLY initialised with a frozen stem/layer1 and identity FrozenBatchNorm -- "
+                              "load a checkpoint (--pretrain_model_path / --resume) before training, or set "
+                              "DATR_BACKBONE_WEIGHTS=<file.pth>.", stacklevel=2)
         num_channels = [256, 512, 1024, 2048][4 - len(return_interm_indices):]
         super().__init__(net, train_backbone, num_channels, return_interm_indices)
 

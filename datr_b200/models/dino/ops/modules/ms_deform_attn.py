@@ -35,6 +35,26 @@ def _is_power_of_2(n):
     return n != 0 and (n & (n - 1)) == 0
 
 
+_CHECKED = set()
+
+
+def _check_levels(spatial_shapes, S):
+    """The reference's `assert (H*W).sum() == S` (ms_deform_attn.py:92).  The kernels clamp every sample inside its
+    level but trust level_start + H*W <= S, so inconsistent shapes would read -- and, in the backward, atomically add --
+    out of bounds.  The reference pays a device->host sync for this at every call; here a given shapes tensor (the
+    transformer caches them per feature-map geometry) is validated once, outside of CUDA-graph capture."""
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, int(S), str(spatial_shapes.device))
+    if key in _CHECKED:
+        return
+    if spatial_shapes.is_cuda and torch.cuda.is_current_stream_capturing():
+        return
+    total = int((spatial_shapes[:, 0] * spatial_shapes[:, 1]).sum())
+    assert total == S, f"spatial_shapes cover {total} positions but input_flatten has {S}"
+    if len(_CHECKED) > 1024:
+        _CHECKED.clear()
+    _CHECKED.add(key)
+
+
 class MSDeformAttn(nn.Module):
     def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
         super().__init__()
@@ -79,8 +99,7 @@ class MSDeformAttn(nn.Module):
         N, Lq, _ = query.shape
         S = input_flatten.shape[1]
         M, L, P = self.n_heads, self.n_levels, self.n_points
-        # (the reference asserts sum(H*W) == S here with a device->host sync, ms_deform_attn.py:92; the C ABI
-        #  bounds every gather by clamping, so the check is left to the caller)
+        _check_levels(input_spatial_shapes, S)      # reference :92
 
         # value.masked_fill(mask[..., None], 0) of the reference (:96-97) is applied in place on the fresh projection
         value = dl.linear(input_flatten, self.value_proj.weight, self.value_proj.bias, zero_rows=input_padding_mask)

@@ -10,6 +10,9 @@ for p in (ROOT, os.path.dirname(os.path.abspath(__file__))):
         sys.path.insert(0, p)
 
 
+os.environ.setdefault("DATR_BACKBONE_WEIGHTS", "none")      # tests load seeded weights; never look for ImageNet files
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

@@ -63,3 +63,18 @@ def test_update_rule_and_api():
     assert EMA.is_parallel(student) is False
     m = EMA.ModelEMA(teacher, decay=0.9999, updates=10)
     assert abs(m.decay(2000) - 0.9999 * (1 - 2.718281828459045 ** -1)) < 1e-12
+
+
+def test_alias_grouping_routes_partial_overlaps_to_the_sequential_path():
+    """Host logic of StateDictEMA on CPU tensors (everything takes the reference's sequential ops there) and the
+    grouping of aliased names: identical storages fold into one entry with a multiplicity."""
+    from datr_b200.ema import StateDictEMA
+    a, b = torch.randn(10), torch.randn(10)
+    want = a.clone()
+    pair = StateDictEMA([a, a, a[2:6]], [b, b, b[2:6]])
+    assert not pair.fast and len(pair.slow) == 3
+    pair.update(0.5)
+    for e, m in ((want, b), (want, b), (want[2:6], b[2:6])):
+        e *= 0.5
+        e += 0.5 * m
+    assert torch.equal(a, want)

@@ -111,28 +111,41 @@ def compare(tag, ours, ref, report):
             for sa, sb in zip(quant(a), quant(b)):
                 tk_diff += len(sb - sa)
     tk_order_equal = all(a.shape == b.shape and torch.allclose(a, b, atol=2e-6, rtol=0) for a, b in zip(ours["topk"], ref["topk"]))
+    tk_pos = sum(int(((a - b).abs().amax(-1) > 2e-6).sum()) for a, b in zip(ours["topk"], ref["topk"]) if a.shape == b.shape)
     m_diff = m_tot = 0
     for a, b in zip(ours["match"], ref["match"]):
         d, t = index_flips(a, b)
         m_diff += d; m_tot += t
     gworst, gk, gn = 0.0, None, 0
+    gerrs = []
     for k, g in ref["grads"].items():
         if k in ours["grads"]:
             e = rel(ours["grads"][k], g)
+            gerrs.append((e, k))
             gn += 1
             if e > gworst:
                 gworst, gk = e, k
+    gerrs.sort(reverse=True)
+    # all gradients as one vector: relative L2 error and cosine (insensitive to which near-tied query slot a token took)
+    num = sum(float(((ours["grads"][k] - g) ** 2).sum()) for k, g in ref["grads"].items() if k in ours["grads"])
+    den = sum(float((g ** 2).sum()) for k, g in ref["grads"].items() if k in ours["grads"])
+    dot = sum(float((ours["grads"][k] * g).sum()) for k, g in ref["grads"].items() if k in ours["grads"])
+    no = sum(float((ours["grads"][k] ** 2).sum()) for k in ref["grads"] if k in ours["grads"])
     report[tag] = {
         "total_loss": {"ours": ours["total"], "reference": ref["total"],
                        "rel": abs(ours["total"] - ref["total"]) / abs(ref["total"])},
         "worst_loss_rel": {"key": worst_k, "rel": worst, "n_losses": len(ref["losses"])},
         "two_stage_topk": {"calls": len(ref["topk"]), "indices": tk_tot, "membership_flips": tk_diff,
-                           "identical_incl_order": bool(tk_order_equal)},
+                           "positions_with_another_token": tk_pos, "identical_incl_order": bool(tk_order_equal)},
         "hungarian": {"matchings": len(ref["match"]), "assignments": m_tot, "flips": m_diff},
         "pred_logits_rel": rel(ours["pred_logits"], ref["pred_logits"]),
         "pred_boxes_rel": rel(ours["pred_boxes"], ref["pred_boxes"]),
         "worst_grad_rel": {"key": gk, "rel": gworst, "n_params": gn,
                            "missing_in_ours": sorted(set(ref["grads"]) - set(ours["grads"]))[:5]},
+        "grads": {"median_rel": gerrs[len(gerrs) // 2][0] if gerrs else None,
+                  "n_above_1e-2": sum(1 for e, _ in gerrs if e > 1e-2), "n_above_1e-3": sum(1 for e, _ in gerrs if e > 1e-3),
+                  "worst5": [(k, round(e, 5)) for e, k in gerrs[:5]],
+                  "global_rel_l2": (num / max(den, 1e-300)) ** 0.5, "global_cosine": dot / max((den * no) ** 0.5, 1e-300)},
     }
     print(f"[parity:{tag}]", json.dumps(report[tag]), flush=True)
 
@@ -180,6 +193,9 @@ def main():
     ap.add_argument("--out", default=None)
     ap.add_argument("--skip-timing", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--weights", default="seeded", choices=["seeded", "init"],
+                    help="seeded: tests/model_cases.seeded_state_dict (large random weights, chaotic: every near-tie flips); "
+                         "init: the reference's own initialisation under torch.manual_seed(0) (what training starts from)")
     ap.add_argument("--dry-run", action="store_true", help="CPU, toy configuration: exercises this script's logic only")
     a = ap.parse_args()
     dry = a.dry_run
@@ -209,8 +225,12 @@ def main():
     torch.manual_seed(0)
     ref_model, ref_crit, _ = ns.dino.build_dino(mk(device="cuda"))
     ref_model.to(dev); ref_crit.to(dev)
-    sd = mcase.seeded_state_dict(ref_model)
+    if a.weights == "seeded":
+        sd = mcase.seeded_state_dict(ref_model)
+    else:
+        sd = {k: v.detach().clone() for k, v in ref_model.state_dict().items()}
     ref_model.load_state_dict(sd, strict=True)
+    report["weights"] = a.weights
     ref_samples = ns.misc.NestedTensor(images, mask)
     ref_runs = {}
     if not a.skip_parity:
@@ -221,9 +241,13 @@ def main():
         set_precision(False, True)                            # torch defaults: what a user of the reference gets
         ref_model.global_proto = torch.zeros_like(ref_model.global_proto); ref_model.Amount = torch.zeros_like(ref_model.Amount)
         ref_runs["default"] = run_parity_pass(ref_model, ref_crit, ref_samples, targets)
+        set_precision(True, True)                             # the reference with TF32 GEMMs too (fair twin of our tf32 mode)
+        ref_model.global_proto = torch.zeros_like(ref_model.global_proto); ref_model.Amount = torch.zeros_like(ref_model.Amount)
+        ref_runs["tf32"] = run_parity_pass(ref_model, ref_crit, ref_samples, targets)
         rep = {}
         compare("reference_default_vs_reference_fp32", ref_runs["default"], ref_runs["fp32"], rep)
-        report["reference_self_noise"] = rep["reference_default_vs_reference_fp32"]
+        compare("reference_allow_tf32_vs_reference_fp32", ref_runs["tf32"], ref_runs["fp32"], rep)
+        report["reference_self_noise"] = rep
     if not a.skip_timing:
         from datr_b200.parallel import param_groups
         timing = {}
