@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the DATR/DINO data-parallel hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload msda|dino]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload dino|dino5|teacher|msda] [--gpu-baseline]
 
 Metric (BASELINE.json): images/sec at 1333x800, batch_size 2 per GPU (a DA training step consumes
 2 source + 2 target images per GPU), plus the MSDeformAttn HBM roofline.  One JSON
@@ -11,7 +12,11 @@ line on stdout (rank 0).  Workloads:
         BASELINE.json configs[1] shapes: two transformer passes, each 6 encoder calls
         (N=2, Lq=S=22223) and 6 decoder calls (Lq=1100 with denoising queries in the source
         pass, 900 in the target pass), forward AND backward: 24 + 24 launches.
-  dino  the full DINO-4scale ResNet-50 forward+backward step (datr_b200.models), same shapes.
+  dino  the full DINO-4scale ResNet-50 DA training step (datr_b200.models), same shapes: BASELINE.json configs[1]/[2]
+        (default; the metric's configuration).
+  dino5 the DINO-5scale step, batch_size 1/GPU, S = 89023 tokens: configs[3].
+  teacher  the teacher-student mutual-learning step (EMA teacher eval pass + pseudo labels + student DA pass with the
+        target-domain criterion + teacher EMA update): configs[4].
 
 Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
 Every call of a step reads its own buffers (the step cycles > 3 GB, far larger than the 126 MB L2).
@@ -59,6 +64,68 @@ def hbm_peak():
         except Exception:
             pass
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        return float(d["bf16_tflops_sustained"]), "measured bf16 sustained (MEASURED_PEAKS.json)"
+    except Exception:
+        return 1400.0, "fallback bf16 sustained (B200_PROFILING.md)"
+
+
+def make_config(workload_text, images_per_step, world):
+    """`config` of the JSON line -- the SAME dict for --impl ours and --impl reference."""
+    return {"workload": workload_text, "images_per_step_per_gpu": images_per_step,
+            "l2": "every call of a step reads its own buffers; the step cycles >3 GB (L2 is 126 MB)",
+            "parallelism": f"dp{world}"}
+
+
+def gpu_baseline_record():
+    """The reference model itself on a B200 of this pool (tools/bench_reference_gpu.py; committed measurement)."""
+    out = {}
+    for tag in ("4scale", "5scale"):
+        p = os.path.join(ROOT, "profiles", f"r02a_reference_gpu_step_{tag}.json")
+        if os.path.exists(p):
+            try:
+                d = json.load(open(p))
+                out[tag] = {k: {"ms_per_step": v.get("ms_per_step"), "images_per_s": v.get("images_per_s")}
+                            for k, v in d.get("reference_step", {}).items() if "ms_per_step" in v}
+                out[tag]["ours_same_run"] = d.get("ours_step")
+            except Exception:
+                pass
+    if out:
+        out["what"] = ("UNMODIFIED reference DINO (baseline/_ref) + its own MSDeformAttn CUDA extension rebuilt for sm_100a "
+                       "(oracle/_ref), eager engine.py step on one B200 of this pool, identical synthetic batch; measured by "
+                       "tools/bench_reference_gpu.py in an earlier gpurun call (profiles/r02a_reference_gpu_step_*.json), "
+                       "NOT in this run; --gpu-baseline re-measures it live")
+    return out or None
+
+
+class LibraryModuleHooks:
+    """Counts nn.Conv2d / nn.GroupNorm / nn.MultiheadAttention modules whose stock forward runs (i.e. cuDNN / ATen does
+    the work): the hand-written paths read the module's weights and never call the module."""
+
+    def __init__(self, model):
+        import torch.nn as nn
+        from datr_b200 import fallbacks
+        self.handles = []
+        for name, m in model.named_modules():
+            if isinstance(m, nn.Conv2d):
+                what = (f"nn.Conv2d {m.kernel_size[0]}x{m.kernel_size[1]} s{m.stride[0]} {m.in_channels}->{m.out_channels} "
+                        f"(cuDNN fprop" + (" + dgrad/wgrad" if any(p.requires_grad for p in m.parameters()) else "") + ")")
+            elif isinstance(m, nn.GroupNorm):
+                what = f"nn.GroupNorm({m.num_groups}, {m.num_channels}) (ATen)"
+            elif isinstance(m, nn.MultiheadAttention):
+                what = "nn.MultiheadAttention (ATen / SDPA)"
+            else:
+                continue
+            self.handles.append(m.register_forward_hook(lambda mod, i, o, w=what: fallbacks.note(w)))
+
+    def remove(self):
+        for h in self.handles:
+            h.remove()
 
 
 def msda_algo_bytes(N, S, M, D, L, Lq, P, es=4):
@@ -240,7 +307,20 @@ class MsdaStep:
                              "frac": v[1] / v[0] / 1e9 / peak, "share": v[0] / total}
             if v[3]:
                 per_kernel[k]["tflops"] = v[3] / v[0] / 1e12
-        return {"bound": "hbm", "kernel": top, "achieved": b / t / 1e9, "peak": peak, "peak_source": peak_src,
+        tpeak, tsrc = tensor_peak()
+        lin = {k: v for k, v in groups.items() if v[3]}
+        tensor = None
+        if lin:
+            fl, tt = sum(v[3] for v in lin.values()), sum(v[0] for v in lin.values())
+            ktop = max(lin, key=lambda k: lin[k][0])
+            tensor = {"what": "all tcgen05 linear launches of the inspected steps (TF32 products: the TF32 pipe peaks at half "
+                              "the bf16 rate the denominator was measured with)",
+                      "tflops": fl / tt / 1e12, "peak": tpeak, "peak_source": tsrc, "tensor_pipe_frac": fl / tt / 1e12 / tpeak,
+                      "top_kernel": ktop, "top_kernel_tflops": lin[ktop][3] / lin[ktop][0] / 1e12,
+                      "top_kernel_frac": lin[ktop][3] / lin[ktop][0] / 1e12 / tpeak, "share_of_timed_kernels": tt / total}
+            for k in lin:
+                per_kernel[k]["tensor_pipe_frac"] = per_kernel[k]["tflops"] / tpeak
+        return {"bound": "hbm", "kernel": top, "achieved": b / t / 1e9, "peak": peak, "peak_source": peak_src, "tensor": tensor,
                 "unit": "GB/s", "frac": b / t / 1e9 / peak, "traffic": TRAFFIC_NCU.get(top.split("<")[0]),
                 "algorithmic_bytes_per_launch": b / n, "avg_launch_us": t / n * 1e6, "share_of_step": t / total,
                 "handwritten_kernel_ms_per_step": None, "per_kernel": per_kernel}
@@ -281,6 +361,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=os.environ.get("DATR_BENCH_WORKLOAD", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-baseline", action="store_true",
+                    help="also time the UNMODIFIED reference model on this GPU (tools/bench_reference_gpu.py) and put it in `gpu_baseline`")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager (DATR_GRAPHS=0-equivalent) step time")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner with printf) and anything
@@ -305,9 +388,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        if args.workload == "dino":
+        if args.workload in ("dino", "dino5", "teacher"):
             from datr_b200 import bench_dino
-            emit(bench_dino.reference_arm(args, threads))
+            line = bench_dino.reference_arm(args, threads, args.workload)
+            text = {"dino": bench_dino.WORKLOAD, "dino5": bench_dino.WORKLOAD_5SCALE, "teacher": bench_dino.WORKLOAD_TEACHER}[args.workload]
+            line["config"] = make_config(text, 2 if args.workload == "dino5" else IMAGES_PER_STEP_PER_GPU, max(1, args.gpus))
+            line["n_gpus"] = max(1, args.gpus)
+            emit(line)
             return
         vals = []
         for _ in range(max(1, min(args.steps, 3))):
@@ -320,7 +407,7 @@ def main():
             "impl": "reference", "metric": "images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": MSDA_WORKLOAD, "l2": "n/a (CPU)"},
+            "config": make_config(MSDA_WORKLOAD, IMAGES_PER_STEP_PER_GPU, max(1, args.gpus)),
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         })
@@ -339,11 +426,13 @@ def main():
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize()
 
-    if args.workload == "dino":
+    if args.workload in ("dino", "dino5", "teacher"):
         from datr_b200 import bench_dino
-        wl = bench_dino.DinoStep(device, rank, world)
+        cls = {"dino": bench_dino.DinoStep, "dino5": bench_dino.Dino5Step, "teacher": bench_dino.TeacherStep}[args.workload]
+        wl = cls(device, rank, world)
     else:
         wl = MsdaStep(device, rank)
+    images_per_gpu = getattr(wl, "n_images", IMAGES_PER_STEP_PER_GPU)
     from datr_b200 import MultiScaleDeformableAttention as MSDA
     from datr_b200 import native
     peak, peak_src = hbm_peak()
@@ -371,17 +460,39 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     timing_note = "per-launch CUDA events on the launching stream inside the timed region"
     sg = getattr(wl, "graphs", None)
+    eager = library = None
     if sg is not None:
         # graph replays launch our kernels without passing through the Python shims: count them from the capture
-        # bookkeeping, and take the per-launch event timings from eager steps of the same workload right after
+        # bookkeeping, and take the per-launch event timings from eager steps of the same workload right after.  The same
+        # eager steps give the step time WITHOUT CUDA graphs (what a caller with varying shapes gets) and the list of
+        # library kernels (cuBLAS / cuDNN / ATen modules) still on the path.
+        from datr_b200 import fallbacks
         launches += sg.replayed_native_launches - g0
         wl.set_graphs(False)
         wl.step(); wl.step()
-        MSDA._timers = DL._timers = []
         k_eager = max(1, min(args.steps, 3))
+        if not args.no_eager:
+            barrier()
+            g0e, g1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0e.record()
+            for _ in range(k_eager):
+                wl.step()
+            g1e.record()
+            barrier()
+            eager = {"ms_per_step": g0e.elapsed_time(g1e) / k_eager, "steps": k_eager,
+                     "what": "the same step with CUDA-graph replay switched off (every kernel launched from Python); graphs need "
+                             "static shapes: per (image size, number of de-noising queries, number of boxes) signature, at "
+                             "most 4 signatures per segment are captured, further ones run eagerly like this"}
+        hooks = LibraryModuleHooks(wl.model) if hasattr(wl, "model") else None
+        fallbacks.reset(); fallbacks.enabled = True
+        MSDA._timers = DL._timers = []
         for _ in range(k_eager):
             wl.step()
         torch.cuda.synchronize()
+        fallbacks.enabled = False
+        if hooks is not None:
+            hooks.remove()
+        library = {k: v / k_eager for k, v in fallbacks.snapshot().items()}
         timers, MSDA._timers, DL._timers = MSDA._timers, None, None
         wl.set_graphs(True)
         timing_note = (f"per-launch CUDA events in {k_eager} eager steps of the same workload run right after the timed "
@@ -409,7 +520,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    images = IMAGES_PER_STEP_PER_GPU * world
+    images = images_per_gpu * world
     value = images * args.steps / (ms * 1e-3)
     e2e = images * k2 / (ms_e2e * 1e-3)
     roof = wl.roofline(timers, peak, peak_src)
@@ -420,20 +531,38 @@ def main():
         "metric": "images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": getattr(wl, "dtype", "f32"), "data": "synthetic",
-        "config": {"workload": wl.workload, "images_per_step_per_gpu": IMAGES_PER_STEP_PER_GPU,
-                   "l2": "every call of a step reads its own buffers; the step cycles >3 GB (L2 is 126 MB)",
-                   "parallelism": f"dp{world}"},
+        "config": make_config(wl.workload, images_per_gpu, world),
         "roofline": roof,
         "e2e": {"value": e2e, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": k2, "ms_per_step": ms_e2e / k2},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if eager is not None:
+        eager["images_per_s"] = images / (eager["ms_per_step"] * 1e-3)
+        line["eager"] = eager
+    if library is not None:
+        line["library_calls_per_step"] = library
+    gb = gpu_baseline_record()
+    if args.gpu_baseline and world == 1:
+        # live: the unmodified reference model on THIS GPU, right now (separate process: it monkey-patches nothing here)
+        out = os.path.join(tempfile.gettempdir(), "datr_gpu_baseline.json")
+        cfg = "5scale" if args.workload == "dino5" else "4scale"
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_reference_gpu.py"), "--config", cfg, "--steps", "5",
+                            "--skip-parity", "--reference-only", "--out", out], capture_output=True, text=True)
+        try:
+            live = json.load(open(out))["reference_step"]
+            gb = dict(gb or {}, live_this_run={k: {"ms_per_step": v.get("ms_per_step"), "images_per_s": v.get("images_per_s")}
+                                               for k, v in live.items()})
+        except Exception as e:  # noqa: BLE001
+            gb = dict(gb or {}, live_this_run={"error": repr(e)[:200], "stderr": r.stderr[-300:]})
+    if gb:
+        line["gpu_baseline"] = gb
     if not args.no_cpu_baseline and world == 1:
-        if args.workload == "dino":
-            # the same training step on the host cores (bounded sample: one step of 1 source + 1 target image)
+        if args.workload in ("dino", "dino5", "teacher"):
+            # the reference's own model on the host cores (bounded sample: 1 warm-up + 2 steps of 1 source + 1 target image)
             from datr_b200 import bench_dino
-            ref = bench_dino.reference_arm(argparse.Namespace(steps=1, warmup=0, gpus=1), threads)
+            ref = bench_dino.reference_arm(argparse.Namespace(steps=2, warmup=1, gpus=1), threads, args.workload)
             line["cpu_baseline"] = ref["cpu_baseline"]
         else:
             ips, step_s, t_call = cpu_port_images_per_s(threads, repeats=1)

@@ -235,18 +235,6 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, samp
     return [grad_value, grad_off, grad_logits]
 
 
-def set_strategy(strategy: int) -> None:
-    """Kernel family of the fp32 / 32-channel path (include/datr_msda.h): 0 auto (run kernels for encoder
-    self-attention, num_query == spatial_size), 1 row kernels, 2 run kernels wherever they exist."""
-    rc = native.lib().datr_msda_set_strategy(int(strategy))
-    if rc != 0:
-        _raise(rc, "datr_msda_set_strategy")
-
-
-def get_strategy() -> int:
-    return int(native.lib().datr_msda_get_strategy())
-
-
 def install(name: str = "MultiScaleDeformableAttention"):
     """Register this module under the reference's extension name."""
     sys.modules[name] = sys.modules[__name__]

@@ -12,7 +12,7 @@ import math
 
 import torch
 
-from . import native
+from . import fallbacks, native
 
 
 def applicable(q: torch.Tensor, blocked, dropout_p: float) -> bool:
@@ -30,6 +30,7 @@ class _SelfAttention(torch.autograd.Function):
         N, H, T, d = q.shape
         scale = 1.0 / math.sqrt(d)
         q3, k3, v3 = (t.reshape(N * H, T, d) for t in (q, k, v))          # copies the strided head views (2 MB each)
+        fallbacks.note("torch.bmm (cuBLAS) decoder self-attention Q K^T and P V", 2)
         p = torch.bmm(q3, k3.transpose(1, 2))                             # [N*H, T, T] scores, then probabilities
         lib = native.lib()
         mask = blocked.contiguous() if blocked is not None else None
@@ -49,6 +50,7 @@ class _SelfAttention(torch.autograd.Function):
         q3, k3, v3, p = ctx.saved_tensors
         N, H, T, d = ctx.shape
         go3 = go.reshape(N * H, T, d)
+        fallbacks.note("torch.bmm (cuBLAS) decoder self-attention backward (dV, dP, dQ, dK)", 4)
         dv = torch.bmm(p.transpose(1, 2), go3)
         ds = torch.bmm(go3, v3.transpose(1, 2))                           # dP, turned into dS in place
         lib = native.lib()

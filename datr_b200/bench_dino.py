@@ -141,32 +141,179 @@ class DinoStep:
                                                                  "what": "ResNet body, encoder x2, two-stage selection x2, decoder x2, heads, image discriminator, criterion losses (forward + backward each)"}}
 
 
-def reference_arm(args, threads):
-    """CPU arm: the same training step run on the host cores with the MSDeformAttn op served by the oracle's port of
-    the reference's grid_sample CPU path (func.py:41-61).  Bounded sample: 1 source + 1 target image per step."""
-    import json  # noqa: F401
-    from oracle import msda as om
-    from datr_b200.models.dino.ops.modules import ms_deform_attn as mod
+WORKLOAD_5SCALE = ("DINO-5scale ResNet-50 DA training step (forward + losses + backward + gradient all-reduce + clip + AdamW), "
+                   "synthetic 1333x800, batch_size 1/GPU = 1 source + 1 target image, 5 feature levels (S = 89023 tokens), "
+                   "900 queries + CDN; fp32 tensors, MSDeformAttn fp32, dense layers TF32 products with fp32 accumulation")
+WORKLOAD_TEACHER = ("Teacher-student mutual-learning step of main_teacher.py / engine.py:146-300 on DINO-4scale ResNet-50: EMA "
+                    "teacher eval pass on the 2 target images -> PostProcess -> thresholded + NMS pseudo labels; student "
+                    "DA pass on 2 source + 2 target images (self_training_flag) -> source criterion + target-domain criterion on "
+                    "the pseudo labels -> backward -> gradient all-reduce -> clip -> AdamW -> teacher EMA update; synthetic "
+                    "1333x800, batch_size 2/GPU; fp32 tensors, dense layers TF32 products with fp32 accumulation")
 
-    class CpuFn:
-        @staticmethod
-        def apply(value, shapes, level_start, loc, attn, step):
-            return om.core_torch(value, shapes, loc, attn)
-    mod.MSDeformAttnFunction = CpuFn
+
+class Dino5Step(DinoStep):
+    """BASELINE.json configs[3]: DINO-5scale (return_interm_indices [0,1,2,3], 5 feature levels), batch_size 1 per GPU."""
+    name = "dino5"
+    workload = WORKLOAD_5SCALE
+
+    def __init__(self, device, rank=0, world=1, **over):
+        super().__init__(device, rank, world, batch_size=1, return_interm_indices=[0, 1, 2, 3], num_feature_levels=5, **over)
+
+
+class TeacherStep(DinoStep):
+    """BASELINE.json configs[4]: the self-training step (engine.py:196-300) followed by the teacher's EMA update
+    (main_teacher.py:384; the reference updates the teacher once per epoch, here it is part of EVERY step, i.e. the
+    step does at least the reference's work).  A randomly initialised teacher scores every query ~0.01, so the
+    reference's threshold 0.3 (config/DA/*_self_training.py:124) would leave the target-domain criterion without work;
+    the benchmark threshold is 0: all PostProcess detections pass, class-wise NMS then keeps <= 100 pseudo boxes per
+    target image -- an upper bound on the pseudo-label work of a real run."""
+    name = "teacher"
+    workload = WORKLOAD_TEACHER
+
+    def __init__(self, device, rank=0, world=1, batch_size=2, **over):
+        super().__init__(device, rank, world, batch_size=batch_size, **over)
+        from datr_b200.models.dino import EMA
+        from datr_b200.models.dino.dino import PostProcess
+        self.teacher = EMA.ModelEMA(self.model, decay=0.9997)            # main_teacher.py:292, ema_decay_teacher
+        self.post = PostProcess(num_select=self.args.num_select, nms_iou_threshold=self.args.nms_iou_threshold)
+        self.threshold = np.asarray([0.0] * self.args.num_classes)
+        h, w = self.host_images.shape[-2:]
+        size = torch.tensor([h, w], device=device)
+        # target-domain label dicts: only their bookkeeping keys are read (self_training_utils.py:52-67)
+        self.target_labels = [{"image_id": torch.tensor([i], device=device), "area": torch.zeros(0, device=device),
+                               "iscrowd": torch.zeros(0, dtype=torch.long, device=device), "orig_size": size, "size": size}
+                              for i in range(batch_size)]
+        self.unit_sizes = torch.ones((batch_size, 2), dtype=torch.long, device=device)
+        self.n_pseudo = 0
+
+    def _step(self, images, mask, targets):
+        from datr_b200.models.dino import self_training_utils as st
+        from datr_b200 import graphs
+        if self.graphs is not None:
+            self.graphs.begin_step()
+        self.grads.zero()
+        samples = NestedTensor(images, mask)
+        # 1. teacher on the (weakly augmented) target images                               engine.py:196-204
+        unlabel = st.get_unlabel_img(samples)
+        active, graphs.ACTIVE = graphs.ACTIVE, None                       # inference pass: eager
+        with torch.no_grad():
+            pred = self.teacher.ema(unlabel)
+            results = self.post(pred, self.unit_sizes, not_to_xyxy=True)                   # :205-207
+        graphs.ACTIVE = active
+        # 2. pseudo labels                                                                  :210-216
+        idx_list, labels_d, boxes_d, scores_d = st.get_pseudo_label_via_threshold(results, threshold=self.threshold)
+        pseudo = st.deal_pesudo_label(self.target_labels, idx_list, labels_d, boxes_d, scores_d)
+        pseudo = st.rescale_pseudo_targets(unlabel, pseudo)
+        # 3. student on the whole batch                                                     :221-225
+        out = self.model(samples, targets, self_training_flag=True)
+        source_out, target_out = st.spilt_output(out)                                       # :232
+        valid_out, pseudo_list = st.get_valid_output(target_out, pseudo, idx_list)          # :235
+        self.n_pseudo = sum(int(t["labels"].shape[0]) for t in pseudo_list)
+        wd = self.criterion.weight_dict
+        loss_src = self.criterion(source_out, targets, target_domain_flag=False)           # :240
+        loss_tgt = self.criterion(valid_out, pseudo_list, target_domain_flag=True)         # :243
+        total_src = sum(loss_src[k] * wd[k] for k in loss_src if k in wd)
+        total_tgt = sum(loss_tgt[k] * wd[k] for k in loss_tgt if k in wd)
+        loss = total_src + total_tgt * wd["loss_self_training"]                             # :257
+        loss.backward()
+        self.grads.all_reduce()
+        self.grads.clip_(self.args.clip_max_norm)
+        self.opt.step()
+        self.teacher.update(self.model)                                                     # main_teacher.py:384
+        return loss
+
+    def extra(self):
+        d = super().extra()
+        d["pseudo_boxes_last_step"] = self.n_pseudo
+        return d
+
+
+def _reference_model_cpu(batch_size, over):
+    """The UNMODIFIED reference model (baseline/_ref, staged by oracle/stage_ref.py; /root/reference in the build
+    container) on the host cores, MSDeformAttn served by the reference's own CPU path ms_deform_attn_core_pytorch
+    (ops/functions/ms_deform_attn_func.py:41-61).  Returns (model, criterion, make_samples) or None."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    tests = os.path.join(root, "tests")
+    if tests not in sys.path:
+        sys.path.insert(0, tests)
+    try:
+        import ref_loader
+        if not ref_loader.available():
+            return None
+        ns = ref_loader.load(cuda_ext=False)
+    except Exception as e:      # noqa: BLE001
+        print(f"[bench] reference model unavailable ({e!r}); falling back to the port", file=sys.stderr)
+        return None
+    return ns, ref_loader
+
+
+def reference_arm(args, threads, workload="dino"):
+    """CPU arm (`bench.py --impl reference`, and the `cpu_baseline` of the default run): the reference's own CPU
+    implementation of the path -- the unmodified reference DINO model + SetCriterion from baseline/_ref with its
+    pure-PyTorch MSDeformAttn (kind "reference"); if the staged tree is missing, datr_b200's mirror of the model with the
+    oracle's port of that op (kind "port").  Every step is a BOUNDED SAMPLE of the GPU arm's workload: the same training
+    step (forward, losses, backward, clip, AdamW; engine.py:54-111) on 1 source + 1 target image instead of the
+    2 + 2 (4-scale) of a GPU step, all host threads.  Runs exactly --warmup + --steps steps."""
     torch.set_num_threads(threads)
-    wl = DinoStep(torch.device("cpu"), batch_size=1)
-    times = []
-    for i in range(max(1, min(args.steps, 2)) + (1 if args.warmup > 0 else 0)):
-        t0 = time.perf_counter()
-        wl.step()
-        times.append(time.perf_counter() - t0)
-    t = min(times[1:] or times)
-    ips = wl.n_images / t
-    sample = ("1 source + 1 target 1333x800 image through the same DINO-4scale DA training step on the host cores "
-              "(torch CPU ops; MSDeformAttn = port of the reference's grid_sample path, oracle/msda.py)")
+    five = workload == "dino5"
+    over = {"return_interm_indices": [0, 1, 2, 3], "num_feature_levels": 5} if five else {}
+    ref = _reference_model_cpu(1, over)
+    n_images = 2
+    rng = np.random.default_rng(42)
+    images = torch.from_numpy(rng.standard_normal((n_images, 3, H_IMG, W_IMG)).astype(np.float32))
+    mask = torch.zeros((n_images, H_IMG, W_IMG), dtype=torch.bool)
+    targets = synth_targets(rng, 1, 91, "cpu")
+    if ref is not None:
+        ns, ref_loader = ref
+        kind = "reference"
+        os.environ.setdefault("DATR_BACKBONE_WEIGHTS", "none")
+        torch.manual_seed(42)
+        with ref_loader.cpu_cuda_shim():
+            model, criterion, _ = ns.dino.build_dino(dino_args(device="cpu", **over))
+        model.train(); criterion.train()
+        opt = torch.optim.AdamW(param_groups(model, 1e-4, 1e-5), lr=1e-4, weight_decay=1e-4)
+        samples = ns.misc.NestedTensor(images, mask)
+
+        def one():
+            with ref_loader.cpu_cuda_shim():                     # the reference hard-codes .cuda() in its training path
+                out = model(samples, targets)
+                loss_dict = criterion(out, targets)
+            wd = criterion.weight_dict
+            loss = sum(loss_dict[k] * wd[k] for k in loss_dict if k in wd)
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+            opt.step()
+            return float(loss)
+        what = "the UNMODIFIED reference DINO + SetCriterion (baseline/_ref) with ms_deform_attn_core_pytorch"
+    else:
+        kind = "port"
+        from oracle import msda as om
+        from datr_b200.models.dino.ops.modules import ms_deform_attn as mod
+
+        class CpuFn:
+            @staticmethod
+            def apply(value, shapes, level_start, loc, attn, step):
+                return om.core_torch(value, shapes, loc, attn)
+        mod.MSDeformAttnFunction = CpuFn
+        wl = DinoStep(torch.device("cpu"), batch_size=1, **over)
+
+        def one():
+            wl.step()
+            return float(wl.last_loss)
+        what = "datr_b200's mirror of the model on torch CPU ops with the oracle's port of ms_deform_attn_core_pytorch"
+    for _ in range(max(0, args.warmup)):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(max(1, args.steps)):
+        last = one()
+    t = (time.perf_counter() - t0) / max(1, args.steps)
+    ips = n_images / t
+    sample = (f"{max(1, args.steps)} timed steps (+{max(0, args.warmup)} warm-up) of the same training step on 1 source + 1 target "
+              f"1333x800 image (a GPU step has {'1 + 1' if five else '2 + 2'}), {what}, {threads} host threads; last loss {last:.3f}")
     return {"impl": "reference", "metric": "images/sec", "value": ips, "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+            "steps": max(1, args.steps), "warmup": max(0, args.warmup), "ms_per_step": t * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "n/a (CPU)"},
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

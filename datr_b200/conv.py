@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import torch
 
-from . import native
+from . import fallbacks, native
 
 
 class _Conv3x3BiasReLU(torch.autograd.Function):
@@ -38,6 +38,7 @@ class _Conv3x3BiasReLU(torch.autograd.Function):
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
         gz = torch.ops.aten.threshold_backward(gy.contiguous(memory_format=torch.channels_last), y, 0.0)
+        fallbacks.note("aten.convolution_backward (cuDNN dgrad + wgrad) of a 3x3 ResNet convolution")
         need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False]
         gx, gw, _ = torch.ops.aten.convolution_backward(gz, x, w, None, [ctx.stride, ctx.stride], [1, 1], [1, 1], False,
                                                         [0, 0], 1, need)

@@ -265,8 +265,8 @@ constexpr int kGeomBytes = 512;  // kMaxLevels * sizeof(LevelGeom) rounded up
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int kP, int kBatch, int kMode>
-__global__ void __launch_bounds__(256)
+template <int kP, int kBatch, int kMode, int kMinBlocks = 0>
+__global__ void __launch_bounds__(256, kMinBlocks)
 msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                  const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                  const float* __restrict__ attn, const float* __restrict__ ref, long long ostride, long long lstride,
@@ -501,336 +501,6 @@ msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
 }
 
 // ------------------------------------------------------------------------------------------------
-// Run kernels: encoder self-attention, where the queries ARE the pixels of the value maps.
-//
-// Neighbouring queries of one head sample neighbouring pixels of every level (their reference points are one pixel
-// apart on their own level, 1/2, 1/4, ... pixel apart on the coarser ones, and the offsets come from a linear map of
-// smoothly varying features).  The row kernels above give that locality to the caches only: a 2x2 footprint costs four
-// 128-byte L1TEX wavefronts and -- in the backward -- four 128-byte reductions sent to L2, whether or not the previous
-// query of the same (head, level, point) just touched the same pixels.  Both kernels sit on those two walls
-// (profiles/r01o_msda_fused_ln_rowmask_ncu_full.txt: l1tex 2.07 cycles per line forward; 82.5 M red sectors = 2.64 GB
-// on the SM->L2 path backward).
-//
-// Here the loop nest is transposed.  An 8-lane group owns ONE sample slot (level l, point p) of one head and WALKS a
-// run of kRunLen consecutive queries, keeping the current 2x2 footprint in registers: the four value rows (float4 per
-// lane) and, in the backward, four gradient accumulators.  With d = anchor(q) - anchor(q-1):
-//   d == 0  same footprint: no load, no reduction, contributions add up in registers
-//   d == 1  footprint moved one pixel right: the right column becomes the left column (register moves), two loads;
-//           backward sends the two pixels that left the footprint to L2 (2 reds instead of 4)
-//   else    four loads; backward flushes the four accumulators
-// so L1TEX wavefronts and red traffic shrink by the run coherence of the data (up to 16x on the coarsest level of the
-// encoder), and never grow: incoherent locations cost what the row kernels cost.
-// Geometry (slot tables) is still computed once per sample by the 8 lanes of a (query, head) row (stage 1, shared
-// with the row kernels: `place`, fused prologue) and published through shared memory; the forward's sum over slots is
-// a two-step shuffle over the four groups of a warp plus a shared-memory partial per warp; the backward's
-// per-sample results return to the row mapping through the slot table for the softmax / location chain rules.
-// ------------------------------------------------------------------------------------------------
-constexpr int kRunLen = 32;     // consecutive queries walked by one group
-constexpr int kRunsPerCta = 2;  // runs (of the same head) per CTA
-constexpr int kRunRows = kRunLen * kRunsPerCta;
-constexpr int kFarPixel = -2;   // "no footprint yet": any real anchor is >= 2 away
-
-__device__ __forceinline__ void red_add4_nz(const float* p, const float4& a) {
-  if (a.x != 0.f || a.y != 0.f || a.z != 0.f || a.w != 0.f)
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
-}
-
-__device__ __forceinline__ const float* byte_off(const float* p, long long bytes) {
-  return reinterpret_cast<const float*>(reinterpret_cast<const char*>(p) + bytes);
-}
-
-// threads of a run: 8 lanes per slot, slots padded to whole warps
-__host__ __device__ inline int run_threads(int taps) { return ((taps + 3) & ~3) * 8; }
-
-template <int kP, int kMode>
-__global__ void __maxnreg__(64)
-msda_fwd_runs_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
-                      const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                      const float* __restrict__ attn, const float* __restrict__ ref, long long ostride, long long lstride,
-                      int N, int S, int M, int L, int Lq, float* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  LevelGeom* geom = reinterpret_cast<LevelGeom*>(smem);
-  const int LP = L * kP, ws = table_stride(LP), ps = pix_stride(LP);
-  const int tpr = run_threads(LP), nw = tpr >> 5;
-  uint4* wtab = reinterpret_cast<uint4*>(smem + kGeomBytes);                 // [64][ws] {w00,w01,w10,w11} * attn
-  float4* part = reinterpret_cast<float4*>(wtab + kRunRows * ws);           // [runs][nw][kRunLen][8] warp partials
-  int* ptab = reinterpret_cast<int*>(part + kRunsPerCta * nw * kRunLen * 8); // [64][ps] anchor pixel
-  load_levels(geom, shapes, lstart, L);
-
-  const int sub = threadIdx.x & 7;
-  const int m = blockIdx.x % M;
-  const int tiles = (Lq + kRunRows - 1) / kRunRows;
-  const int tile = blockIdx.x / M;
-  const int b = tile / tiles, q0 = (tile % tiles) * kRunRows;
-  const int rs4 = M * 32 * 4;
-  const float* vb = value + (long long)b * S * (M * 32) + m * 32 + sub * 4;
-
-  // stage 1: the 8 lanes of a (query, head) row publish its slots (rows past the end repeat the last query)
-  for (int rr = threadIdx.x >> 3; rr < kRunRows; rr += blockDim.x >> 3) {
-    const long long bq = (long long)b * Lq + min(q0 + rr, Lq - 1);
-    const long long row = bq * M + m;
-    uint4* myw = wtab + rr * ws;
-    int* myp = ptab + rr * ps;
-    auto publish = [&](int s, float x, float y, float a) {
-      const Slots t = place(x, y, a, geom[s / kP]);
-      const float ay0 = t.wy0 * t.a, ay1 = t.wy1 * t.a;
-      myw[s] = make_uint4(__float_as_uint(ay0 * t.wx0), __float_as_uint(ay0 * t.wx1),
-                          __float_as_uint(ay1 * t.wx0), __float_as_uint(ay1 * t.wx1));
-      myp[s] = t.pix;
-    };
-    if constexpr (kMode == 0) {
-      for (int s = sub; s < LP; s += 8) {
-        const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
-        publish(s, xy.x, xy.y, __ldg(attn + row * LP + s));
-      }
-    } else {
-      const RowTaps t = fused_taps<kMode, kP>(loc + bq * ostride + (long long)m * LP * 2, attn + bq * lstride + (long long)m * LP,
-                                              ref, bq, sub, L, LP, geom);
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c)
-        if (c * 8 + sub < LP) publish(c * 8 + sub, t.x[c], t.y[c], t.a[c]);
-    }
-  }
-  __syncthreads();
-
-  // stage 2: group `slot` of a run walks the run's queries
-  {
-    const int run = threadIdx.x / tpr, tr = threadIdx.x - run * tpr;
-    const int slot = tr >> 3, wir = tr >> 5;
-    const bool used = slot < LP;               // padding groups of the last warp add zeros
-    const int s = used ? slot : 0;
-    const LevelGeom g = geom[s / kP];
-    const bool wide = g.W >= 2;
-    const int d01 = wide ? rs4 : 0;
-    const long long d10 = g.H >= 2 ? (long long)g.W * rs4 : 0;
-    const long long d11 = d10 + d01;
-    const int n = max(0, min(kRunLen, Lq - (q0 + run * kRunLen)));
-    const uint4* wrow = wtab + (run * kRunLen) * ws + s;
-    const int* prow = ptab + (run * kRunLen) * ps + s;
-    float4* prt = part + ((run * nw + wir) * kRunLen) * 8 + sub;
-    int cur = kFarPixel;
-    float4 v00 = make_float4(0.f, 0.f, 0.f, 0.f), v01 = v00, v10 = v00, v11 = v00;
-    for (int i = 0; i < n; ++i) {
-      const int pix = prow[i * ps];
-      const uint4 w = wrow[i * ws];
-      const int d = pix - cur;
-      if (d != 0) {
-        const bool shift = wide && d == 1;
-        const float* p00 = pixel_ptr(vb, pix, rs4);
-        if (shift) { v00 = v01; v10 = v11; }
-        else { v00 = ldg4_ordered(p00); v10 = ldg4_ordered(byte_off(p00, d10)); }
-        v01 = ldg4_ordered(byte_off(p00, d01));
-        v11 = ldg4_ordered(byte_off(p00, d11));
-        cur = pix;
-      }
-      const float w00 = used ? __uint_as_float(w.x) : 0.f, w01 = used ? __uint_as_float(w.y) : 0.f;
-      const float w10 = used ? __uint_as_float(w.z) : 0.f, w11 = used ? __uint_as_float(w.w) : 0.f;
-      float4 a;
-      a.x = fmaf(w11, v11.x, fmaf(w10, v10.x, fmaf(w01, v01.x, w00 * v00.x)));
-      a.y = fmaf(w11, v11.y, fmaf(w10, v10.y, fmaf(w01, v01.y, w00 * v00.y)));
-      a.z = fmaf(w11, v11.z, fmaf(w10, v10.z, fmaf(w01, v01.z, w00 * v00.z)));
-      a.w = fmaf(w11, v11.w, fmaf(w10, v10.w, fmaf(w01, v01.w, w00 * v00.w)));
-      // sum over the four slots of this warp
-      a.x += __shfl_xor_sync(0xffffffffu, a.x, 8);  a.y += __shfl_xor_sync(0xffffffffu, a.y, 8);
-      a.z += __shfl_xor_sync(0xffffffffu, a.z, 8);  a.w += __shfl_xor_sync(0xffffffffu, a.w, 8);
-      a.x += __shfl_xor_sync(0xffffffffu, a.x, 16); a.y += __shfl_xor_sync(0xffffffffu, a.y, 16);
-      a.z += __shfl_xor_sync(0xffffffffu, a.z, 16); a.w += __shfl_xor_sync(0xffffffffu, a.w, 16);
-      if ((threadIdx.x & 31) < 8) prt[i * 8] = a;
-    }
-  }
-  __syncthreads();
-
-  // stage 3: sum the warps of a run, one (query, head) row per 8 lanes
-  for (int rr = threadIdx.x >> 3; rr < kRunRows; rr += blockDim.x >> 3) {
-    const int q = q0 + rr;
-    if (q >= Lq) continue;
-    const int run = rr / kRunLen, i = rr - run * kRunLen;
-    const float4* prt = part + ((run * nw) * kRunLen + i) * 8 + sub;
-    float4 acc = prt[0];
-    for (int w = 1; w < nw; ++w) {
-      const float4 t = prt[w * kRunLen * 8];
-      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-    }
-    *reinterpret_cast<float4*>(out + (((long long)b * Lq + q) * M + m) * 32 + sub * 4) = acc;
-  }
-}
-
-template <int kP, int kMode>
-__global__ void __maxnreg__(80)
-msda_bwd_runs_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
-                      const int64_t* __restrict__ lstart, const float* __restrict__ loc,
-                      const float* __restrict__ attn, const float* __restrict__ ref, const float* __restrict__ grad_out,
-                      long long ostride, long long lstride, int N, int S, int M, int L, int Lq,
-                      float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
-  extern __shared__ __align__(16) unsigned char smem[];
-  LevelGeom* geom = reinterpret_cast<LevelGeom*>(smem);
-  const int LP = L * kP, ws = table_stride(LP);
-  const int tpr = run_threads(LP);
-  uint4* tab0 = reinterpret_cast<uint4*>(smem + kGeomBytes);   // [64][ws] {pix, a, softmax weight, -}
-  uint4* tab1 = tab0 + kRunRows * ws;                          // {wy0, wy1, wx0, wx1}
-  uint4* tab2 = tab1 + kRunRows * ws;                          // {sy0, sy1, sx0, sx1}, then {d/d attn, d/d x, d/d y}
-  float4* gtile = reinterpret_cast<float4*>(tab2 + kRunRows * ws);  // [64][8] grad_out rows of this head
-  load_levels(geom, shapes, lstart, L);
-
-  const int sub = threadIdx.x & 7;
-  const int m = blockIdx.x % M;
-  const int tiles = (Lq + kRunRows - 1) / kRunRows;
-  const int tile = blockIdx.x / M;
-  const int b = tile / tiles, q0 = (tile % tiles) * kRunRows;
-  const int rs4 = M * 32 * 4;
-  const long long voff = (long long)b * S * (M * 32) + m * 32 + sub * 4;
-  const float* vb = value + voff;
-  const float* gb = grad_value + voff;
-
-  for (int rr = threadIdx.x >> 3; rr < kRunRows; rr += blockDim.x >> 3) {
-    const long long bq = (long long)b * Lq + min(q0 + rr, Lq - 1);
-    const long long row = bq * M + m;
-    uint4* my0 = tab0 + rr * ws;
-    uint4* my1 = tab1 + rr * ws;
-    uint4* my2 = tab2 + rr * ws;
-    auto publish = [&](int s, float x, float y, float a, float soft) {
-      const Slots t = place(x, y, a, geom[s / kP]);
-      my0[s] = make_uint4(unsigned(t.pix), __float_as_uint(t.a), __float_as_uint(soft), 0u);
-      my1[s] = make_uint4(__float_as_uint(t.wy0), __float_as_uint(t.wy1), __float_as_uint(t.wx0), __float_as_uint(t.wx1));
-      my2[s] = make_uint4(__float_as_uint(t.sy0), __float_as_uint(t.sy1), __float_as_uint(t.sx0), __float_as_uint(t.sx1));
-    };
-    if constexpr (kMode == 0) {
-      for (int s = sub; s < LP; s += 8) {
-        const float2 xy = __ldg(reinterpret_cast<const float2*>(loc) + row * LP + s);
-        publish(s, xy.x, xy.y, __ldg(attn + row * LP + s), 0.f);
-      }
-    } else {
-      const RowTaps t = fused_taps<kMode, kP>(loc + bq * ostride + (long long)m * LP * 2, attn + bq * lstride + (long long)m * LP,
-                                              ref, bq, sub, L, LP, geom);
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c)
-        if (c * 8 + sub < LP) publish(c * 8 + sub, t.x[c], t.y[c], t.a[c], t.a[c]);
-    }
-    gtile[rr * 8 + sub] = ldg4(grad_out + row * 32 + sub * 4);
-  }
-  __syncthreads();
-
-  {
-    const int run = threadIdx.x / tpr, tr = threadIdx.x - run * tpr;
-    const int slot = tr >> 3;
-    const bool used = slot < LP;
-    const int s = used ? slot : 0;
-    const LevelGeom g = geom[s / kP];
-    const bool wide = g.W >= 2;
-    const int d01 = wide ? rs4 : 0;
-    const long long d10 = g.H >= 2 ? (long long)g.W * rs4 : 0;
-    const long long d11 = d10 + d01;
-    const float fW = float(g.W), fH = float(g.H);
-    const int n = max(0, min(kRunLen, Lq - (q0 + run * kRunLen)));   // padding groups walk along with weight 0
-    const int base = (run * kRunLen) * ws + s;
-    const float4* grow = gtile + (run * kRunLen) * 8 + sub;
-    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-    int cur = kFarPixel;
-    float4 v00 = zero, v01 = zero, v10 = zero, v11 = zero;
-    float4 c00 = zero, c01 = zero, c10 = zero, c11 = zero;   // gradient of the footprint's four pixels
-    for (int i = 0; i < n; ++i) {
-      const uint4 q0r = tab0[base + i * ws], q1 = tab1[base + i * ws], q2 = tab2[base + i * ws];
-      const float4 go = grow[i * 8];
-      const int pix = int(q0r.x);
-      const float a = used ? __uint_as_float(q0r.y) : 0.f;
-      const int d = pix - cur;
-      if (d != 0) {
-        const bool shift = wide && d == 1;
-        const float* gp = pixel_ptr(gb, cur, rs4);
-        red_add4_nz(gp, c00);
-        red_add4_nz(byte_off(gp, d10), c10);
-        const float* p00 = pixel_ptr(vb, pix, rs4);
-        if (shift) {
-          c00 = c01; c10 = c11; v00 = v01; v10 = v11;
-        } else {
-          red_add4_nz(byte_off(gp, d01), c01);
-          red_add4_nz(byte_off(gp, d11), c11);
-          c00 = zero; c10 = zero;
-          v00 = ldg4_ordered(p00); v10 = ldg4_ordered(byte_off(p00, d10));
-        }
-        c01 = zero; c11 = zero;
-        v01 = ldg4_ordered(byte_off(p00, d01));
-        v11 = ldg4_ordered(byte_off(p00, d11));
-        cur = pix;
-      }
-      const float wy0 = __uint_as_float(q1.x), wy1 = __uint_as_float(q1.y);
-      const float wx0 = __uint_as_float(q1.z), wx1 = __uint_as_float(q1.w);
-      const float ay0 = wy0 * a, ay1 = wy1 * a;
-      const float w00 = ay0 * wx0, w01 = ay0 * wx1, w10 = ay1 * wx0, w11 = ay1 * wx1;
-      c00.x = fmaf(w00, go.x, c00.x); c00.y = fmaf(w00, go.y, c00.y); c00.z = fmaf(w00, go.z, c00.z); c00.w = fmaf(w00, go.w, c00.w);
-      c01.x = fmaf(w01, go.x, c01.x); c01.y = fmaf(w01, go.y, c01.y); c01.z = fmaf(w01, go.z, c01.z); c01.w = fmaf(w01, go.w, c01.w);
-      c10.x = fmaf(w10, go.x, c10.x); c10.y = fmaf(w10, go.y, c10.y); c10.z = fmaf(w10, go.z, c10.z); c10.w = fmaf(w10, go.w, c10.w);
-      c11.x = fmaf(w11, go.x, c11.x); c11.y = fmaf(w11, go.y, c11.y); c11.z = fmaf(w11, go.z, c11.z); c11.w = fmaf(w11, go.w, c11.w);
-      const float e00 = dot4(go, v00), e01 = dot4(go, v01), e10 = dot4(go, v10), e11 = dot4(go, v11);
-      const float r0 = fmaf(wx1, e01, wx0 * e00), r1 = fmaf(wx1, e11, wx0 * e10);
-      const float sx0 = __uint_as_float(q2.z), sx1 = __uint_as_float(q2.w);
-      const float t0 = fmaf(sx1, e01, sx0 * e00), t1 = fmaf(sx1, e11, sx0 * e10);
-      float pa = fmaf(wy1, r1, wy0 * r0);                                                // cuh:156
-      float px = fmaf(wy1, t1, wy0 * t0);                                                // cuh:157 (x)
-      float py = fmaf(__uint_as_float(q2.y), r1, __uint_as_float(q2.x) * r0);            // cuh:158 (y)
-      pa = group8_sum(pa); px = group8_sum(px); py = group8_sum(py);
-      // all 8 lanes of the group have read record i (the shuffles are warp-synchronous): reuse its slot of table 2
-      if (sub == 0 && used)
-        tab2[base + i * ws] = make_uint4(__float_as_uint(pa), __float_as_uint(px * (a * fW)), __float_as_uint(py * (a * fH)), 0u);
-    }
-    const float* gp = pixel_ptr(gb, cur, rs4);
-    red_add4_nz(gp, c00);
-    red_add4_nz(byte_off(gp, d01), c01);
-    red_add4_nz(byte_off(gp, d10), c10);
-    red_add4_nz(byte_off(gp, d11), c11);
-  }
-  __syncthreads();
-
-  // stage 3: back to one (query, head) row per 8 lanes: softmax / location chain rules, coalesced gradient rows
-  for (int rr = threadIdx.x >> 3; rr < kRunRows; rr += blockDim.x >> 3) {
-    const int q = q0 + rr;
-    const bool live = q < Lq;
-    const long long bq = (long long)b * Lq + min(q, Lq - 1);
-    const long long row = bq * M + m;
-    const uint4* r0 = tab0 + rr * ws;
-    const uint4* r2 = tab2 + rr * ws;
-    if constexpr (kMode == 0) {
-      if (live)
-        for (int s = sub; s < LP; s += 8) {
-          const uint4 res = r2[s];
-          grad_attn[row * LP + s] = __uint_as_float(res.x);
-          reinterpret_cast<float2*>(grad_loc)[row * LP + s] = make_float2(__uint_as_float(res.y), __uint_as_float(res.z));
-        }
-    } else {
-      uint4 res[kChunks];
-      float soft[kChunks];
-      float dot = 0.f;
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        res[c] = make_uint4(0u, 0u, 0u, 0u);
-        soft[c] = 0.f;
-        if (c * 8 + sub < LP) { res[c] = r2[c * 8 + sub]; soft[c] = __uint_as_float(r0[c * 8 + sub].z); }
-        dot = fmaf(soft[c], __uint_as_float(res[c].x), dot);
-      }
-      dot = group8_sum(dot);
-#pragma unroll
-      for (int c = 0; c < kChunks; ++c) {
-        const int s = c * 8 + sub;
-        if (live && s < LP) {
-          const int l = s / kP;
-          float gx = __uint_as_float(res[c].y), gy = __uint_as_float(res[c].z);
-          if (kMode == 1) {
-            gx = gx / float(geom[l].W);
-            gy = gy / float(geom[l].H);
-          } else {
-            const float4 rr4 = __ldg(reinterpret_cast<const float4*>(ref) + bq * L + l);
-            gx = ((gx * 0.5f) * rr4.z) / float(kP);
-            gy = ((gy * 0.5f) * rr4.w) / float(kP);
-          }
-          grad_attn[bq * lstride + (long long)m * LP + s] = soft[c] * (__uint_as_float(res[c].x) - dot);
-          *reinterpret_cast<float2*>(grad_loc + bq * ostride + ((long long)m * LP + s) * 2) = make_float2(gx, gy);
-        }
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Generic kernels: any channel count / point count, float or double.  One warp per (b,q,m) row,
 // lanes stride over channels.
 // ------------------------------------------------------------------------------------------------
@@ -973,83 +643,34 @@ int allow_big_smem() {
   return DATR_OK;
 }
 
-// Kernel family of the fp32 / D = 32 path: 0 = auto (run kernels when the queries are the pixels of the value maps,
-// i.e. Lq == S: encoder self-attention), 1 = always the row kernels, 2 = run kernels wherever they exist.
-// Process-wide tuning knob (datr_msda_set_strategy); initialised from the environment variable DATR_MSDA_STRATEGY.
-std::atomic<int> g_strategy{-1};
-
-int strategy() {
-  int v = g_strategy.load(std::memory_order_relaxed);
-  if (v < 0) {
-    const char* e = getenv("DATR_MSDA_STRATEGY");
-    v = e ? atoi(e) : 0;
-    if (v < 0 || v > 2) v = 0;
-    g_strategy.store(v, std::memory_order_relaxed);
-  }
-  return v;
-}
-
-bool use_runs(int mode, int P, int L, int Lq, int S) {
-  if (P != 4 || mode == 2 || L * P > kMaxTaps) return false;  // instantiated for the DINO encoder (4 points, 2-d references)
-  const int st = strategy();
-  return st == 2 || (st == 0 && Lq == S);
-}
-
-size_t runs_smem_fwd(int LP) {
-  return kGeomBytes + (size_t)kRunRows * table_stride(LP) * 16 + (size_t)kRunsPerCta * (run_threads(LP) / 32) * kRunLen * 128 +
-         (size_t)kRunRows * pix_stride(LP) * 4;
-}
-size_t runs_smem_bwd(int LP) { return kGeomBytes + (size_t)kRunRows * table_stride(LP) * 48 + (size_t)kRunRows * 128; }
-
-int allow_runs_smem() {
-  static std::atomic<uint64_t> done{0};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaGetDevice failed%s");
-  const uint64_t bit = 1ull << (dev & 63);
-  if (done.load(std::memory_order_acquire) & bit) return DATR_OK;
-  const int fb = (int)runs_smem_fwd(kMaxTaps), bb = (int)runs_smem_bwd(kMaxTaps);
-  cudaError_t e = cudaFuncSetAttribute(msda_fwd_runs_f32_d32<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(msda_fwd_runs_f32_d32<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fb);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(msda_bwd_runs_f32_d32<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bb);
-  if (e == cudaSuccess) e = cudaFuncSetAttribute(msda_bwd_runs_f32_d32<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bb);
-  if (e != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  done.fetch_or(bit, std::memory_order_release);
-  return DATR_OK;
-}
-
-long long runs_ctas(int N, int Lq, int M) { return (long long)N * ((Lq + kRunRows - 1) / kRunRows) * M; }
-
 // launchers of the fp32 / D = 32 kernels; mode 0 = materialised locations + weights, 1 / 2 = fused prologue (R = 2 / 4)
 int launch_fwd_fast(int mode, const float* v, const int64_t* shapes, const int64_t* lstart, const float* lc,
                     const float* at, const float* ref, long long ostride, long long lstride, int N, int S, int M, int L,
                     int Lq, int P, float* o, cudaStream_t stream) {
-  if (use_runs(mode, P, L, Lq, S)) {
-    const long long rc_ = runs_ctas(N, Lq, M);
-    if (rc_ > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
-    if (int rc = allow_runs_smem()) return rc;
-    const int threads = kRunsPerCta * run_threads(L * P);
-    const size_t sm = runs_smem_fwd(L * P);
-    if (mode == 0)
-      msda_fwd_runs_f32_d32<4, 0><<<(unsigned)rc_, threads, sm, stream>>>(v, shapes, lstart, lc, at, ref, ostride, lstride, N, S, M, L, Lq, o);
-    else
-      msda_fwd_runs_f32_d32<4, 1><<<(unsigned)rc_, threads, sm, stream>>>(v, shapes, lstart, lc, at, ref, ostride, lstride, N, S, M, L, Lq, o);
-    return after_launch("msda_fwd_runs_f32_d32");
-  }
   const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
   if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
   const int LP = L * P;
   const size_t smem = kGeomBytes + (size_t)kRowsPerCta * (table_stride(LP) * 16 + pix_stride(LP) * 4);
 #define DATR_FWD(PP, BB, MM) \
   msda_fwd_f32_d32<PP, BB, MM><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, ostride, lstride, N, S, M, L, Lq, o)
+#define DATR_FWD4(BB, MM, KK) \
+  msda_fwd_f32_d32<4, BB, MM, KK><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, ostride, lstride, N, S, M, L, Lq, o)
+  // 4 points (DINO): measured on B200 (profiles/r02d_msda_fwd_variants.txt) -- long calls (encoder) are fastest with
+  // 2 samples of loads in flight at 5 CTAs/SM (171 vs 177 us at config 2, 409 vs 433 us at 5 scales), short calls
+  // (decoder, a few hundred CTAs per SM wave) with 4 samples in flight at 4 CTAs/SM (19.5 vs 22.5 us)
+  const bool short_call = (long long)Lq * 4 < (long long)S;
 #define DATR_FWD_P(MM)                  \
   switch (P) {                          \
     case 1: DATR_FWD(1, 1, MM); break;  \
     case 2: DATR_FWD(2, 2, MM); break;  \
-    case 4: DATR_FWD(4, 2, MM); break;  \
+    case 4:                             \
+      if (short_call) DATR_FWD4(4, MM, 4); else DATR_FWD4(2, MM, 5); \
+      break;                            \
     default: DATR_FWD(8, 2, MM); break; \
   }
   if (mode == 0) { DATR_FWD_P(0) } else if (mode == 1) { DATR_FWD_P(1) } else { DATR_FWD_P(2) }
 #undef DATR_FWD_P
+#undef DATR_FWD4
 #undef DATR_FWD
   return after_launch("msda_fwd_f32_d32");
 }
@@ -1057,18 +678,6 @@ int launch_fwd_fast(int mode, const float* v, const int64_t* shapes, const int64
 int launch_bwd_fast(int mode, const float* v, const int64_t* shapes, const int64_t* lstart, const float* lc,
                     const float* at, const float* ref, const float* go, long long ostride, long long lstride, int N, int S,
                     int M, int L, int Lq, int P, float* gv, float* gl, float* ga, cudaStream_t stream) {
-  if (use_runs(mode, P, L, Lq, S)) {
-    const long long rc_ = runs_ctas(N, Lq, M);
-    if (rc_ > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
-    if (int rc = allow_runs_smem()) return rc;
-    const int threads = kRunsPerCta * run_threads(L * P);
-    const size_t sm = runs_smem_bwd(L * P);
-    if (mode == 0)
-      msda_bwd_runs_f32_d32<4, 0><<<(unsigned)rc_, threads, sm, stream>>>(v, shapes, lstart, lc, at, ref, go, ostride, lstride, N, S, M, L, Lq, gv, gl, ga);
-    else
-      msda_bwd_runs_f32_d32<4, 1><<<(unsigned)rc_, threads, sm, stream>>>(v, shapes, lstart, lc, at, ref, go, ostride, lstride, N, S, M, L, Lq, gv, gl, ga);
-    return after_launch("msda_bwd_runs_f32_d32");
-  }
   const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
   if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
   const size_t smem = kGeomBytes + (size_t)kRowsPerCta * table_stride(L * P) * 48;
@@ -1200,13 +809,6 @@ int datr_msda_fused_backward(const void* value, const int64_t* shapes, const int
                          Lq, P, static_cast<float*>(grad_value), static_cast<float*>(grad_offsets),
                          static_cast<float*>(grad_logits), stream);
 }
-
-int datr_msda_set_strategy(int s) {
-  if (s < 0 || s > 2) return fail(DATR_ERR_BAD_ARGUMENT, "strategy must be 0 (auto), 1 (row kernels) or 2 (run kernels)%s");
-  g_strategy.store(s, std::memory_order_relaxed);
-  return DATR_OK;
-}
-int datr_msda_get_strategy(void) { return strategy(); }
 
 const char* datr_last_error(void) { return g_err; }
 int datr_abi_version(void) { return 1; }

@@ -18,7 +18,7 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
-from . import native
+from . import fallbacks, native
 
 _MODE = "fp32"
 _WGRAD = True          # weight/bias gradients on the tcgen05 kernel (False: cuBLAS GEMM + column-sum kernels)
@@ -156,13 +156,18 @@ class _LinearTF32(torch.autograd.Function):
                 g2 = torch.ops.aten.threshold_backward(g2, act, 0.0)
         gx = gw = None
         if ctx.needs_input_grad[0]:
-            gx = _launch(g2, _c(w.t()), None, None, False).view(ctx.xshape) if N % 32 == 0 and K % 4 == 0 else (g2 @ w).view(ctx.xshape)
+            if N % 32 == 0 and K % 4 == 0:
+                gx = _launch(g2, _c(w.t()), None, None, False).view(ctx.xshape)
+            else:
+                fallbacks.note(f"torch.matmul (cuBLAS) dgrad N={N} K={K}")
+                gx = (g2 @ w).view(ctx.xshape)
         if fused:
             gw, gb = _wgrad(g2, x2, want_gb)
         else:
             if want_gb and gb is None:
                 gb = _colsum(g2)[1]
             if want_gw:
+                fallbacks.note(f"torch.matmul (cuBLAS) wgrad N={N} K={K}")
                 gw = g2.t() @ x2
         return gx, gw, gb, gres, None, None
 
@@ -222,6 +227,8 @@ def linear(x, weight, bias=None, relu=False, residual=None, zero_rows=None):
         return zero_masked_rows(F.linear(x, weight, bias), zero_rows)
     if _MODE == "tf32" and eligible(x, weight):
         return _LinearTF32.apply(x, weight, bias, residual, relu)
+    if _MODE == "tf32" and x.is_cuda:
+        fallbacks.note(f"F.linear (cuBLAS) N={weight.shape[0]} K={weight.shape[1]}: outside the tcgen05 kernel's shapes (N % 4, N >= 32, K % 32)")
     y = F.linear(x, weight, bias)
     if relu == 1:
         y = F.relu(y)

@@ -23,8 +23,7 @@ LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
-EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward", "datr_msda_fused_backward",
-           "datr_msda_set_strategy", "datr_msda_get_strategy", "datr_last_error", "datr_abi_version",
+EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward", "datr_msda_fused_backward", "datr_last_error", "datr_abi_version",
            "datr_launch_count", "datr_linear_tf32", "datr_linear_last_error", "datr_linear_launch_count",
            "datr_layernorm256_forward", "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count",
            "datr_colsum", "datr_relu_bwd_colsum", "datr_colsum_last_error", "datr_colsum_launch_count",
@@ -93,10 +92,6 @@ def lib() -> ctypes.CDLL:
         L.datr_msda_fused_forward.argtypes = [vp, i64p, i64p, vp, ll, vp, ll, vp, i, i, i, i, i, i, i, i, i, vp, vp]
         L.datr_msda_fused_backward.restype = i
         L.datr_msda_fused_backward.argtypes = [vp, i64p, i64p, vp, ll, vp, ll, vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp]
-        L.datr_msda_set_strategy.restype = i
-        L.datr_msda_set_strategy.argtypes = [i]
-        L.datr_msda_get_strategy.restype = i
-        L.datr_msda_get_strategy.argtypes = []
         L.datr_last_error.restype = ctypes.c_char_p
         L.datr_last_error.argtypes = []
         L.datr_abi_version.restype = i

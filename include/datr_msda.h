@@ -103,17 +103,6 @@ int datr_msda_fused_backward(const void* value, const int64_t* spatial_shapes, c
                              int channels, int num_levels, int num_query, int num_point, int dtype,
                              void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits, void* stream);
 
-/*
- * Kernel family of the fp32 / 32-channel path (no reference counterpart: the reference has one kernel per direction).
- *   0  auto (default): "run" kernels when num_query == spatial_size, i.e. the queries are the pixels of the value maps
- *      (encoder self-attention, deformable_transformer.py:779): an 8-lane group walks consecutive queries of one
- *      (head, level, point) and keeps the 2x2 footprint in registers; "row" kernels otherwise (decoder cross-attention)
- *   1  always the row kernels      2  run kernels wherever they are instantiated (4 points, 2-d reference points)
- * Results are identical up to fp32 summation order.  Process-wide; also read once from DATR_MSDA_STRATEGY.
- */
-int datr_msda_set_strategy(int strategy);
-int datr_msda_get_strategy(void);
-
 /* Message of the last failing call made by the calling thread ("" if none). */
 const char* datr_last_error(void);
 

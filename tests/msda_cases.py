@@ -87,6 +87,33 @@ def make_inputs(N, M, D, Lq, P, levels, loc_mode="uniform", seed=0, dtype=np.flo
     )
 
 
+def init_pattern_offsets(N, Lq, M, L, P, jitter, rng):
+    """Offsets in pixels as MSDeformAttn._reset_parameters leaves them (weight 0, bias = direction grid), + jitter."""
+    th = np.arange(M) * (2.0 * np.pi / M)
+    grid = np.stack([np.cos(th), np.sin(th)], -1)
+    grid = grid / np.abs(grid).max(-1, keepdims=True)
+    off = np.tile(grid[:, None, None, :], (1, L, P, 1)) * (np.arange(P) + 1)[None, None, :, None]
+    off = np.broadcast_to(off[None, None], (N, Lq, M, L, P, 2)).copy()
+    return off + rng.standard_normal(off.shape) * jitter
+
+
+def coherent_inputs(N, M, P, levels, jitter, seed, Lq=-1):
+    rng = np.random.default_rng(seed)
+    L, S = len(levels), sum(h * w for h, w in levels)
+    if Lq < 0:
+        Lq = S
+    ref = encoder_reference_points(levels)[np.arange(Lq) % S]
+    inv = np.array([[1.0 / w, 1.0 / h] for h, w in levels])[None, None, None, :, None, :]
+    off = init_pattern_offsets(N, Lq, M, L, P, jitter, rng)
+    loc = ref[None, :, None, None, None, :] + off * inv
+    logits = rng.standard_normal((N, Lq, M, L * P))
+    e = np.exp(logits - logits.max(-1, keepdims=True))
+    return dict(value=rng.standard_normal((N, S, M, 32)).astype(np.float32), shapes=np.array(levels, dtype=np.int64),
+                level_start=level_start_index(levels), loc=loc.astype(np.float32),
+                attn=(e / e.sum(-1, keepdims=True)).reshape(N, Lq, M, L, P).astype(np.float32),
+                grad_out=rng.standard_normal((N, Lq, M * 32)).astype(np.float32))
+
+
 def small_case(name, dtype=np.float32):
     for c in SMALL_CASES:
         if c[0] == name:

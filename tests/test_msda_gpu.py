@@ -216,3 +216,25 @@ def test_runs_on_the_current_stream_and_other_threads(ops):
     torch.cuda.synchronize()
     t = threading.Thread(target=work); t.start(); t.join()
     assert torch.equal(res["out"], base)
+
+
+THIN_LEVELS = {
+    "l4": [(12, 17), (6, 9), (3, 5), (2, 3)],
+    "thin": [(9, 1), (1, 7), (1, 1), (5, 2)],          # levels one pixel wide / high / a single pixel
+    "wide": [(3, 70), (2, 35), (1, 18), (1, 9)],
+}
+
+
+@pytest.mark.parametrize("jitter", [0.0, 0.02, 0.6], ids=["init", "subpixel", "halfpixel"])
+@pytest.mark.parametrize("lv", list(THIN_LEVELS))
+def test_initial_offset_pattern_locations(ops, lv, jitter):
+    """The locations a freshly built model samples (ops/modules/ms_deform_attn.py:62-76: point k of head m sits k pixels
+    along direction m from the query's own pixel centre on every level): exact-integer pixel coordinates at jitter 0,
+    i.e. three of four corner weights exactly zero, and floor() flipping with the sign of the rounding error."""
+    MSDA, _ = ops
+    inp = mc.coherent_inputs(2, 8, 4, THIN_LEVELS[lv], jitter, seed=list(THIN_LEVELS).index(lv) * 10 + int(jitter * 100))
+    got = run_cuda(MSDA, to_dev(inp, torch.float32))
+    ora = [om.fwd(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["attn"]),
+           *om.bwd(inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["attn"], inp["grad_out"])]
+    for g, o, key in zip(got, ora, ("out", "gv", "gl", "ga")):
+        assert mc.rel_err(g, o) < REL_F32_TIGHT * 3, key

@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--weights", default="seeded", choices=["seeded", "init"],
                     help="seeded: tests/model_cases.seeded_state_dict (large random weights, chaotic: every near-tie flips); "
                          "init: the reference's own initialisation under torch.manual_seed(0) (what training starts from)")
+    ap.add_argument("--reference-only", action="store_true", help="time / check the reference model only")
     ap.add_argument("--dry-run", action="store_true", help="CPU, toy configuration: exercises this script's logic only")
     a = ap.parse_args()
     dry = a.dry_run
@@ -268,6 +269,13 @@ def main():
     stack.close()
     if not dry:
         torch.cuda.empty_cache()
+
+    if a.reference_only:
+        if a.out:
+            os.makedirs(os.path.dirname(os.path.abspath(a.out)), exist_ok=True)
+            json.dump(report, open(a.out, "w"), indent=1)
+        print(json.dumps(report))
+        return
 
     # ---------------- ours ----------------
     from datr_b200 import bench_dino, linear as dl

@@ -32,10 +32,10 @@ def timeit(fn, iters=20, flush=None):
 
 def main():
     """Location distributions: `encoder` = pixel centres + N(0, (2 px)^2) per sample (no coherence between neighbouring
-    queries: worst case of the run kernels); `init` = the offset pattern of MSDeformAttn._reset_parameters (what a
+    queries); `init` = the offset pattern of MSDeformAttn._reset_parameters (what a
     freshly built model, and bench.py's dino workload, samples); `init+0.3px` = that pattern with per-sample jitter
     (smooth learned offsets); `uniform` = locations anywhere in the map."""
-    from test_msda_runs_gpu import coherent_inputs
+    coherent_inputs = mc.coherent_inputs
     ref = None if "--no-ref" in sys.argv else build_ref.load()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     cases = [("cfg2_enc", 2, mc.CFG2_LEVELS, -1, "encoder"), ("cfg2_enc_init", 2, mc.CFG2_LEVELS, -1, ("coherent", 0.0)),
@@ -43,7 +43,11 @@ def main():
              ("cfg2_enc_uniform", 2, mc.CFG2_LEVELS, -1, "uniform"),
              ("cfg2_dec1100", 2, mc.CFG2_LEVELS, 1100, "uniform"), ("cfg1_enc", 1, mc.CFG1_LEVELS, -1, "encoder"),
              ("cfg4_enc", 1, mc.CFG4_LEVELS, -1, "encoder"), ("cfg4_enc_init+0.3px", 1, mc.CFG4_LEVELS, -1, ("coherent", 0.3))]
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--cases=")]
+    fused = "--fused" in sys.argv
     for name, N, levels, Lq, mode in cases:
+        if only and name not in only[0]:
+            continue
         if isinstance(mode, tuple):
             inp = coherent_inputs(N, 8, 4, levels, mode[1], 1)
         else:
@@ -52,11 +56,21 @@ def main():
         args = (d["value"], d["shapes"], d["level_start"], d["loc"], d["attn"])
         S = d["value"].shape[1]; LQ = d["loc"].shape[1]
         fb, bb = algo_bytes(N, S, 8, 32, len(levels), LQ, 4)
-        for impl, mod in (("rows", MSDA), ("runs", MSDA), ("ref", ref)):
+        if fused and LQ == S:
+            # the module-level entry points the model calls: raw offsets + logits + 2-d reference points
+            refp = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(
+                mc.encoder_reference_points(levels)[None, :, None, :], (N, S, len(levels), 2)), dtype=np.float32)).cuda()
+            wh = d["shapes"].flip(-1).float()
+            off = ((d["loc"] - refp[:, :, None, :, None, :]) * wh[None, None, None, :, None, :]).contiguous()
+            lg = d["attn"].flatten(3).log().contiguous()
+            fa = (d["value"], d["shapes"], d["level_start"], off, lg, refp)
+            tf, _ = timeit(lambda: MSDA.ms_deform_attn_fused_forward(*fa), flush=flush)
+            tb, _ = timeit(lambda: MSDA.ms_deform_attn_fused_backward(*fa, d["grad_out"]), flush=flush)
+            print(f"{name:18s} fused cold fwd {tf*1e3:8.1f} us ({fb/tf/1e6:7.1f} GB/s, {fb/tf/1e6/PEAK:5.3f}) "
+                  f"bwd {tb*1e3:8.1f} us ({bb/tb/1e6:7.1f} GB/s, {bb/tb/1e6/PEAK:5.3f})", flush=True)
+        for impl, mod in (("ours", MSDA), ("ref", ref)):
             if mod is None:
                 continue
-            if impl != "ref":
-                MSDA.set_strategy(1 if impl == "rows" else 2)
             for flushed, fl in (("cold", flush),):
                 tf, tfm = timeit(lambda: mod.ms_deform_attn_forward(*args, 64), flush=fl)
                 tb, tbm = timeit(lambda: mod.ms_deform_attn_backward(*args, d["grad_out"], 64), flush=fl)
