@@ -21,6 +21,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 
 #include "datr_linear.h"
 #include "tcgen05_common.cuh"
@@ -64,8 +65,8 @@ __host__ __device__ constexpr uint32_t tf32_idesc_mn(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | (uint32_t(n >> 3) << 17) | (uint32_t(BM >> 4) << 24);
 }
 
-__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+__device__ __forceinline__ void red_add2(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
 template <int BN, int STAGES>
@@ -140,21 +141,27 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tma_dz, const __grid_const
         umma_commit(acc_full);
       }
     } else {
+      // accumulator rows = rows of dW.  tcgen05.ld.16x256b hands four neighbouring lanes one 32-byte sector of a dW row
+      // (profiles/r02f_tmem_ld_layout_probe.txt), so the partial tile is added with 8-byte vector reductions that
+      // always cover whole sectors (the 32x32b layout scattered 16-byte pieces over 32 rows per instruction).
       const int lane_base = (warp & 3) * 32;
-      const int n = n0 + lane_base + lane;                    // row of dW owned by this thread
+      const int n = n0 + lane_base + lane;                    // row of dW whose bias gradient this thread adds
+      const int rq = lane >> 2, cq = (lane & 3) * 2;
       mbar_wait(acc_full, 0);
       tc_fence_after();
       const uint32_t t0 = tmem_d + (uint32_t(lane_base) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int ch = 0; ch < 2 * (BN / 64); ++ch) {
+        const int h = ch & 1, c0 = (ch >> 1) * 64;
         uint32_t v[32];
-        tmem_ld32(t0 + uint32_t(c), v);
-        if (n < N) {
-          float* row = dw + (size_t)n * K + k0 + c;
+        tmem_ld_16x256b_x8(tmem_d + uint32_t(c0) + (uint32_t(lane_base + 16 * h) << 16), v);
+        const int n_lo = n0 + lane_base + 16 * h + rq, n_hi = n_lo + 8;
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            if (k0 + c + j + 4 <= K)
-              red_add4(row + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int g = 0; g < 8; ++g) {
+          const int col = k0 + c0 + 8 * g + cq;
+          if (col >= K) break;                                // K % 4 == 0 and col is even
+          if (n_lo < N) red_add2(dw + (size_t)n_lo * K + col, __uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]));
+          if (n_hi < N) red_add2(dw + (size_t)n_hi * K + col, __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
         }
       }
       if (db != nullptr && k0 == 0) {                         // one K tile per dW row block carries the bias gradient
@@ -201,7 +208,11 @@ int launch(const CUtensorMap& mdz, const CUtensorMap& mx, float* dw, float* db, 
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   const int tiles = ((N + BM - 1) / BM) * ((K + BN - 1) / BN);
-  int splits = (2 * sms + tiles - 1) / tiles;                 // about two CTAs' worth of tiles per SM in total
+  // one CTA per SM (shared memory): every wave pays the prologue and the reduction epilogue again.  Measured
+  // (profiles/r02f_wgrad_waves.txt, M = 44 446): one wave is faster when dW has few row blocks (N <= 256: 55 -> 41 us at
+  // 256 x 256, 173 -> 162 us at 256 x 2048), two waves when it has many (N = 2048: 136 vs 157 us).
+  const int waves = N <= 256 ? 1 : 2;
+  int splits = (waves * sms + tiles - 1) / tiles;
   const int max_splits = (M + 4 * BK - 1) / (4 * BK);         // at least 128 rows per slab
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
