@@ -70,7 +70,10 @@ class DinoStep:
             self.model.to(memory_format=torch.channels_last)
         self.criterion.train()
         broadcast_parameters(self.model)
-        self.grads = FlatGradients(self.model)
+        # backbone gradients are produced last: they sit at the end of the flat buffer, and the exchange of everything
+        # else starts from a backward hook while the ResNet backward is still running (parallel.py)
+        self.grads = FlatGradients(self.model, late=lambda n: n.startswith("backbone"))
+        self.model._on_backbone_output_grad = self.grads.reduce_early
         self.opt = torch.optim.AdamW(param_groups(self.model, args.lr, args.lr_backbone), lr=args.lr,
                                      weight_decay=args.weight_decay, fused=device.type == "cuda")
         rng = np.random.default_rng(42 + rank)                  # main.py:138: seed + rank

@@ -1,11 +1,14 @@
 """3x3 convolution + FrozenBN + ReLU on NHWC activations through the implicit-GEMM tcgen05 kernel
 (host side of include/datr_conv.h; csrc/conv3x3_tf32.cu).
 
-`conv3x3_bias_relu(x, weight, bias, stride)`: x [N,Cin,H,W] and weight [Cout,Cin,3,3] in channels_last memory
-format (i.e. NHWC / [Cout,3,3,Cin] in memory), bias [Cout]; returns relu(conv(x, weight, padding=1) + bias) as a
-channels_last tensor.  Forward = our kernel (TF32 products, fp32 accumulation); backward = ReLU mask + ATen's
-convolution_backward (cuDNN dgrad / wgrad) on the same operands.  Used by the ResNet bottleneck's conv2 in "tf32" mode
-(reference models/dino/backbone.py:97); FrozenBN is folded into weight / bias by the caller."""
+`conv3x3_bias_act(x, weight, bias, stride, act)`: x [N,Cin,H,W] and weight [Cout,Cin,3,3] in channels_last memory
+format (i.e. NHWC / [Cout,3,3,Cin] in memory), bias [Cout]; returns act(conv(x, weight, padding=1) + bias) as a
+channels_last tensor, act = identity / ReLU / LeakyReLU(0.2).  Forward = our kernel (TF32 products, fp32 accumulation).
+Backward: activation mask; the input gradient of stride-1 layers is the SAME kernel on the rotated, channel-swapped
+filter; weight gradients (and the input gradient of stride-2 layers) come from ATen's convolution_backward (cuDNN).
+Used in "tf32" mode by the ResNet bottleneck's conv2 (reference models/dino/backbone.py:97; FrozenBN folded into weight /
+bias by the caller), the image-level domain discriminator (DA_utils.py:50-79) and the extra stride-2 input projection
+(dino.py:118-123)."""
 from __future__ import annotations
 
 import torch
@@ -13,44 +16,71 @@ import torch
 from . import fallbacks, native
 
 
-class _Conv3x3BiasReLU(torch.autograd.Function):
+def _launch(xc, wc, bias, stride, act):
+    n, cin, h, w = xc.shape
+    cout = wc.shape[0]
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    y = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=xc.device, memory_format=torch.channels_last)
+    lib = native.lib()
+    with torch.cuda.device(xc.device):
+        rc = lib.datr_conv3x3_nhwc_tf32(xc.data_ptr(), wc.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                        y.data_ptr(), n, h, w, cin, cout, stride, act,
+                                        torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"datr_conv3x3_nhwc_tf32 failed (code {rc}): {lib.datr_conv_last_error().decode()}")
+    return y
+
+
+class _Conv3x3(torch.autograd.Function):
+    """act(conv3x3(x, weight, padding=1, stride) + bias), act: 0 identity, 1 ReLU, 2 LeakyReLU(0.2)."""
+
     @staticmethod
-    def forward(ctx, x, weight, bias, stride):
-        n, cin, h, w = x.shape
-        cout = weight.shape[0]
+    def forward(ctx, x, weight, bias, stride, act):
         xc = x.contiguous(memory_format=torch.channels_last)
         wc = weight.contiguous(memory_format=torch.channels_last)
-        ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
-        y = torch.empty((n, cout, ho, wo), dtype=torch.float32, device=x.device, memory_format=torch.channels_last)
-        lib = native.lib()
-        with torch.cuda.device(x.device):
-            rc = lib.datr_conv3x3_nhwc_tf32(xc.data_ptr(), wc.data_ptr(), bias.data_ptr() if bias is not None else None,
-                                            y.data_ptr(), n, h, w, cin, cout, stride, 1,
-                                            torch.cuda.current_stream().cuda_stream)
-        if rc != 0:
-            raise RuntimeError(f"datr_conv3x3_nhwc_tf32 failed (code {rc}): {lib.datr_conv_last_error().decode()}")
-        ctx.stride = stride
-        ctx.save_for_backward(xc, wc, y)
+        y = _launch(xc, wc, bias, stride, act)
+        ctx.stride, ctx.act = stride, act
+        ctx.save_for_backward(xc, wc, y if act else None)
         return y
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         x, w, y = ctx.saved_tensors
-        gz = torch.ops.aten.threshold_backward(gy.contiguous(memory_format=torch.channels_last), y, 0.0)
-        fallbacks.note("aten.convolution_backward (cuDNN dgrad + wgrad) of a 3x3 ResNet convolution")
-        need = [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False]
-        gx, gw, _ = torch.ops.aten.convolution_backward(gz, x, w, None, [ctx.stride, ctx.stride], [1, 1], [1, 1], False,
-                                                        [0, 0], 1, need)
+        gz = gy.contiguous(memory_format=torch.channels_last)
+        if ctx.act == 1:
+            gz = torch.ops.aten.threshold_backward(gz, y, 0.0)
+        elif ctx.act == 2:      # LeakyReLU(0.2) keeps the sign: the mask can be read from the output
+            gz = torch.where(y > 0, gz, gz * 0.2)
+        cout, cin = w.shape[0], w.shape[1]
+        gx = gw = None
+        own_dgrad = ctx.needs_input_grad[0] and ctx.stride == 1 and cout % 32 == 0 and cin % 4 == 0
+        if own_dgrad:
+            # input gradient of a stride-1 convolution = the same convolution of gz with the filter rotated by 180 degrees
+            # and its channel axes swapped: the forward kernel on a [Cin, 3, 3, Cout] copy of the (small) weight
+            w_rot = w.flip(2, 3).transpose(0, 1).contiguous(memory_format=torch.channels_last)
+            gx = _launch(gz, w_rot, None, 1, 0)
+        need = [ctx.needs_input_grad[0] and not own_dgrad, ctx.needs_input_grad[1], False]
+        if need[0] or need[1]:
+            fallbacks.note("aten.convolution_backward (cuDNN " + " + ".join(n for n, k in (("dgrad", need[0]), ("wgrad", need[1])) if k)
+                           + ") of a 3x3 convolution")
+            gx2, gw, _ = torch.ops.aten.convolution_backward(gz, x, w, None, [ctx.stride, ctx.stride], [1, 1], [1, 1], False,
+                                                             [0, 0], 1, need)
+            gx = gx2 if need[0] else gx
         gb = gz.sum((0, 2, 3)) if ctx.needs_input_grad[2] else None
-        return gx, gw, gb, None
+        return gx, gw, gb, None, None
 
 
 def eligible(x: torch.Tensor, conv: torch.nn.Conv2d) -> bool:
     return (x.is_cuda and x.dtype == torch.float32 and conv.kernel_size == (3, 3) and conv.padding == (1, 1)
-            and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None and conv.stride in ((1, 1), (2, 2))
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.stride in ((1, 1), (2, 2))
             and conv.in_channels % 32 == 0 and conv.out_channels % 4 == 0)
 
 
 def conv3x3_bias_relu(x, weight, bias, stride: int):
-    return _Conv3x3BiasReLU.apply(x, weight, bias, stride)
+    return _Conv3x3.apply(x, weight, bias, stride, 1)
+
+
+def conv3x3_bias_act(x, weight, bias, stride: int, act: int):
+    """act: 0 identity, 1 ReLU, 2 LeakyReLU(0.2)."""
+    return _Conv3x3.apply(x, weight, bias, stride, act)

@@ -179,7 +179,11 @@ conv3x3_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_cons
             if (oy < cs.Ho && ox < cs.Wo) {
               float4 t = o[j];
               t.x += b4.x; t.y += b4.y; t.z += b4.z; t.w += b4.w;
-              if (relu) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+              if (relu == 1) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+              else if (relu == 2) {       // LeakyReLU(0.2) of the image-level domain discriminator (DA_utils.py:61-79)
+                t.x = t.x > 0.f ? t.x : 0.2f * t.x; t.y = t.y > 0.f ? t.y : 0.2f * t.y;
+                t.z = t.z > 0.f ? t.z : 0.2f * t.z; t.w = t.w > 0.f ? t.w : 0.2f * t.w;
+              }
               *reinterpret_cast<float4*>(y + (((size_t)n * cs.Ho + oy) * cs.Wo + ox) * cs.Cout + col) = t;
             }
           }

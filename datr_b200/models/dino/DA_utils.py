@@ -58,9 +58,16 @@ class FCDiscriminator_img(nn.Module):
         self.leaky_relu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
 
     def forward(self, x):
+        from datr_b200 import conv as dconv, linear as dl
         for conv in (self.conv1, self.conv2, self.conv3):
-            x = self.leaky_relu(conv(x))
-        return self.classifier(x)
+            if (dl.get_mode() == "tf32" and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+                    and dconv.eligible(x, conv)):
+                # conv + bias + LeakyReLU(0.2) in one implicit-GEMM tcgen05 kernel; its input gradient runs on the
+                # same kernel (datr_b200.conv)
+                x = dconv.conv3x3_bias_act(x, conv.weight, conv.bias, 1, 2)
+            else:
+                x = self.leaky_relu(conv(x))
+        return self.classifier(x)       # 128 -> 1 channel: outside the kernel's shapes (Cout % 4), library convolution
 
 
 def get_prototype_class_wise(object_query_last_layer, outputs_class, num_classes, global_proto=None, global_amount=None):

@@ -152,10 +152,30 @@ class DINO(nn.Module):
         if graphs.ACTIVE is not None and samples.tensors.is_cuda:
             base = self.backbone[0]
             feats = graphs.ACTIVE.run("body", lambda: graphs.BodySegment(base.body), (samples.tensors,))
+            self._watch_backbone_output_grads(feats)
             srcs, masks, poss = graphs.ACTIVE.call("project", self.input_proj, self._project, tuple(feats), samples.mask)
             return list(srcs), list(masks), list(poss)
         features, poss = self.backbone(samples)
+        self._watch_backbone_output_grads([f.tensors for f in features])
         return self._project_levels(features, poss, samples.mask)
+
+    def _watch_backbone_output_grads(self, feats):
+        """Data-parallel hook (datr_b200.parallel.FlatGradients.reduce_early): `self._on_backbone_output_grad`, if set, is
+        called during the backward pass at the moment the gradients of ALL backbone feature maps exist -- every
+        parameter outside the backbone has its final gradient then, and only the ResNet backward is still to run, so
+        the caller can start exchanging the first part of the gradients underneath it."""
+        cb = getattr(self, "_on_backbone_output_grad", None)
+        feats = [f for f in feats if f.requires_grad]
+        if cb is None or not feats or not torch.is_grad_enabled():
+            return
+        pending = [len(feats)]
+
+        def fire(_grad):
+            pending[0] -= 1
+            if pending[0] == 0:
+                cb()
+        for f in feats:
+            f.register_hook(fire)
 
     def _project(self, feats, mask):
         """Everything between the ResNet body and the transformer as a pure tensor function: mask down-sampling
@@ -165,15 +185,32 @@ class DINO(nn.Module):
         srcs, masks, poss = self._project_levels(features, poss, mask)
         return tuple(srcs), tuple(masks), tuple(poss)
 
+    @staticmethod
+    def _input_proj(proj, x):
+        """One input projection (reference dino.py:111-126: Conv2d 1x1, or 3x3 stride 2 for the extra levels, + GroupNorm).
+        On NHWC CUDA tensors in tensor-core mode the 1x1 convolution is a GEMM over pixels on the tcgen05 linear kernel
+        and the 3x3 one runs on the implicit-GEMM kernel (bias in the epilogue); GroupNorm stays ATen."""
+        from datr_b200 import conv as dconv, linear as dl
+        conv, norm = proj[0], proj[1]
+        if (dl.get_mode() == "tf32" and x.is_cuda and x.dtype == torch.float32 and x.dim() == 4
+                and x.is_contiguous(memory_format=torch.channels_last)):
+            n, cin, h, w = x.shape
+            if conv.kernel_size == (1, 1) and conv.stride == (1, 1) and cin % 32 == 0:
+                y = dl.linear(x.permute(0, 2, 3, 1).reshape(-1, cin), conv.weight.reshape(conv.out_channels, cin), conv.bias)
+                return norm(y.view(n, h, w, conv.out_channels).permute(0, 3, 1, 2))
+            if dconv.eligible(x, conv):
+                return norm(dconv.conv3x3_bias_act(x, conv.weight, conv.bias, conv.stride[0], 0))
+        return proj(x)
+
     def _project_levels(self, features, poss, full_mask):
         srcs, masks = [], []
         for l, feat in enumerate(features):
             src, mask = feat.decompose()
             assert mask is not None
-            srcs.append(self.input_proj[l](src))
+            srcs.append(self._input_proj(self.input_proj[l], src))
             masks.append(mask)
         for l in range(len(srcs), self.num_feature_levels):
-            src = self.input_proj[l](features[-1].tensors if l == len(features) else srcs[-1])
+            src = self._input_proj(self.input_proj[l], features[-1].tensors if l == len(features) else srcs[-1])
             mask = F.interpolate(full_mask[None].float(), size=src.shape[-2:]).to(torch.bool)[0]
             poss.append(self.backbone[1](NestedTensor(src, mask)).to(src.dtype))
             srcs.append(src)

@@ -5,8 +5,9 @@ Replaces the reference's `DistributedDataParallel(model, find_unused_parameters=
 training step: every trainable parameter's .grad is a view into one contiguous buffer, so
   * zeroing the gradients is one memset,
   * parameters that did not take part in the step contribute zeros (what find_unused_parameters achieves),
-  * the gradient exchange is a single 191 MB (DINO-4scale) sum-all-reduce over NVLink followed by a scale by
-    1/world_size -- DDP's averaging semantics,
+  * the gradient exchange is a 191 MB (DINO-4scale) sum-all-reduce over NVLink with DDP's averaging semantics (the
+    1/world_size rides in the clipping pass); the transformer / head part of the buffer is reduced from a backward hook
+    while the ResNet backward is still running (reduce_early), the backbone part right after the backward,
   * gradient clipping (engine.py:110, max_norm 0.1) is one norm + one scale over the flat buffer.
 Works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests).
 
@@ -25,9 +26,18 @@ import torch.distributed as dist
 
 
 class FlatGradients:
-    def __init__(self, model: torch.nn.Module, process_group=None, gather: bool = False):
+    def __init__(self, model: torch.nn.Module, process_group=None, gather: bool = False, late=None):
+        """`late(name) -> bool` marks the parameters whose gradients are produced LAST by the backward pass (the backbone in
+        DINO: it runs first in the forward).  They are laid out at the end of the buffer, so `reduce_early()` -- called
+        from a backward hook once every other gradient is final -- can start the all-reduce of the first part while the
+        backward of the late part is still running (gradient exchange overlapped with compute)."""
         self.gather, self._pending = gather, False
-        self.params = [p for p in model.parameters() if p.requires_grad]
+        named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+        if late is not None:
+            named = [(n, p) for n, p in named if not late(n)] + [(n, p) for n, p in named if late(n)]
+        self.params = [p for _, p in named]
+        self.split = sum(p.numel() for n, p in named if late is None or not late(n))     # first element of the late part
+        self._early_handle = None
         assert self.params, "model has no trainable parameters"
         dev, dt = self.params[0].device, self.params[0].dtype
         assert all(p.device == dev and p.dtype == dt for p in self.params)
@@ -76,19 +86,45 @@ class FlatGradients:
         return all(p.grad is not None and base <= p.grad.data_ptr() < base + self.numel * self.flat.element_size()
                    for p in self.params)
 
+    def reduce_early(self):
+        """Start the sum-all-reduce of the early part of the buffer (asynchronously: the collective is ordered after the
+        work already enqueued on the current stream and runs beside what is enqueued next).  Call it from a backward hook
+        once the gradients of every non-late parameter are final; all_reduce() finishes the job.  No-op on one rank, in
+        gather mode, without a late part, or if it already ran in this step."""
+        if self.world_size == 1 or self.gather or self._early_handle is not None or self.split in (0, self.numel):
+            return
+        self._early_handle = dist.all_reduce(self.flat[:self.split], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
     def all_reduce(self):
-        """Average the gradients over the ranks: one collective on the flat buffer."""
+        """Sum the gradients over the ranks: one collective on the flat buffer, or -- after reduce_early() -- one on the
+        late part plus the wait for the early one.  The division by the world size (DDP's averaging) rides in clip_()'s
+        single scaling pass; call average_() instead if the step does not clip."""
         self.collect()
         ws = self.world_size
+        self._unscaled = ws > 1
         if ws > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.mul_(1.0 / ws)
+            if self._early_handle is not None:
+                dist.all_reduce(self.flat[self.split:], op=dist.ReduceOp.SUM, group=self.group)
+                self._early_handle.wait()
+                self._early_handle = None
+            else:
+                dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+
+    def average_(self):
+        """Apply the pending 1 / world_size of all_reduce() (a no-op after clip_(), which folds it into its own pass)."""
+        if getattr(self, "_unscaled", False):
+            self.flat.mul_(1.0 / self.world_size)
+            self._unscaled = False
 
     def clip_(self, max_norm: float):
-        """torch.nn.utils.clip_grad_norm_ on the flat buffer; returns the total norm (0-dim tensor, no host sync)."""
+        """torch.nn.utils.clip_grad_norm_ on the flat buffer; returns the total norm of the averaged gradient (0-dim
+        tensor, no host sync).  One norm + one scaling pass, which also applies the 1 / world_size left pending by
+        all_reduce()."""
         self.collect()
-        norm = torch.linalg.vector_norm(self.flat)
-        self.flat.mul_(torch.clamp(max_norm / (norm + 1e-6), max=1.0))
+        inv = 1.0 / self.world_size if getattr(self, "_unscaled", False) else 1.0
+        self._unscaled = False
+        norm = torch.linalg.vector_norm(self.flat) * inv
+        self.flat.mul_(torch.clamp(max_norm / (norm + 1e-6), max=1.0) * inv)
         return norm
 
 

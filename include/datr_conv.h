@@ -4,14 +4,19 @@
  *   datr_conv3x3_nhwc_tf32  <-  conv2 (3x3, padding 1, stride 1 or 2, no bias) of the ResNet-50 bottlenecks the
  *                               reference's backbone runs through cuDNN (models/dino/backbone.py:97 ->
  *                               torchvision.models.resnet Bottleneck.conv2), followed by FrozenBatchNorm2d
- *                               (backbone.py:62-72; folded into `w` and `bias` by the caller) and ReLU.
+ *                               (backbone.py:62-72; folded into `w` and `bias` by the caller) and ReLU;
+ *                               the 3x3 convolutions + LeakyReLU(0.2) of the image-level domain discriminator
+ *                               (models/dino/DA_utils.py:50-79, FCDiscriminator_img); and, on rotated / transposed
+ *                               weights, the input gradient (dgrad) of any stride-1 3x3 convolution.
  *
  *   y[n, oy, ox, co] = act( bias[co] + sum_{ky,kx,ci} x[n, s*oy + ky - 1, s*ox + kx - 1, ci] * w[co, ky, kx, ci] )
  *
  * x [N,H,W,Cin], w [Cout,3,3,Cin], y [N,Ho,Wo,Cout] (Ho = (H-1)/s + 1, Wo likewise): fp32, contiguous (NHWC /
  * channels_last), 16-byte aligned, caller-owned device memory; bias [Cout] may be NULL; Cin % 32 == 0, Cout % 4 == 0.
+ * `relu`: 0 = identity, 1 = ReLU, 2 = LeakyReLU(0.2).
  * TF32 products, fp32 accumulation.  Work is enqueued on `stream`; returns 0 or a negative code.
- * Forward only: the gradients of this layer are taken with the library convolution-backward routines.
+ * The weight gradient of these layers (and the input gradient of the stride-2 ones) is taken with the library
+ * convolution-backward routines.
  */
 #ifndef DATR_CONV_H_
 #define DATR_CONV_H_

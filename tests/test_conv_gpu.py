@@ -35,6 +35,7 @@ def test_forward_backward(N, Cin, Cout, H, W, stride):
     n0 = native.conv_launch_count()
     y = conv3x3_bias_relu(xa, wa, ba, stride)
     assert native.conv_launch_count() == n0 + 1
+    own_dgrad = stride == 1 and Cout % 32 == 0
     assert y.is_contiguous(memory_format=torch.channels_last) or y.numel() == y.shape[1]
     xd, wd, bd = (t.double().clone().requires_grad_(True) for t in (x, w, b))
     z = F.conv2d(xd, wd, bd, stride=stride, padding=1)
@@ -42,7 +43,65 @@ def test_forward_backward(N, Cin, Cout, H, W, stride):
     assert rel(y.detach(), z.detach().clamp_min(0)) < REL
     gy = torch.randn(y.shape, generator=g).cuda()
     y.backward(gy)
+    assert native.conv_launch_count() == n0 + 1 + int(own_dgrad)      # stride-1 input gradient = the forward kernel again
     (z * (y.detach() > 0)).backward(gy.double())        # same active set as the kernel's output
     torch.backends.cudnn.allow_tf32 = False
     for got, want in ((xa.grad, xd.grad), (wa.grad, wd.grad), (ba.grad, bd.grad)):
         assert rel(got, want) < 5e-3
+
+
+@pytest.mark.parametrize("act", [0, 2], ids=["identity", "leaky_relu"])
+@pytest.mark.parametrize("N,Cin,Cout,H,W", [(2, 256, 256, 25, 42), (2, 256, 128, 13, 21), (1, 128, 128, 50, 84)])
+def test_discriminator_layers_leaky_relu_and_own_dgrad(N, Cin, Cout, H, W, act):
+    """The layers of the image-level domain discriminator (DA_utils.py:50-79): conv + bias + LeakyReLU(0.2), input
+    gradient on the same kernel (rotated filter), weight gradient from the library; everything against fp64 torch."""
+    from datr_b200 import native
+    from datr_b200.conv import conv3x3_bias_act
+    g = torch.Generator(device="cpu").manual_seed(Cin + Cout + H + act)
+    x = torch.randn(N, Cin, H, W, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) / (3 * Cin ** 0.5)).cuda().contiguous(memory_format=torch.channels_last)
+    b = torch.randn(Cout, generator=g).cuda()
+    xa, wa, ba = (t.clone().requires_grad_(True) for t in (x, w, b))
+    n0 = native.conv_launch_count()
+    y = conv3x3_bias_act(xa, wa, ba, 1, act)
+    xd, wd, bd = (t.double().clone().requires_grad_(True) for t in (x, w, b))
+    z = F.conv2d(xd, wd, bd, padding=1)
+    zd = F.leaky_relu(z, 0.2) if act == 2 else z
+    assert rel(y.detach(), zd.detach()) < REL
+    gy = torch.randn(y.shape, generator=g).cuda()
+    y.backward(gy)
+    assert native.conv_launch_count() == n0 + 2
+    if act == 2:       # same sign pattern as the kernel's output
+        (z * torch.where(y.detach() > 0, 1.0, 0.2).double()).backward(gy.double())
+    else:
+        zd.backward(gy.double())
+    for got, want in ((xa.grad, xd.grad), (wa.grad, wd.grad), (ba.grad, bd.grad)):
+        assert rel(got, want) < 5e-3
+
+
+def test_image_discriminator_module_uses_the_kernel_and_matches_fp64():
+    from datr_b200 import linear as dl, native
+    from datr_b200.models.dino.DA_utils import FCDiscriminator_img
+    torch.manual_seed(0)
+    m = FCDiscriminator_img(256).cuda().to(memory_format=torch.channels_last)
+    x = torch.randn(2, 256, 25, 42, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    ref = FCDiscriminator_img(256).double().cuda()
+    ref.load_state_dict({k: v.double() for k, v in m.state_dict().items()})
+    xd = x.detach().double().requires_grad_(True)
+    want = ref(xd)
+    want.sum().backward()
+    dl.set_mode("tf32")
+    try:
+        n0 = native.conv_launch_count()
+        got = m(x)
+        got.sum().backward()
+        assert native.conv_launch_count() == n0 + 6        # 3 forward + 3 input-gradient launches
+    finally:
+        dl.set_mode("fp32")
+    # four chained TF32 layers: a LeakyReLU input within rounding distance of zero takes slope 0.2 in one run and 1 in
+    # the other, so single gradient elements can differ by percents; the bar is on the relative L2 error
+    l2 = lambda a, b: float((a.double() - b).norm() / b.norm())
+    assert rel(got.detach(), want.detach()) < 5e-3
+    assert l2(x.grad, xd.grad) < 1e-2
+    for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        assert l2(p.grad, q.grad) < 1e-2, k

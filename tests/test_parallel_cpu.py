@@ -90,3 +90,61 @@ def test_single_process_modes_agree():
         grads.all_reduce()
         res.append(grads.flat.clone())
     assert torch.allclose(res[0], res[1], rtol=1e-6, atol=1e-8)
+
+
+class TwoStage(torch.nn.Module):
+    """`stem` runs first in the forward, so its gradients arrive last (the role of DINO's backbone)."""
+
+    def __init__(self):
+        super().__init__()
+        self.head = torch.nn.Linear(16, 4)
+        self.stem = torch.nn.Linear(8, 16)
+        self.fired = 0
+
+    def forward(self, x, on_features_grad=None):
+        f = torch.relu(self.stem(x))
+        if on_features_grad is not None:
+            f.register_hook(lambda g: (on_features_grad(), None)[1])       # every head gradient is final when this fires
+        return self.head(f).sum()
+
+
+def overlap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = TwoStage()
+        grads = FlatGradients(net, late=lambda n: n.startswith("stem"))
+        assert grads.split == sum(p.numel() for p in net.head.parameters())
+        x = torch.randn(5, 8, generator=torch.Generator().manual_seed(42 + rank))
+        for step in range(2):
+            grads.zero()
+            net(x, on_features_grad=grads.reduce_early).backward()
+            assert grads._early_handle is not None                           # the hook started the first collective
+            grads.all_reduce()
+            norm = grads.clip_(0.1)
+        out[rank] = ({n: p.grad.clone() for n, p in net.named_parameters()}, float(norm))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_early_reduce_from_a_backward_hook_gives_the_same_averaged_clipped_gradients():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = mp.Manager().dict()
+    mp.spawn(overlap_worker, args=(2, port, out), nprocs=2, join=True)
+    local = []
+    for rank in (0, 1):
+        torch.manual_seed(0)
+        net = TwoStage()
+        net(torch.randn(5, 8, generator=torch.Generator().manual_seed(42 + rank))).backward()
+        local.append({n: p.grad.clone() for n, p in net.named_parameters()})
+    want = {n: (local[0][n] + local[1][n]) / 2 for n in local[0]}
+    total = torch.sqrt(sum((g ** 2).sum() for g in want.values()))
+    scale = min(1.0, 0.1 / (float(total) + 1e-6))
+    for rank in (0, 1):
+        got, norm = out[rank]
+        assert abs(norm - float(total)) < 1e-5 * max(1.0, float(total))
+        for n in want:
+            assert torch.allclose(got[n], want[n] * scale, rtol=1e-5, atol=1e-7), n

@@ -308,7 +308,8 @@ def main():
             ours[mode] = r
             compare(f"ours_{mode}_vs_reference_fp32", r, ref_runs["fp32"], report)
         if mode == "tf32" and not a.skip_timing:
-            wl.grads = __import__("datr_b200.parallel", fromlist=["FlatGradients"]).FlatGradients(wl.model)
+            wl.grads = __import__("datr_b200.parallel", fromlist=["FlatGradients"]).FlatGradients(wl.model, late=lambda n: n.startswith("backbone"))
+            wl.model._on_backbone_output_grad = wl.grads.reduce_early
             wl.opt = torch.optim.AdamW(__import__("datr_b200.parallel", fromlist=["param_groups"]).param_groups(wl.model, 1e-4, 1e-5),
                                        lr=1e-4, weight_decay=1e-4, fused=True)
             wl.images.copy_(images)
