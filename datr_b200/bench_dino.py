@@ -141,7 +141,7 @@ class DinoStep:
         return {"loss": float(self.last_loss.detach()) if self.last_loss is not None else None,
                 "grad_allreduce_bytes": self.grads.numel * 4,
                 "cuda_graphs": None if self.graphs is None else {"segments": self.graphs.captures,
-                                                                 "what": "ResNet body, encoder x2, two-stage selection x2, decoder x2, heads, image discriminator, criterion losses (forward + backward each)"}}
+                                                                 "what": "ResNet body, input projections, flatten, encoder (source + target halves in one call), two-stage selection x2, decoder x2, heads, image discriminator, criterion losses (forward + backward each)"}}
 
 
 WORKLOAD_5SCALE = ("DINO-5scale ResNet-50 DA training step (forward + losses + backward + gradient all-reduce + clip + AdamW), "

@@ -457,6 +457,13 @@ class DeformableTransformer(nn.Module):
         refpoint_embed [N,n_dn,4] / tgt [N,n_dn,C]: de-noising queries (None at inference).
         Returns (hs: list of [N,nq,C] per decoder layer, references: list of [N,nq,4] (layers + 1),
         hs_enc [1,N,nq,C] | None, ref_enc [1,N,nq,4] | None, init_box_proposal [N,nq,4])."""
+        return self.decode(self.encode(srcs, masks, pos_embeds), refpoint_embed, tgt, attn_mask)
+
+    def encode(self, srcs, masks, pos_embeds):
+        """Level flattening + the deformable encoder (reference forward :267-316).  Every operation of this half works on
+        one image at a time (token-wise GEMMs / LayerNorm, per-image MSDeformAttn), so DINO.forward runs it ONCE on the
+        source and target halves of a domain-adaptation batch together and hands each half to decode(): half the kernel
+        launches of two separate passes, twice the rows per GEMM, one gradient arrival per encoder parameter."""
         shapes_list = [tuple(s.shape[-2:]) for s in srcs]
         if graphs.ACTIVE is not None and srcs[0].is_cuda:
             owner = self.__dict__.get("_level_embed_owner")
@@ -469,7 +476,6 @@ class DeformableTransformer(nn.Module):
                 "flatten", owner, self._flatten_levels, tuple(srcs), tuple(masks), tuple(pos_embeds))
         else:
             src_flat, pos_flat, mask_flat, valid_ratios = self._flatten_levels(tuple(srcs), tuple(masks), tuple(pos_embeds))
-        bs = src_flat.shape[0]
         spatial_shapes, level_start_index = self._shape_tensors(shapes_list, src_flat.device)
 
         if graphs.ACTIVE is not None and src_flat.is_cuda:
@@ -479,7 +485,19 @@ class DeformableTransformer(nn.Module):
             memory, _, _ = self.encoder(src_flat, pos=pos_flat, level_start_index=level_start_index,
                                         spatial_shapes=spatial_shapes, valid_ratios=valid_ratios,
                                         key_padding_mask=mask_flat, shapes_list=shapes_list)
+        return memory, pos_flat, mask_flat, valid_ratios, spatial_shapes, level_start_index, shapes_list
 
+    @staticmethod
+    def split_encoded(enc, sizes):
+        """Cut the batch axis of encode()'s result into consecutive parts of `sizes` images (torch.split: the backward
+        of all parts is ONE concatenation into the encoder's output gradient)."""
+        memory, pos_flat, mask_flat, valid_ratios, spatial_shapes, level_start_index, shapes_list = enc
+        parts = zip(memory.split(sizes), pos_flat.split(sizes), mask_flat.split(sizes), valid_ratios.split(sizes))
+        return [(m, p, k, v, spatial_shapes, level_start_index, shapes_list) for m, p, k, v in parts]
+
+    def decode(self, enc, refpoint_embed, tgt, attn_mask=None):
+        """Two-stage query selection + decoder on an encode() result (reference forward :318-431)."""
+        memory, pos_flat, mask_flat, valid_ratios, spatial_shapes, level_start_index, shapes_list = enc
         if graphs.ACTIVE is not None and memory.is_cuda:
             owners = self.__dict__.setdefault("_two_stage_owner", nn.ModuleList(
                 [m for m in (getattr(self, "enc_output", None), getattr(self, "enc_output_norm", None),

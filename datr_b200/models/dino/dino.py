@@ -34,6 +34,8 @@ from .dn_components import dn_post_process, prepare_for_cdn
 from .matcher import BatchedMatch, batchable, build_matcher, match_many, matching_sets, prefetch, take_prefetched
 from .utils import MLP, sigmoid_focal_loss
 
+_JOINT_ENCODER = os.environ.get("DATR_JOINT_ENCODER", "1") != "0"
+
 
 class DINO(nn.Module):
     """Backbone -> input projections -> (CDN queries) -> deformable transformer -> class / box heads,
@@ -197,9 +199,13 @@ class DINO(nn.Module):
             n, cin, h, w = x.shape
             if conv.kernel_size == (1, 1) and conv.stride == (1, 1) and cin % 32 == 0:
                 y = dl.linear(x.permute(0, 2, 3, 1).reshape(-1, cin), conv.weight.reshape(conv.out_channels, cin), conv.bias)
-                return norm(y.view(n, h, w, conv.out_channels).permute(0, 3, 1, 2))
+                y = norm(y.view(n, h, w, conv.out_channels).permute(0, 3, 1, 2))
+                # ATen's CUDA GroupNorm hands back an NCHW-contiguous tensor: return to NHWC once, here, so that the
+                # discriminator convolutions and the token flattening downstream work on views
+                return y.contiguous(memory_format=torch.channels_last)
             if dconv.eligible(x, conv):
-                return norm(dconv.conv3x3_bias_act(x, conv.weight, conv.bias, conv.stride[0], 0))
+                y = norm(dconv.conv3x3_bias_act(x, conv.weight, conv.bias, conv.stride[0], 0))
+                return y.contiguous(memory_format=torch.channels_last)
         return proj(x)
 
     def _project_levels(self, features, poss, full_mask):
@@ -293,10 +299,19 @@ class DINO(nn.Module):
             dn_bbox = dn_label = attn_mask = dn_meta = None
 
         srcs, masks, poss = self._features(samples)
+        enc_t = None
         if self.training:
             srcs, masks, poss, srcs_all, masks_all, poss_all, srcs_t, masks_t, poss_t = decompose_features(srcs, masks, poss)
-
-        hs, reference, hs_enc, ref_enc, init_box_proposal = self.transformer(srcs, masks, dn_bbox, poss, dn_label, attn_mask)
+            # The reference runs the transformer on the source half here (:291) and on the target half below (:380-382).
+            # Its encoder treats every image independently, so both halves go through it in ONE call (DATR_JOINT_ENCODER=0
+            # keeps two calls); the query selection and the decoder then run per half as in the reference.
+            if _JOINT_ENCODER:
+                half = srcs[0].shape[0]
+                enc_s, enc_t = self.transformer.split_encoded(self.transformer.encode(srcs_all, masks_all, poss_all),
+                                                              [half, srcs_all[0].shape[0] - half])
+                hs, reference, hs_enc, ref_enc, init_box_proposal = self.transformer.decode(enc_s, dn_bbox, dn_label, attn_mask)
+        if enc_t is None:
+            hs, reference, hs_enc, ref_enc, init_box_proposal = self.transformer(srcs, masks, dn_bbox, poss, dn_label, attn_mask)
         # keeps label_enc in the autograd graph when there are no objects.  (Eager on purpose: label_enc already feeds
         # the eager de-noising query construction, and a parameter must not be shared between a live eager graph and a
         # segment being captured.)
@@ -324,7 +339,10 @@ class DINO(nn.Module):
         pad = dn_meta["pad_size"] if dn_meta is not None else 0
         proto_s, present_s = self._prototypes(hs[-1][:, pad:, :], out["pred_logits"])
 
-        hs_t, reference_t, hs_enc_t, ref_enc_t, init_box_proposal_t = self.transformer(srcs_t, masks_t, None, poss_t, None, None)
+        if enc_t is not None:
+            hs_t, reference_t, hs_enc_t, ref_enc_t, init_box_proposal_t = self.transformer.decode(enc_t, None, None, None)
+        else:
+            hs_t, reference_t, hs_enc_t, ref_enc_t, init_box_proposal_t = self.transformer(srcs_t, masks_t, None, poss_t, None, None)
         proto_t, present_t = self._prototypes(hs_t[-1], self.class_embed[-1](hs_t[-1]))
 
         da["proto_DA"] = {"da_protos": self.Proto_D(grad_reverse(torch.cat([proto_s, proto_t], dim=0))),

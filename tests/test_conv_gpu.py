@@ -98,10 +98,14 @@ def test_image_discriminator_module_uses_the_kernel_and_matches_fp64():
         assert native.conv_launch_count() == n0 + 6        # 3 forward + 3 input-gradient launches
     finally:
         dl.set_mode("fp32")
-    # four chained TF32 layers: a LeakyReLU input within rounding distance of zero takes slope 0.2 in one run and 1 in
-    # the other, so single gradient elements can differ by percents; the bar is on the relative L2 error
+    # Gradients of four chained layers against an fp64 run of the reference module: a LeakyReLU input within TF32
+    # rounding distance of zero (~1 unit in 1000 per layer) takes slope 0.2 in one run and 1 in the other, a 5x change of
+    # that unit's contribution, i.e. sqrt(1e-3) ~ 3 % relative L2 error with identical arithmetic everywhere else (the
+    # per-layer tests above pin the arithmetic at 5e-3 with the mask taken from the kernel's own output).  The bar here is
+    # therefore direction (cosine) and a 5 % L2 band.
     l2 = lambda a, b: float((a.double() - b).norm() / b.norm())
+    cos = lambda a, b: float((a.double() * b).sum() / (a.double().norm() * b.norm()))
     assert rel(got.detach(), want.detach()) < 5e-3
-    assert l2(x.grad, xd.grad) < 1e-2
+    assert l2(x.grad, xd.grad) < 5e-2 and cos(x.grad, xd.grad) > 0.998
     for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
-        assert l2(p.grad, q.grad) < 1e-2, k
+        assert l2(p.grad, q.grad) < 5e-2 and cos(p.grad, q.grad) > 0.998, k
