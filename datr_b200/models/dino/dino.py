@@ -35,6 +35,7 @@ from .matcher import BatchedMatch, batchable, build_matcher, match_many, matchin
 from .utils import MLP, sigmoid_focal_loss
 
 _JOINT_ENCODER = os.environ.get("DATR_JOINT_ENCODER", "1") != "0"
+_JOINT_DECODER = os.environ.get("DATR_JOINT_DECODER", "1") != "0"
 
 
 class DINO(nn.Module):
@@ -299,7 +300,7 @@ class DINO(nn.Module):
             dn_bbox = dn_label = attn_mask = dn_meta = None
 
         srcs, masks, poss = self._features(samples)
-        enc_t = None
+        enc_t = joint_t = None
         if self.training:
             srcs, masks, poss, srcs_all, masks_all, poss_all, srcs_t, masks_t, poss_t = decompose_features(srcs, masks, poss)
             # The reference runs the transformer on the source half here (:291) and on the target half below (:380-382).
@@ -307,9 +308,31 @@ class DINO(nn.Module):
             # keeps two calls); the query selection and the decoder then run per half as in the reference.
             if _JOINT_ENCODER:
                 half = srcs[0].shape[0]
-                enc_s, enc_t = self.transformer.split_encoded(self.transformer.encode(srcs_all, masks_all, poss_all),
-                                                              [half, srcs_all[0].shape[0] - half])
-                hs, reference, hs_enc, ref_enc, init_box_proposal = self.transformer.decode(enc_s, dn_bbox, dn_label, attn_mask)
+                enc_all = self.transformer.encode(srcs_all, masks_all, poss_all)
+                if _JOINT_DECODER and srcs_all[0].shape[0] == 2 * half:
+                    # Query selection and decoder of both halves in ONE call as well.  The target half gets all-zero
+                    # de-noising queries in the slots the source half fills: the de-noising attention mask
+                    # (dn_components.py:105-121) hides those slots from the matching queries, and everything else in the
+                    # decoder acts on one query at a time, so the matching queries of the target half come out exactly as
+                    # from a separate pass without de-noising queries; the dummy slots are dropped below.  The decoder is
+                    # bound by kernel count, not by arithmetic: one call costs little more than each of the two did.
+                    dn_b = dn_l = None
+                    if dn_bbox is not None:
+                        dn_b = torch.cat([dn_bbox, torch.zeros_like(dn_bbox)], 0)
+                        dn_l = torch.cat([dn_label, torch.zeros_like(dn_label)], 0)
+                    hs_a, ref_a, hs_enc_a, ref_enc_a, ibp_a = self.transformer.decode(enc_all, dn_b, dn_l, attn_mask)
+                    npad = dn_bbox.shape[1] if dn_bbox is not None else 0
+                    hs, reference = [h[:half] for h in hs_a], [r[:half] for r in ref_a]
+                    hs_enc = hs_enc_a[:, :half] if hs_enc_a is not None else None
+                    ref_enc = ref_enc_a[:, :half] if ref_enc_a is not None else None
+                    init_box_proposal = ibp_a[:half]
+                    joint_t = ([h[half:, npad:] for h in hs_a], [r[half:, npad:] for r in ref_a],
+                               hs_enc_a[:, half:] if hs_enc_a is not None else None,
+                               ref_enc_a[:, half:] if ref_enc_a is not None else None, ibp_a[half:])
+                    enc_t = enc_all
+                else:
+                    enc_s, enc_t = self.transformer.split_encoded(enc_all, [half, srcs_all[0].shape[0] - half])
+                    hs, reference, hs_enc, ref_enc, init_box_proposal = self.transformer.decode(enc_s, dn_bbox, dn_label, attn_mask)
         if enc_t is None:
             hs, reference, hs_enc, ref_enc, init_box_proposal = self.transformer(srcs, masks, dn_bbox, poss, dn_label, attn_mask)
         # keeps label_enc in the autograd graph when there are no objects.  (Eager on purpose: label_enc already feeds
@@ -339,7 +362,9 @@ class DINO(nn.Module):
         pad = dn_meta["pad_size"] if dn_meta is not None else 0
         proto_s, present_s = self._prototypes(hs[-1][:, pad:, :], out["pred_logits"])
 
-        if enc_t is not None:
+        if joint_t is not None:
+            hs_t, reference_t, hs_enc_t, ref_enc_t, init_box_proposal_t = joint_t
+        elif enc_t is not None:
             hs_t, reference_t, hs_enc_t, ref_enc_t, init_box_proposal_t = self.transformer.decode(enc_t, None, None, None)
         else:
             hs_t, reference_t, hs_enc_t, ref_enc_t, init_box_proposal_t = self.transformer(srcs_t, masks_t, None, poss_t, None, None)
