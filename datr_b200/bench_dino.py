@@ -198,11 +198,9 @@ class TeacherStep(DinoStep):
         samples = NestedTensor(images, mask)
         # 1. teacher on the (weakly augmented) target images                               engine.py:196-204
         unlabel = st.get_unlabel_img(samples)
-        active, graphs.ACTIVE = graphs.ACTIVE, None                       # inference pass: eager
-        with torch.no_grad():
+        with torch.no_grad():                                             # forward-only graph segments (graphs.py)
             pred = self.teacher.ema(unlabel)
             results = self.post(pred, self.unit_sizes, not_to_xyxy=True)                   # :205-207
-        graphs.ACTIVE = active
         # 2. pseudo labels                                                                  :210-216
         idx_list, labels_d, boxes_d, scores_d = st.get_pseudo_label_via_threshold(results, threshold=self.threshold)
         pseudo = st.deal_pesudo_label(self.target_labels, idx_list, labels_d, boxes_d, scores_d)

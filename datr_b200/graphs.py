@@ -41,6 +41,7 @@ class StepGraphs:
         self.captures = 0
         self.per_segment = {}                  # (name, index) -> number of signatures captured so far
         self.max_signatures = 4                # beyond that a segment runs eagerly for unseen signatures
+        self.capture_inference = True          # no-grad passes get forward-only graphs (False: they run eagerly)
         import os
         self.skip = set(filter(None, os.environ.get("DATR_GRAPH_SKIP", "").split(",")))   # segment names kept eager
 
@@ -54,34 +55,72 @@ class StepGraphs:
             return fn(*args)
         return _call_segment(self, name, owner, fn, args)
 
-    def run(self, name, make_module, args, key_extra=(), want_module=False):
-        """Run segment `name` on tensor arguments `args` through its graph (capturing it on first use)."""
+    def run(self, name, make_module, args, key_extra=(), want_module=False, owner=None):
+        """Run segment `name` on tensor arguments `args` through its graph (capturing it on first use).  `owner`
+        (optional) is the module the segment belongs to: two models that run the same segment on the same shapes (student
+        and EMA teacher) get separate graphs."""
         idx = self.calls.get(name, 0)
         self.calls[name] = idx + 1
-        key = (name, idx, torch.is_grad_enabled(), key_extra) + tuple((tuple(a.shape), a.dtype, a.requires_grad) for a in args)
+        grad = torch.is_grad_enabled()
+        key = (name, idx, grad, id(owner) if owner is not None else None, key_extra) + \
+            tuple((tuple(a.shape), a.dtype, a.requires_grad) for a in args)
         entry = self.cache.get(key)
         if entry is None:
-            # inference passes stay eager; so does a segment whose signature keeps changing (e.g. the criterion with
-            # real data: its index tensors are sized by the number of boxes in the batch) -- capturing costs far more
-            # than one eager pass and every capture keeps its private memory pool
-            if not torch.is_grad_enabled() or self.per_segment.get((name, idx), 0) >= self.max_signatures:
+            # a segment whose signature keeps changing (e.g. the criterion with real data: its index tensors are sized by
+            # the number of boxes in the batch) stays eager: capturing costs far more than one eager pass and every
+            # capture keeps its private memory pool
+            if self.per_segment.get((name, idx), 0) >= self.max_signatures or (not grad and not self.capture_inference):
                 module = make_module()
                 out = module(*args)
                 return (out, module) if want_module else out
             self.per_segment[(name, idx)] = self.per_segment.get((name, idx), 0) + 1
             module = make_module()
-            sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
             n0 = _native_launches()
-            graphed = torch.cuda.make_graphed_callables(module, sample, num_warmup_iters=self.warmup_iters,
-                                                        allow_unused_input=True)
-            # warm-up iterations + one capture each ran forward and backward eagerly/under capture once
-            per_pair = (_native_launches() - n0) // (self.warmup_iters + 1)
+            if grad:
+                sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
+                graphed = torch.cuda.make_graphed_callables(module, sample, num_warmup_iters=self.warmup_iters,
+                                                            allow_unused_input=True)
+                # warm-up iterations + one capture each ran forward and backward eagerly/under capture once
+                per_pair = (_native_launches() - n0) // (self.warmup_iters + 1)
+            else:
+                graphed = _InferenceGraph(module, args, self.warmup_iters)
+                per_pair = (_native_launches() - n0) // (self.warmup_iters + 1)
             entry = self.cache[key] = (graphed, per_pair)
             self.captures += 1
         graphed, per_pair = entry
         self.replayed_native_launches += per_pair
         out = graphed(*args)
         return (out, graphed) if want_module else out
+
+
+class _InferenceGraph:
+    """Forward-only CUDA graph of a segment (no-grad passes: the EMA teacher of the self-training step, evaluation).
+    Inputs are copied into static buffers, the captured forward is replayed, and the STATIC output tensors are returned:
+    they are valid until the next replay of the same segment, i.e. until the same point of the next step."""
+
+    def __init__(self, module, args, warmup_iters):
+        self.module = module
+        self.static_in = tuple(a.detach().clone() for a in args)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup_iters):
+                module(*self.static_in)
+        cur.wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad():
+            self.static_out = module(*self.static_in)
+
+    def __getattr__(self, name):            # FnSegment bookkeeping (out_spec, out_consts, out_n) lives on the module
+        return getattr(self.__dict__["module"], name)
+
+    def __call__(self, *args):
+        for s, a in zip(self.static_in, args):
+            if s.data_ptr() != a.data_ptr():
+                s.copy_(a)
+        self.graph.replay()
+        return self.static_out
 
 
 class FnSegment(nn.Module):
@@ -121,7 +160,7 @@ def _call_segment(sg: "StepGraphs", name, owner, fn, args):
         return holder["m"]
 
     key_extra = (repr(spec), repr(consts))
-    out_tensors, module = sg.run(name, make, tensors, key_extra=key_extra, want_module=True)
+    out_tensors, module = sg.run(name, make, tensors, key_extra=key_extra, want_module=True, owner=owner)
     if not isinstance(out_tensors, tuple):
         out_tensors = (out_tensors,)
     it = iter(out_tensors)

@@ -480,7 +480,8 @@ class DeformableTransformer(nn.Module):
 
         if graphs.ACTIVE is not None and src_flat.is_cuda:
             memory = graphs.ACTIVE.run("encoder", lambda: graphs.EncoderSegment(self.encoder, shapes_list),
-                                       (src_flat, pos_flat, spatial_shapes, level_start_index, valid_ratios, mask_flat))
+                                       (src_flat, pos_flat, spatial_shapes, level_start_index, valid_ratios, mask_flat),
+                                       owner=self.encoder)
         else:
             memory, _, _ = self.encoder(src_flat, pos=pos_flat, level_start_index=level_start_index,
                                         spatial_shapes=spatial_shapes, valid_ratios=valid_ratios,
@@ -513,7 +514,7 @@ class DeformableTransformer(nn.Module):
         if graphs.ACTIVE is not None and tgt.is_cuda:
             dec_args = (tgt, memory, mask_flat, pos_flat, refpoint_embed, level_start_index, spatial_shapes, valid_ratios)
             flat = graphs.ACTIVE.run("decoder", lambda: graphs.DecoderSegment(self.decoder, attn_mask is not None),
-                                     dec_args + ((attn_mask,) if attn_mask is not None else ()))
+                                     dec_args + ((attn_mask,) if attn_mask is not None else ()), owner=self.decoder)
             n_layers = len(self.decoder.layers)
             hs, references = list(flat[:n_layers]), list(flat[n_layers:])
         else:

@@ -154,7 +154,7 @@ class DINO(nn.Module):
         """Backbone + input projections (+ the extra stride-2 levels): per level (src, mask, pos)."""
         if graphs.ACTIVE is not None and samples.tensors.is_cuda:
             base = self.backbone[0]
-            feats = graphs.ACTIVE.run("body", lambda: graphs.BodySegment(base.body), (samples.tensors,))
+            feats = graphs.ACTIVE.run("body", lambda: graphs.BodySegment(base.body), (samples.tensors,), owner=base.body)
             self._watch_backbone_output_grads(feats)
             srcs, masks, poss = graphs.ACTIVE.call("project", self.input_proj, self._project, tuple(feats), samples.mask)
             return list(srcs), list(masks), list(poss)
