@@ -69,10 +69,19 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(a), "f"(b) : "memory");
 }
 
+// 3x3 convolution mode (on != 0): the reduction runs over output pixels, taken as patches of kPW x kPH = 32 pixels of one
+// image; `dz` is the output gradient [N, Ho, Wo, Cout], `x` the input [N, H, W, Cin], and dW is the channels_last weight
+// [Cout, 3, 3, Cin] seen as a [Cout, 9 * Cin] matrix: a BN-wide column tile lies inside ONE filter tap (Cin % BN == 0),
+// whose shifted input patch is fetched by a 4-D TMA box (zero fill = the convolution's padding, element stride = its
+// stride), exactly like the forward kernel's A operand (conv3x3_tf32.cu).
+struct ConvGeom { int on, Cin, stride, tiles_x, tiles_y; };
+constexpr int kPW = 16, kPH = 2;
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tma_dz, const __grid_constant__ CUtensorMap tma_x,
-                  float* __restrict__ dw, float* __restrict__ db, int M, int N, int K, int splits, int rows_per_split) {
+                  float* __restrict__ dw, float* __restrict__ db, int M, int N, int K, int splits, int rows_per_split,
+                  const ConvGeom cg) {
   using L = Smem<BN, STAGES>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -115,6 +124,19 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tma_dz, const __grid_const
           mbar_wait(empty + s, ((kb / STAGES) & 1) ^ 1);
           mbar_expect_tx(full + s, L::kStage);
           unsigned char* a = smem + s * L::kStage;
+          if (cg.on) {
+            const int pb = m / BK;                              // patch index: (image, patch row, patch column)
+            const int per_img = cg.tiles_x * cg.tiles_y;
+            const int img = pb / per_img, q = pb - img * per_img;
+            const int y0 = (q / cg.tiles_x) * kPH, x0 = (q % cg.tiles_x) * kPW;
+            const int tap = k0 / cg.Cin, ci0 = k0 - tap * cg.Cin;
+            const int ix = cg.stride * x0 + tap % 3 - 1, iy = cg.stride * y0 + tap / 3 - 1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_load_4d(a + c * kChunk, &tma_dz, n0 + 32 * c, x0, y0, img, full + s);
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) tma_load_4d(a + L::kA + c * kChunk, &tma_x, ci0 + 32 * c, ix, iy, img, full + s);
+            continue;
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) tma_load_2d(a + c * kChunk, &tma_dz, n0 + 32 * c, m, full + s);
 #pragma unroll
@@ -194,7 +216,8 @@ int make_map(CUtensorMap* map, const float* base, int rows, int cols) {
 }
 
 template <int BN, int STAGES>
-int launch(const CUtensorMap& mdz, const CUtensorMap& mx, float* dw, float* db, int M, int N, int K, cudaStream_t stream) {
+int launch(const CUtensorMap& mdz, const CUtensorMap& mx, float* dw, float* db, int M, int N, int K, cudaStream_t stream,
+           const ConvGeom& cg = ConvGeom{0, 0, 0, 0, 0}) {
   using L = Smem<BN, STAGES>;
   static std::atomic<uint64_t> opted{0};
   int dev = 0;
@@ -219,7 +242,7 @@ int launch(const CUtensorMap& mdz, const CUtensorMap& mx, float* dw, float* db, 
   int rows_per_split = ((M + splits - 1) / splits + BK - 1) / BK * BK;
   splits = (M + rows_per_split - 1) / rows_per_split;
   wgrad_tf32_kernel<BN, STAGES><<<unsigned(tiles * splits), kThreads, L::kTotal, stream>>>(mdz, mx, dw, db, M, N, K, splits,
-                                                                                          rows_per_split);
+                                                                                          rows_per_split, cg);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "wgrad_tf32_kernel launch: %s", cudaGetErrorString(e));
   g_wg_launches.fetch_add(1, std::memory_order_relaxed);
@@ -244,6 +267,53 @@ int datr_linear_wgrad_tf32(const float* dz, const float* x, float* dw, float* db
   if (int rc = make_map(&mdz, dz, M, N)) return rc;
   if (int rc = make_map(&mx, x, M, K)) return rc;
   return K > 128 ? launch<256, 4>(mdz, mx, dw, db, M, N, K, stream) : launch<128, 6>(mdz, mx, dw, db, M, N, K, stream);
+}
+
+// Weight (and bias) gradient of a 3x3 convolution, padding 1, stride 1 or 2, NHWC tensors:
+//   dw[co, ky, kx, ci] = sum_{n, oy, ox} gz[n, oy, ox, co] * x[n, s*oy + ky - 1, s*ox + kx - 1, ci],   db[co] = sum gz[..., co]
+// (the wgrad half of aten.convolution_backward for the ResNet bottleneck conv2 layers, reference backbone.py:97, the
+// image-level discriminator, DA_utils.py:50-79, and the extra input projection, dino.py:118-123).
+int datr_conv3x3_wgrad_nhwc_tf32(const float* gz, const float* x, float* dw, float* db, int N, int H, int W, int Cin,
+                                 int Cout, int stride, void* stream_) {
+  if (!gz || !x || !dw) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "null pointer argument%s");
+  if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "all dimensions must be positive%s");
+  if (stride != 1 && stride != 2) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "stride must be 1 or 2%s");
+  if (Cin % 128 != 0 || Cout % 4 != 0) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "Cin %% 128 == 0 and Cout %% 4 == 0 required%s");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(gz) || !al16(x) || !al16(dw)) return wfail(DATR_LINEAR_ERR_ALIGNMENT, "buffers must be 16-byte aligned%s");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  const int K = 9 * Cin;
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)Cout * K, stream);
+  if (e == cudaSuccess && db) e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)Cout, stream);
+  if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  ConvGeom cg;
+  cg.on = 1; cg.Cin = Cin; cg.stride = stride;
+  cg.tiles_x = (Wo + kPW - 1) / kPW; cg.tiles_y = (Ho + kPH - 1) / kPH;
+  const long long patches = (long long)N * cg.tiles_x * cg.tiles_y;
+  if (patches * BK > 0x7fffffffLL) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "problem too large%s");
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return wfail(DATR_LINEAR_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable%s");
+  CUtensorMap mdz, mx;
+  auto encode4 = [&](CUtensorMap* map, const float* base, int C, int w_, int h_, int st) -> int {
+    const cuuint64_t gdim[4] = {cuuint64_t(C), cuuint64_t(w_), cuuint64_t(h_), cuuint64_t(N)};
+    const cuuint64_t gstr[3] = {cuuint64_t(C) * 4, cuuint64_t(w_) * C * 4, cuuint64_t(h_) * w_ * C * 4};
+    const cuuint32_t box[4] = {32, cuuint32_t((kPW - 1) * st + 1), cuuint32_t((kPH - 1) * st + 1), 1};
+    const cuuint32_t estr[4] = {1, cuuint32_t(st), cuuint32_t(st), 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 4, const_cast<float*>(base), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      snprintf(g_wg_err, sizeof g_wg_err, "cuTensorMapEncodeTiled (4-D) failed (CUresult %d)", int(r));
+      return DATR_LINEAR_ERR_CUDA;
+    }
+    return DATR_LINEAR_OK;
+  };
+  if (int rc = encode4(&mdz, gz, Cout, Wo, Ho, 1)) return rc;
+  if (int rc = encode4(&mx, x, Cin, W, H, stride)) return rc;
+  // the kernel walks "rows" in units of BK: one patch of 32 pixels per k-block
+  const int M = int(patches) * BK;
+  return Cin % 256 == 0 ? launch<256, 4>(mdz, mx, dw, db, M, Cout, K, stream, cg) : launch<128, 6>(mdz, mx, dw, db, M, Cout, K, stream, cg);
 }
 
 const char* datr_linear_wgrad_last_error(void) { return g_wg_err; }

@@ -61,7 +61,7 @@ class FCDiscriminator_img(nn.Module):
         from datr_b200 import conv as dconv, linear as dl
         for conv in (self.conv1, self.conv2, self.conv3):
             if (dl.get_mode() == "tf32" and x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
-                    and dconv.eligible(x, conv)):
+                    and dconv.use_kernel(x, conv)):
                 # conv + bias + LeakyReLU(0.2) in one implicit-GEMM tcgen05 kernel; its input gradient runs on the
                 # same kernel (datr_b200.conv)
                 x = dconv.conv3x3_bias_act(x, conv.weight, conv.bias, 1, 2)

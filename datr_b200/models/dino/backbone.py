@@ -84,7 +84,7 @@ class Bottleneck(nn.Module):
             # NHWC activations: the three 1x1 convolutions are GEMMs over pixels; FrozenBN folds into weight / bias
             # and ReLU / the residual add ride in the tcgen05 kernel's epilogue (datr_b200.linear); 3x3 stays cuDNN
             y = _conv1x1_bn(x, self.conv1, self.bn1, relu=1)
-            if dconv.eligible(y, self.conv2):
+            if dconv.use_kernel(y, self.conv2):
                 # conv2 + FrozenBN + ReLU: im2col-free implicit GEMM (4-D TMA box per tap, datr_b200.conv)
                 scale, shift = self.bn2.scale_shift()
                 y = dconv.conv3x3_bias_relu(y, self.conv2.weight * scale.view(-1, 1, 1, 1), shift, self.conv2.stride[0])

@@ -204,7 +204,7 @@ class DINO(nn.Module):
                 # ATen's CUDA GroupNorm hands back an NCHW-contiguous tensor: return to NHWC once, here, so that the
                 # discriminator convolutions and the token flattening downstream work on views
                 return y.contiguous(memory_format=torch.channels_last)
-            if dconv.eligible(x, conv):
+            if dconv.use_kernel(x, conv):
                 y = norm(dconv.conv3x3_bias_act(x, conv.weight, conv.bias, conv.stride[0], 0))
                 return y.contiguous(memory_format=torch.channels_last)
         return proj(x)

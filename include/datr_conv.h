@@ -31,6 +31,18 @@ enum { DATR_CONV_OK = 0, DATR_CONV_ERR_BAD_ARGUMENT = -1, DATR_CONV_ERR_ALIGNMEN
 
 int datr_conv3x3_nhwc_tf32(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Cin,
                            int Cout, int stride, int relu, void* stream);
+/*
+ * Weight (and bias) gradient of the same convolution -- the wgrad half of aten::convolution_backward (cuDNN) behind the
+ * layers above:
+ *   dw[co, ky, kx, ci] = sum_{n, oy, ox} gz[n, oy, ox, co] * x[n, s*oy + ky - 1, s*ox + kx - 1, ci]     db[co] = sum gz[..., co]
+ * gz [N,Ho,Wo,Cout] (gradient of the pre-activation output), x [N,H,W,Cin], dw [Cout,3,3,Cin], db [Cout] or NULL; fp32,
+ * NHWC, 16-byte aligned; Cin % 128 == 0, Cout % 4 == 0.  Runs on the tensor-core weight-gradient kernel of
+ * datr_linear.h (csrc/wgrad_tf32.cu) with 4-D TMA boxes for the shifted input patches; dw / db are zero-filled by the
+ * library on `stream`, partial tiles are reduced with vector atomics.  Returns 0 or a negative DATR_CONV_* code;
+ * message: datr_linear_wgrad_last_error(); launches are counted by datr_linear_wgrad_launch_count().
+ */
+int datr_conv3x3_wgrad_nhwc_tf32(const float* gz, const float* x, float* dw, float* db, int N, int H, int W, int Cin,
+                                 int Cout, int stride, void* stream);
 const char* datr_conv_last_error(void);
 uint64_t datr_conv_launch_count(void);
 

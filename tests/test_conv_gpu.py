@@ -1,12 +1,22 @@
 """GPU parity of the implicit-GEMM 3x3 convolution (include/datr_conv.h) against torch's convolution in fp64 on the
-same NHWC inputs.  Bar: tensor-core (TF32) class, 2e-3 relative per tensor forward; gradients (cuDNN backward on the
-same operands, ReLU mask taken from the kernel's own output) 2e-3."""
+same NHWC inputs: forward, input gradient (the forward kernel on the rotated filter for stride 1), weight / bias
+gradient (tensor-core weight-gradient kernel with 4-D TMA patches for Cin % 128 == 0).  Bar: tensor-core (TF32) class,
+2e-3 relative per tensor forward, 5e-3 for the gradients (activation mask taken from the kernel's own output)."""
 import pytest
 import torch
 import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 REL = 2e-3
+
+
+@pytest.fixture(autouse=True)
+def own_kernels(monkeypatch):
+    """The step routes by measured speed (datr_b200/conv.py: own forward on large maps only, library backward); the
+    parity tests exercise the own kernels at every shape."""
+    from datr_b200 import conv
+    monkeypatch.setattr(conv, "OWN_BACKWARD", True)
+    monkeypatch.setattr(conv, "MIN_OUTPUT_PIXELS", 0)
 
 CASES = [  # N, Cin, Cout, H, W, stride
     (2, 64, 64, 50, 84, 1),
@@ -42,8 +52,10 @@ def test_forward_backward(N, Cin, Cout, H, W, stride):
     assert y.shape == z.shape
     assert rel(y.detach(), z.detach().clamp_min(0)) < REL
     gy = torch.randn(y.shape, generator=g).cuda()
+    w0 = native.wgrad_launch_count()
     y.backward(gy)
     assert native.conv_launch_count() == n0 + 1 + int(own_dgrad)      # stride-1 input gradient = the forward kernel again
+    assert native.wgrad_launch_count() == w0 + int(Cin % 128 == 0)    # weight gradient on the tensor-core wgrad kernel
     (z * (y.detach() > 0)).backward(gy.double())        # same active set as the kernel's output
     torch.backends.cudnn.allow_tf32 = False
     for got, want in ((xa.grad, xd.grad), (wa.grad, wd.grad), (ba.grad, bd.grad)):
@@ -109,3 +121,22 @@ def test_image_discriminator_module_uses_the_kernel_and_matches_fp64():
     assert l2(x.grad, xd.grad) < 5e-2 and cos(x.grad, xd.grad) > 0.998
     for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
         assert l2(p.grad, q.grad) < 5e-2 and cos(p.grad, q.grad) > 0.998, k
+
+
+def test_routing_by_measured_speed(monkeypatch):
+    """Default routing (profiles/r02n_bench_conv_backward.txt): own forward kernel for >= 40 000 output pixels, library
+    backward.  The ResNet layer2 conv2 of a 4-image 1333x800 batch takes the kernel, layer3 does not."""
+    from datr_b200 import conv, native
+    monkeypatch.setattr(conv, "OWN_BACKWARD", False)
+    monkeypatch.setattr(conv, "MIN_OUTPUT_PIXELS", 40000)
+    big = torch.zeros(4, 128, 100, 167, device="cuda").contiguous(memory_format=torch.channels_last)
+    small = torch.zeros(4, 256, 50, 84, device="cuda").contiguous(memory_format=torch.channels_last)
+    assert conv.use_kernel(big, torch.nn.Conv2d(128, 128, 3, padding=1, bias=False))
+    assert not conv.use_kernel(small, torch.nn.Conv2d(256, 256, 3, padding=1, bias=False))
+    assert not conv.use_kernel(big, torch.nn.Conv2d(128, 128, 3, padding=1, stride=2, bias=False))      # 16 700 output pixels
+    x = torch.randn(1, 128, 20, 30, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    w = torch.randn(128, 128, 3, 3, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    n0, w0 = native.conv_launch_count(), native.wgrad_launch_count()
+    conv.conv3x3_bias_act(x, w, None, 1, 1).sum().backward()
+    assert native.conv_launch_count() == n0 + 1 and native.wgrad_launch_count() == w0      # backward went to the library
+    assert x.grad is not None and w.grad is not None

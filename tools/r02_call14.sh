@@ -1,0 +1,4 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_conv_gpu.py tests/test_linear_gpu.py tests/test_model_gpu.py -q > gpurun_out/r02m_tests.txt 2>&1; echo "tests rc=$?"; tail -12 gpurun_out/r02m_tests.txt | cut -c1-220
+timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/r02m_bench_default.json 2> gpurun_out/r02m_bench_default.err; echo "bench rc=$?"; cut -c1-260 gpurun_out/r02m_bench_default.json; tail -2 gpurun_out/r02m_bench_default.err | cut -c1-300
