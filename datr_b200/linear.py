@@ -41,6 +41,20 @@ def get_mode() -> str:
     return _MODE
 
 
+class fp32_products:
+    """Context: library matmuls inside run with true fp32 products (cuBLAS SIMT), whatever the surrounding mode.  Used
+    for the class-logit heads whose outputs feed index work -- the two-stage top-k over all encoder tokens
+    (deformable_transformer.py:342) and the Hungarian cost matrix (matcher.py:47-95): given the same inputs these indices
+    are then bit-identical to an fp32 run; 91-wide layers are a rounding error of the step's FLOPs."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
 def eligible(x: torch.Tensor, weight: torch.Tensor) -> bool:
     N, K = weight.shape
     return (x.is_cuda and x.dtype == torch.float32 and weight.dtype == torch.float32 and K % 32 == 0 and N % 4 == 0

@@ -406,7 +406,8 @@ class DeformableTransformer(nn.Module):
             input_hw = self.two_stage_wh_embedding.weight[0] if self.two_stage_learn_wh else None
             output_memory, output_proposals = gen_encoder_output_proposals(memory, mask_flat, shapes_list, input_hw)
             output_memory = ln(self.enc_output_norm, dl.linear(output_memory, self.enc_output.weight, self.enc_output.bias))
-            class_all = self.enc_out_class_embed(output_memory)
+            with dl.fp32_products():    # feeds the top-k below: fp32 products, so equal inputs give equal indices
+                class_all = self.enc_out_class_embed(output_memory)
             topk = torch.topk(class_all.max(-1)[0], self.num_queries, dim=1)[1]               # [N,nq] int64
             tgt_undetach = torch.gather(output_memory, 1, topk.unsqueeze(-1).expand(-1, -1, self.d_model))
             prop_sel = torch.gather(output_proposals, 1, topk.unsqueeze(-1).expand(-1, -1, 4))

@@ -228,8 +228,10 @@ class DINO(nn.Module):
         """Per-decoder-layer class logits [n_layers, N, nq, classes] and the logits of the selected encoder proposals.
         (Kept outside the captured head segment: the 91-wide library GEMMs of these layers do not survive CUDA-graph
         capture of their backward on this stack; they are 7 small launches.)"""
-        classes = torch.stack([head(h) for head, h in zip(self.class_embed, hs)])
-        interm = self.transformer.enc_out_class_embed(hs_enc[-1]) if hs_enc is not None else None
+        from datr_b200 import linear as dl
+        with dl.fp32_products():        # these logits feed the Hungarian cost matrices: fp32 products
+            classes = torch.stack([head(h) for head, h in zip(self.class_embed, hs)])
+            interm = self.transformer.enc_out_class_embed(hs_enc[-1]) if hs_enc is not None else None
         return classes, interm
 
     def _boxes(self, hs, reference):
