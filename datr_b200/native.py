@@ -51,16 +51,30 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile libdatr_b200.so in-tree (cross-compiles without a GPU)."""
-    if force or _stale():
-        cmd = ["nvcc", *NVCC_FLAGS, f"-I{INCLUDE_DIR}", "-o", LIB_PATH, *SOURCES]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            raise NativeLibraryError("nvcc failed:\n" + res.stdout + res.stderr)
-        if verbose:
-            print(res.stderr)
+    """Compile libdatr_b200.so in-tree (cross-compiles without a GPU).  Safe under one-process-per-GPU launches: the
+    compile runs under an inter-process file lock, writes to a temporary file and renames it into place, so no rank can
+    load a half-written library and only the first rank to get the lock compiles."""
+    if not (force or _stale()):
+        return LIB_PATH
+    import fcntl
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if force or _stale():          # another process may have built it while we waited
+                tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+                cmd = ["nvcc", *NVCC_FLAGS, f"-I{INCLUDE_DIR}", "-o", tmp, *SOURCES]
+                if verbose:
+                    cmd.insert(1, "-Xptxas=-v")
+                res = subprocess.run(cmd, capture_output=True, text=True)
+                if res.returncode != 0:
+                    if os.path.exists(tmp):
+                        os.unlink(tmp)
+                    raise NativeLibraryError("nvcc failed:\n" + res.stdout + res.stderr)
+                os.replace(tmp, LIB_PATH)
+                if verbose:
+                    print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
