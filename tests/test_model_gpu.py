@@ -210,3 +210,67 @@ def test_channels_last_and_graph_replay_match_eager(small, cpu_noise):
     for k in want:
         den = max(float(want[k].abs().max()), 1e-6)
         assert float((got[k] - want[k]).abs().max()) / den < 5e-3, k
+
+
+@pytest.mark.parametrize("flag", [False, True], ids=["burn_in", "self_training"])
+def test_joint_encoder_decoder_passes_match_the_two_pass_structure(small, cpu_noise, flag, monkeypatch):
+    """DINO.forward runs the encoder and the decoder ONCE on the source + target halves (zero de-noising slots for the
+    target half, hidden by the de-noising attention mask); the reference runs the transformer twice (dino.py:291, :380-382).
+    Same outputs, losses and gradients up to fp32 summation order."""
+    from datr_b200.models.dino import dino as dmod
+    model, crit, _ = small
+    tg = mcase.targets(device="cuda")
+    images = [i.cuda() for i in mcase.images()]
+
+    def run(joint):
+        monkeypatch.setattr(dmod, "_JOINT_ENCODER", joint)
+        monkeypatch.setattr(dmod, "_JOINT_DECODER", joint)
+        model.train(); crit.train()
+        model.global_proto = None
+        torch.manual_seed(7)
+        out = model(images, tg, self_training_flag=flag)
+        losses = crit(out, tg)
+        total = mcase.total_loss(losses, crit.weight_dict)
+        model.zero_grad()
+        total.backward()
+        flat = {k: v.detach().clone() for k, v in mcase.flatten(out).items() if v.dtype.is_floating_point}
+        return flat, float(total), {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    out_j, loss_j, grad_j = run(True)
+    out_s, loss_s, grad_s = run(False)
+    assert set(out_j) == set(out_s) and set(grad_j) == set(grad_s)
+    assert abs(loss_j - loss_s) < 1e-5 * abs(loss_s)
+    for k in out_s:
+        a, b = out_j[k], out_s[k]
+        m = torch.isfinite(b)
+        assert torch.equal(torch.isfinite(a), m), k
+        assert float((a[m] - b[m]).abs().max()) <= 1e-4 * max(float(b[m].abs().max()), 1e-6), k
+    for k in grad_s:
+        den = max(float(grad_s[k].abs().max()), 1e-6)
+        assert float((grad_j[k] - grad_s[k]).abs().max()) / den < 2e-3, k
+
+
+def test_inference_graph_segments_match_eager(small):
+    """No-grad passes (the EMA teacher of the self-training step) replay forward-only CUDA graphs: same outputs as the
+    eager evaluation pass, also after the weights changed in place."""
+    import copy
+    from datr_b200 import graphs
+    model, _, _ = small
+    teacher = copy.deepcopy(model).to(memory_format=torch.channels_last).eval()
+    images = torch.stack([torch.nn.functional.pad(i, (0, 160 - i.shape[2], 0, 128 - i.shape[1])) for i in mcase.images()]).cuda()
+    images = images.contiguous(memory_format=torch.channels_last)
+    sg = graphs.StepGraphs()
+    for step in range(3):
+        with torch.no_grad():
+            want = teacher(images)
+            graphs.ACTIVE = sg
+            try:
+                sg.begin_step()
+                got = teacher(images)
+            finally:
+                graphs.ACTIVE = None
+            for k in ("pred_logits", "pred_boxes"):
+                assert float((got[k] - want[k]).abs().max()) <= 1e-4 * float(want[k].abs().max()), (step, k)
+            for p in teacher.parameters():          # what the EMA update does: in-place change, same storage
+                p.mul_(0.999)
+    assert sg.captures >= 5 and sg.replayed_native_launches > 0

@@ -28,3 +28,14 @@ with open(out, "w") as f:
     for e in rows[:160]:
         f.write(f"{e.self_device_time_total/1e3:8.3f} ms {e.count:5d}x  {e.key[:48]:48s} {str(e.input_shapes)[:170]}\n")
 print(open(out).read()[:3000])
+
+# second table: launches per operator name (where the short-kernel tail comes from)
+by = {}
+for e in rows:
+    a = by.setdefault(e.key, [0, 0.0])
+    a[0] += e.count; a[1] += e.self_device_time_total
+with open(out, "a") as f:
+    f.write("\nby operator name, sorted by number of calls with device work:\n")
+    for k, (n, t) in sorted(by.items(), key=lambda kv: -kv[1][0])[:60]:
+        f.write(f"{n:6d}x {t/1e3:8.3f} ms  {k[:80]}\n")
+print(open(out).read().split("by operator name")[1][:4500])
