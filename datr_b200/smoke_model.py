@@ -25,7 +25,8 @@ def run():
     torch.cuda.synchronize()
     launches = native.launch_count() - n0
     assert torch.isfinite(loss).item(), "non-finite loss"
-    assert launches == 2 * 2 * (2 + 2), launches          # 2 passes x (2 enc + 2 dec) x (fwd + bwd)
+    # source + target halves share ONE encoder and ONE decoder pass: (2 enc + 2 dec layers) x (fwd + bwd)
+    assert launches == 2 * (2 + 2), launches
     g = model.transformer.encoder.layers[0].self_attn.sampling_offsets.weight.grad
     assert g is not None and torch.isfinite(g).all().item()
     print(f"[smoke] DINO DA training step ok: loss={loss.item():.4f}, MSDeformAttn launches={launches}")
