@@ -23,6 +23,28 @@ _DTYPES = {torch.float32: 0, torch.float64: 1}
 # (kind, shape_key, start_event, end_event) recorded on the launching stream.
 _timers = None
 
+# Host copies of (spatial_shapes, level_start_index) per device tensor pair: the backward builds its TMA tensor maps
+# from them (include/datr_msda.h, *_hs entry points).  Filled by one device->host read per distinct pair, never while a
+# CUDA graph is being captured; a miss during capture just selects the vector-reduction scatter.
+_HOST_GEOMETRY = {}
+
+
+def host_geometry(spatial_shapes, level_start_index):
+    """(int64[L,2] array, int64[L] array) ctypes copies of the two device tensors, or (None, None)."""
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, level_start_index.data_ptr(), level_start_index._version,
+           str(spatial_shapes.device))
+    hit = _HOST_GEOMETRY.get(key)
+    if hit is None:
+        if torch.cuda.is_current_stream_capturing():
+            return None, None
+        import ctypes
+        sh = [int(v) for v in spatial_shapes.reshape(-1).tolist()]
+        st = [int(v) for v in level_start_index.reshape(-1).tolist()]
+        if len(_HOST_GEOMETRY) > 256:
+            _HOST_GEOMETRY.clear()
+        hit = _HOST_GEOMETRY[key] = ((ctypes.c_int64 * len(sh))(*sh), (ctypes.c_int64 * len(st))(*st))
+    return hit
+
 
 def _check(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, extra=()):
     named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
@@ -103,7 +125,8 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
         if _timers is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-        rc = lib.datr_msda_backward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+        hs, hl = host_geometry(spatial_shapes, level_start_index)
+        rc = lib.datr_msda_backward_hs(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), hs, hl,
                                     sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(),
                                     N, S, M, D, L, Lq, P, _DTYPES[value.dtype],
                                     grad_value.data_ptr(), grad_loc.data_ptr(), grad_attn.data_ptr(),
@@ -170,11 +193,39 @@ def _check_fused(value, spatial_shapes, level_start_index, offsets, logits, ref,
     return N, S, M, D, L, Lq, P, R, _row_stride("sampling_offsets", offsets), _row_stride("attn_logits", logits)
 
 
+PAIR_STORAGE = {torch.bfloat16: 1, torch.float16: 2}     # include/datr_msda.h: DATR_STORE_BF16_PAIRS / _FP16_PAIRS
+
+
+def pack_value_pairs(value, spatial_shapes, level_start_index, dtype=torch.bfloat16):
+    """value [N,S,M,32] fp32 -> pair rows [N,S,M,64] of `dtype` (bf16 / fp16): per (pixel, head) line and per 16-byte
+    lane segment, 4 channels of the pixel and the same 4 channels of its right-hand neighbour (include/datr_msda.h).
+    No gradient flows through the result; the backward of the fused op still produces the fp32 grad_value."""
+    if not (value.is_cuda and value.dtype == torch.float32 and value.dim() == 4 and value.shape[-1] == 32
+            and value.is_contiguous()):
+        raise RuntimeError("pack_value_pairs expects a contiguous CUDA fp32 value map [N,S,M,32]")
+    if dtype not in PAIR_STORAGE:
+        raise RuntimeError("pair rows are stored as torch.bfloat16 or torch.float16")
+    N, S, M, _ = value.shape
+    L = spatial_shapes.shape[0]
+    with torch.cuda.device(value.device):
+        pairs = torch.empty((N, S, M, 64), dtype=dtype, device=value.device)
+        rc = native.lib().datr_msda_pack_value_pairs(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                                     N, S, M, L, PAIR_STORAGE[dtype], pairs.data_ptr(),
+                                                     torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        _raise(rc, "pack_value_pairs")
+    return pairs
+
+
 def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampling_offsets, attn_logits,
-                                 reference_points):
-    """Extension (not in the reference's module): MSDeformAttn.forward's prologue + the op in one kernel."""
+                                 reference_points, pairs=None):
+    """Extension (not in the reference's module): MSDeformAttn.forward's prologue + the op in one kernel.
+    `pairs` (optional, from pack_value_pairs(value, ...)): gather from the 16-bit pair rows instead of `value`."""
     N, S, M, D, L, Lq, P, R, so, sl = _check_fused(value, spatial_shapes, level_start_index, sampling_offsets,
                                                    attn_logits, reference_points)
+    if pairs is not None and (tuple(pairs.shape) != (N, S, M, 64) or pairs.dtype not in PAIR_STORAGE
+                              or not pairs.is_contiguous() or pairs.device != value.device or D != 32):
+        raise RuntimeError("pairs must be the [N,S,M,64] bf16 / fp16 tensor of pack_value_pairs(value, ...)")
     lib = native.lib()
     with torch.cuda.device(value.device):
         out = torch.empty((N, Lq, M * D), dtype=value.dtype, device=value.device)
@@ -182,13 +233,19 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, sampl
         if _timers is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-        rc = lib.datr_msda_fused_forward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
-                                         sampling_offsets.data_ptr(), so, attn_logits.data_ptr(), sl,
-                                         reference_points.data_ptr(), R, N, S, M, D, L, Lq, P, 0, out.data_ptr(),
-                                         stream.cuda_stream)
+        if pairs is None:
+            rc = lib.datr_msda_fused_forward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                             sampling_offsets.data_ptr(), so, attn_logits.data_ptr(), sl,
+                                             reference_points.data_ptr(), R, N, S, M, D, L, Lq, P, 0, out.data_ptr(),
+                                             stream.cuda_stream)
+        else:
+            rc = lib.datr_msda_fused_forward_pairs(pairs.data_ptr(), PAIR_STORAGE[pairs.dtype], spatial_shapes.data_ptr(),
+                                                   level_start_index.data_ptr(), sampling_offsets.data_ptr(), so,
+                                                   attn_logits.data_ptr(), sl, reference_points.data_ptr(), R,
+                                                   N, S, M, D, L, Lq, P, out.data_ptr(), stream.cuda_stream)
         if _timers is not None:
             e1.record(stream)
-            _timers.append(("fwd", (N, S, M, D, L, Lq, P, value.element_size()), e0, e1))
+            _timers.append(("fwd", (N, S, M, D, L, Lq, P, value.element_size() if pairs is None else 2), e0, e1))
     if rc != 0:
         _raise(rc, "ms_deform_attn_fused_forward")
     return out
@@ -222,7 +279,8 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, samp
         if _timers is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-        rc = lib.datr_msda_fused_backward(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+        hs, hl = host_geometry(spatial_shapes, level_start_index)
+        rc = lib.datr_msda_fused_backward_hs(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), hs, hl,
                                           sampling_offsets.data_ptr(), so, attn_logits.data_ptr(), sl,
                                           reference_points.data_ptr(), R, grad_output.data_ptr(),
                                           N, S, M, D, L, Lq, P, 0, grad_value.data_ptr(), grad_off.data_ptr(),

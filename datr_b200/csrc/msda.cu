@@ -26,6 +26,9 @@
 //     thread 0, cuh:377-393); grad_value uses 16-byte vector reductions (red.global.add.v4.f32),
 //     one per slot per lane, predicated off for empty slots, instead of 4 scalar atomics.
 //   * any other channel count, and fp64, run the generic warp-per-row kernels below.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -100,6 +103,7 @@ constexpr int kMaxTaps = 32;     // L*P limit of the fast path
 
 struct Slots {
   int pix;                  // pixel index (level start included) of the anchor (by,bx)
+  int anchor;               // by << 16 | bx
   float a;                  // attention weight (0 if the sample is rejected)
   float wy0, wy1, wx0, wx1; // interpolation weight carried by each slot (0 = slot unused)
   float sy0, sy1, sx0, sx1; // d(weight)/d(coordinate) of each slot: -1, +1 or 0
@@ -116,6 +120,7 @@ __device__ __forceinline__ Slots place(float locx, float locy, float a, const Le
   const int by = min(max(y0, 0), max(H - 2, 0)), bx = min(max(x0, 0), max(W - 2, 0));
   Slots s;
   s.pix = g.start + by * W + bx;
+  s.anchor = (by << 16) | bx;
   s.a = ok ? a : 0.f;
   const bool y_on0 = ok && y0 == by, y1_on0 = ok && y0 + 1 == by;          // slot 0 = row by
   s.wy0 = y_on0 ? hy : (y1_on0 ? ly : 0.f);
@@ -262,16 +267,61 @@ __host__ __device__ inline int pix_stride(int taps) { return taps | 1; }
 
 constexpr int kGeomBytes = 512;  // kMaxLevels * sizeof(LevelGeom) rounded up
 
+
+// ------------------------------------------------------------------------------------------------
+// TMA scatter of the backward (kStages > 0 variants; opt-in, NOT the default).  Measured on B200
+// (tools/probes/msda_tma_red_probe.cu, profiles/r02w_msda_tma_red_probe.txt): 22.8 M corner lines take 322 us as
+// red.global.add.v4.f32 and 321 us as 5.7 M `cp.reduce.async.bulk.tensor` boxes of 2 x 2 pixels -- the wall of the
+// scatter is the L2 atomic units (9 TB/s of fp32 adds), not the SM's load/store path.  In the full kernel the staging
+// (4 STS.128 + proxy fence + 2 warp barriers per sample, 3 instead of 4 CTAs/SM) costs more than taking the reductions
+// out of L1TEX saves: 502 / 513 us (1 / 2 buffers) against 447 us (profiles/r02x_msda_bwd_tma_variants.txt).
+// One tensor map per level over grad_value: dims {32 channels, heads, W, H, batch}, box {32, 1, 2, 2, 1}; the four
+// weighted rows of a sample are staged in shared memory ([corner][32 floats], the box layout) and lane 0 of the row
+// issues ONE reduce per sample.
+// ------------------------------------------------------------------------------------------------
+constexpr int kTmaLevels = 4;
+struct LevelMaps { CUtensorMap m[kTmaLevels]; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void tma_red_add_5d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.reduce.async.bulk.tensor.5d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-template <int kP, int kBatch, int kMode, int kMinBlocks = 0>
+// kStore = 0: value rows are fp32 [N,S,M,32] (the reference's layout).  kStore = 1 / 2: `value` points at PAIR rows
+// (datr_msda_pack_value_pairs): the 128-byte line of (pixel, head) holds, per lane, 4 channels of the pixel and the same
+// 4 channels of its right-hand neighbour as bf16 (1) / fp16 (2), so a sample costs TWO line gathers instead of four --
+// the forward is bound by the L1TEX line rate, not by bytes.
+template <int kStore>
+__device__ __forceinline__ void unpack_pair(const float4& raw, float4& left, float4& right) {
+  const uint32_t a = __float_as_uint(raw.x), b = __float_as_uint(raw.y), c = __float_as_uint(raw.z), d = __float_as_uint(raw.w);
+  if constexpr (kStore == 1) {
+    left = make_float4(__uint_as_float(a << 16), __uint_as_float(a & 0xffff0000u), __uint_as_float(b << 16),
+                       __uint_as_float(b & 0xffff0000u));
+    right = make_float4(__uint_as_float(c << 16), __uint_as_float(c & 0xffff0000u), __uint_as_float(d << 16),
+                        __uint_as_float(d & 0xffff0000u));
+  } else {
+    const float2 l0 = __half22float2(*reinterpret_cast<const __half2*>(&a)), l1 = __half22float2(*reinterpret_cast<const __half2*>(&b));
+    const float2 r0 = __half22float2(*reinterpret_cast<const __half2*>(&c)), r1 = __half22float2(*reinterpret_cast<const __half2*>(&d));
+    left = make_float4(l0.x, l0.y, l1.x, l1.y);
+    right = make_float4(r0.x, r0.y, r1.x, r1.y);
+  }
+}
+
+template <int kP, int kBatch, int kMode, int kMinBlocks = 0, int kStore = 0>
 __global__ void __launch_bounds__(256, kMinBlocks)
 msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
                  const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                  const float* __restrict__ attn, const float* __restrict__ ref, long long ostride, long long lstride,
                  int N, int S, int M, int L, int Lq, float* __restrict__ out) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   LevelGeom* geom = reinterpret_cast<LevelGeom*>(smem);
   const int LP = L * kP, ws = table_stride(LP), ps = pix_stride(LP);
   uint4* wtab = reinterpret_cast<uint4*>(smem + kGeomBytes);            // [32][ws] {w00,w01,w10,w11} * attn
@@ -330,14 +380,23 @@ msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
         const int pix = myp[s];
         w[j] = myw[s];
         v[j][0] = ldg4_ordered(pixel_ptr(vb, pix, rs4));
-        v[j][1] = ldg4_ordered(pixel_ptr(vb01, pix, rs4));
-        v[j][2] = ldg4_ordered(pixel_ptr(vb10, pix, rs4));
-        v[j][3] = ldg4_ordered(pixel_ptr(vb11, pix, rs4));
+        if constexpr (kStore == 0) {
+          v[j][1] = ldg4_ordered(pixel_ptr(vb01, pix, rs4));
+          v[j][2] = ldg4_ordered(pixel_ptr(vb10, pix, rs4));
+          v[j][3] = ldg4_ordered(pixel_ptr(vb11, pix, rs4));
+        } else {
+          v[j][2] = ldg4_ordered(pixel_ptr(vb10, pix, rs4));
+        }
       }
 #pragma unroll
       for (int j = 0; j < kBatch; ++j) {
         const float wj[4] = {__uint_as_float(w[j].x), __uint_as_float(w[j].y), __uint_as_float(w[j].z),
                              __uint_as_float(w[j].w)};
+        if constexpr (kStore != 0) {
+          const float4 top = v[j][0], bottom = v[j][2];
+          unpack_pair<kStore>(top, v[j][0], v[j][1]);
+          unpack_pair<kStore>(bottom, v[j][2], v[j][3]);
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           acc.x = fmaf(wj[i], v[j][i].x, acc.x);
@@ -354,19 +413,20 @@ msda_fwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-template <int kP, int kMode>
+template <int kP, int kMode, int kStages = 0>   // kStages > 0: TMA scatter with that many staging buffers per warp
 __global__ void __launch_bounds__(256, 4)
-msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ shapes,
+msda_bwd_f32_d32(const __grid_constant__ LevelMaps maps, const float* __restrict__ value, const int64_t* __restrict__ shapes,
                  const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                  const float* __restrict__ attn, const float* __restrict__ ref, const float* __restrict__ grad_out,
                  long long ostride, long long lstride, int N, int S, int M, int L, int Lq,
                  float* __restrict__ grad_value, float* __restrict__ grad_loc, float* __restrict__ grad_attn) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   LevelGeom* geom = reinterpret_cast<LevelGeom*>(smem);
   const int LP = L * kP, ws = table_stride(LP);
   uint4* tab0 = reinterpret_cast<uint4*>(smem + kGeomBytes);   // [32][ws] {pix, a, a*W, a*H}
   uint4* tab1 = tab0 + kRowsPerCta * ws;                       // {wy0, wy1, wx0, wx1}
   uint4* tab2 = tab1 + kRowsPerCta * ws;                       // {sy0, sy1, sx0, sx1}
+  constexpr bool kTma = kStages > 0;
   load_levels(geom, shapes, lstart, L);
 
   const int r = threadIdx.x >> 3, sub = threadIdx.x & 7;
@@ -384,13 +444,23 @@ msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
   uint4* my0 = tab0 + r * ws;
   uint4* my1 = tab1 + r * ws;
   uint4* my2 = tab2 + r * ws;
+  // TMA variant: staging [warp][buffer][row of the warp][corner][32 floats] behind the tables, 128-byte aligned
+  float* stage = nullptr;
+  if constexpr (kTma) {
+    const uint32_t tables = kGeomBytes + 3u * kRowsPerCta * ws * 16u;
+    stage = reinterpret_cast<float*>(smem + ((tables + 127u) & ~127u)) + (threadIdx.x >> 5) * (kStages * 4 * 128) +
+            (r & 3) * 128 + sub * 4;
+  }
 
   auto publish = [&](int s, float x, float y, float a) {
     const LevelGeom g = geom[s / kP];
     const Slots t = place(x, y, a, g);
     const float al = live ? t.a : 0.f;  // dead rows scatter nothing
-    my0[s] = make_uint4(unsigned(t.pix), __float_as_uint(al), __float_as_uint(t.a * float(g.W)),
-                        __float_as_uint(t.a * float(g.H)));
+    if constexpr (kTma)   // {pix, a, anchor (by << 16 | bx) = box coordinates of the reduce, -}
+      my0[s] = make_uint4(unsigned(t.pix), __float_as_uint(al), unsigned(t.anchor), 0u);
+    else
+      my0[s] = make_uint4(unsigned(t.pix), __float_as_uint(al), __float_as_uint(t.a * float(g.W)),
+                          __float_as_uint(t.a * float(g.H)));
     my1[s] = make_uint4(__float_as_uint(t.wy0), __float_as_uint(t.wy1), __float_as_uint(t.wx0), __float_as_uint(t.wx1));
     my2[s] = make_uint4(__float_as_uint(t.sy0), __float_as_uint(t.sy1), __float_as_uint(t.sx0), __float_as_uint(t.sx1));
   };
@@ -431,13 +501,32 @@ msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
       const float4 v01 = ldg4_ordered(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p00) + d01));
       const float4 v10 = ldg4_ordered(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p00) + d10));
       const float4 v11 = ldg4_ordered(reinterpret_cast<const float*>(reinterpret_cast<const char*>(p00) + d11));
-      // grad_value: slot weight * attn * grad_out, one 16-byte reduction per slot (skipped if weight 0)
-      const float* g00 = pixel_ptr(gb, pix, rs4);
       const float ay0 = wy0 * a, ay1 = wy1 * a;
-      red_add4_if(g00, ay0 * wx0, g);
-      red_add4_if(reinterpret_cast<const float*>(reinterpret_cast<const char*>(g00) + d01), ay0 * wx1, g);
-      red_add4_if(reinterpret_cast<const float*>(reinterpret_cast<const char*>(g00) + d10), ay1 * wx0, g);
-      red_add4_if(reinterpret_cast<const float*>(reinterpret_cast<const char*>(g00) + d11), ay1 * wx1, g);
+      if constexpr (kTma) {
+        // grad_value: the four weighted rows go to the staging buffer of this (warp, sample parity) and lane 0 of the
+        // row hands them to the TMA unit as ONE 2x2-pixel reduce.  The buffer was last used kStages samples ago.
+        float* st = stage + (s % kStages) * (4 * 128);
+        if (sub == 0) bulk_wait_read<kStages - 1>();
+        __syncwarp();
+        const float c00 = ay0 * wx0, c01 = ay0 * wx1, c10 = ay1 * wx0, c11 = ay1 * wx1;
+        *reinterpret_cast<float4*>(st) = make_float4(c00 * g.x, c00 * g.y, c00 * g.z, c00 * g.w);
+        *reinterpret_cast<float4*>(st + 32) = make_float4(c01 * g.x, c01 * g.y, c01 * g.z, c01 * g.w);
+        *reinterpret_cast<float4*>(st + 64) = make_float4(c10 * g.x, c10 * g.y, c10 * g.z, c10 * g.w);
+        *reinterpret_cast<float4*>(st + 96) = make_float4(c11 * g.x, c11 * g.y, c11 * g.z, c11 * g.w);
+        fence_async_smem();
+        __syncwarp();
+        if (sub == 0) {
+          if (a != 0.f) tma_red_add_5d(&maps.m[l], st, 0, m, int(q0.z & 0xffffu), int(q0.z >> 16), b);
+          bulk_commit();
+        }
+      } else {
+        // grad_value: slot weight * attn * grad_out, one 16-byte reduction per slot (skipped if weight 0)
+        const float* g00 = pixel_ptr(gb, pix, rs4);
+        red_add4_if(g00, ay0 * wx0, g);
+        red_add4_if(reinterpret_cast<const float*>(reinterpret_cast<const char*>(g00) + d01), ay0 * wx1, g);
+        red_add4_if(reinterpret_cast<const float*>(reinterpret_cast<const char*>(g00) + d10), ay1 * wx0, g);
+        red_add4_if(reinterpret_cast<const float*>(reinterpret_cast<const char*>(g00) + d11), ay1 * wx1, g);
+      }
       // <grad_out, slot value> over this lane's 4 channels
       const float e00 = dot4(g, v00), e01 = dot4(g, v01), e10 = dot4(g, v10), e11 = dot4(g, v11);
       const float r0 = fmaf(wx1, e01, wx0 * e00), r1 = fmaf(wx1, e11, wx0 * e10);       // interpolate along x
@@ -447,8 +536,10 @@ msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
       float px = fmaf(wy1, t1, wy0 * t0);                                                // cuh:157 (x)
       float py = fmaf(__uint_as_float(q2.y), r1, __uint_as_float(q2.x) * r0);            // cuh:158 (y)
       pa = group8_sum(pa); px = group8_sum(px); py = group8_sum(py);
+      // attn * (W, H): read from table 0, or rebuilt from the same two factors when the TMA variant keeps the anchor there
+      const float aW = kTma ? a * float(W) : __uint_as_float(q0.z), aH = kTma ? a * float(H) : __uint_as_float(q0.w);
       if constexpr (kMode == 0) {
-        if (sub == (s & 7)) { keep_a = pa; keep_x = px * __uint_as_float(q0.z); keep_y = py * __uint_as_float(q0.w); }
+        if (sub == (s & 7)) { keep_a = pa; keep_x = px * aW; keep_y = py * aH; }
         if ((s & 7) == 7 || s == LP - 1) {
           const int s0 = s & ~7;
           if (live && s0 + sub <= s) {
@@ -460,10 +551,12 @@ msda_bwd_f32_d32(const float* __restrict__ value, const int64_t* __restrict__ sh
         // every lane of the row has read record s (the shuffles above are warp-synchronous): reuse its slot of
         // table 2 for {d/d attn, d/d loc.x, d/d loc.y}; the owner lane of the sample collects it after the loop
         if (sub == (s & 7))
-          my2[s] = make_uint4(__float_as_uint(pa), __float_as_uint(px * __uint_as_float(q0.z)),
-                              __float_as_uint(py * __uint_as_float(q0.w)), 0u);
+          my2[s] = make_uint4(__float_as_uint(pa), __float_as_uint(px * aW), __float_as_uint(py * aH), 0u);
       }
     }
+  }
+  if constexpr (kTma) {
+    if (sub == 0) bulk_wait_read<0>();   // the staging buffers must outlive the last reads of the TMA unit
   }
   if constexpr (kMode != 0) {
     // softmax backward (d logit_s = a_s * (d a_s - sum_t a_t * d a_t)) and the chain rule of the location formula
@@ -591,6 +684,43 @@ msda_bwd_generic(const T* __restrict__ value, const int64_t* __restrict__ shapes
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Pair rows: [N,S,M,32] fp32 -> [N,S,M,8][left 4 channels, right 4 channels] 16-bit, where `right` is the pixel one
+// column further in the same level row (zeros in the last column: the kernels anchor every 2x2 block at x <= W-2).
+// ------------------------------------------------------------------------------------------------
+template <int kStore>
+__device__ __forceinline__ uint2 pack4(const float4& v) {
+  if constexpr (kStore == 1) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  } else {
+    const __half2 a = __floats2half2_rn(fminf(fmaxf(v.x, -65504.f), 65504.f), fminf(fmaxf(v.y, -65504.f), 65504.f));
+    const __half2 b = __floats2half2_rn(fminf(fmaxf(v.z, -65504.f), 65504.f), fminf(fmaxf(v.w, -65504.f), 65504.f));
+    return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  }
+}
+
+template <int kStore>
+__global__ void __launch_bounds__(256)
+msda_pack_pairs(const float* __restrict__ value, const int64_t* __restrict__ shapes, const int64_t* __restrict__ lstart,
+                long long total, int S, int M, int L, uint4* __restrict__ pairs) {
+  __shared__ LevelGeom geom[kMaxLevels];
+  load_levels(geom, shapes, lstart, L);
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 16-byte output = (n, s, m, lane)
+  if (t >= total) return;
+  const int per_pixel = M * 8;
+  const int s = int((t / per_pixel) % S);
+  int W = 1, x = 0;
+  for (int l = 0; l < L; ++l)
+    if (s >= geom[l].start && s < geom[l].start + geom[l].H * geom[l].W) { W = geom[l].W; x = (s - geom[l].start) % W; }
+  const float4 left = __ldg(reinterpret_cast<const float4*>(value) + t);
+  float4 right = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (x + 1 < W) right = __ldg(reinterpret_cast<const float4*>(value) + t + per_pixel);
+  const uint2 a = pack4<kStore>(left), b = pack4<kStore>(right);
+  pairs[t] = make_uint4(a.x, a.y, b.x, b.y);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Host side.
 // ------------------------------------------------------------------------------------------------
@@ -631,12 +761,15 @@ int allow_big_smem() {
   if (cudaGetDevice(&dev) != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaGetDevice failed%s");
   const uint64_t bit = 1ull << (dev & 63);
   if (done.load(std::memory_order_acquire) & bit) return DATR_OK;
-  const int bytes = 64 * 1024;
+  const int bytes = 96 * 1024;
   cudaError_t e = cudaSuccess;
 #define DATR_OPT(K) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
 #define DATR_OPT_MODES(PP) DATR_OPT((msda_bwd_f32_d32<PP, 0>)); DATR_OPT((msda_bwd_f32_d32<PP, 1>)); DATR_OPT((msda_bwd_f32_d32<PP, 2>))
   DATR_OPT_MODES(1); DATR_OPT_MODES(2); DATR_OPT_MODES(4); DATR_OPT_MODES(8);
 #undef DATR_OPT_MODES
+#define DATR_OPT_TMA(SS) DATR_OPT((msda_bwd_f32_d32<4, 0, SS>)); DATR_OPT((msda_bwd_f32_d32<4, 1, SS>)); DATR_OPT((msda_bwd_f32_d32<4, 2, SS>))
+  DATR_OPT_TMA(1); DATR_OPT_TMA(2);
+#undef DATR_OPT_TMA
 #undef DATR_OPT
   if (e != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   done.fetch_or(bit, std::memory_order_release);
@@ -646,15 +779,15 @@ int allow_big_smem() {
 // launchers of the fp32 / D = 32 kernels; mode 0 = materialised locations + weights, 1 / 2 = fused prologue (R = 2 / 4)
 int launch_fwd_fast(int mode, const float* v, const int64_t* shapes, const int64_t* lstart, const float* lc,
                     const float* at, const float* ref, long long ostride, long long lstride, int N, int S, int M, int L,
-                    int Lq, int P, float* o, cudaStream_t stream) {
+                    int Lq, int P, float* o, cudaStream_t stream, int store = 0) {
   const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
   if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
   const int LP = L * P;
   const size_t smem = kGeomBytes + (size_t)kRowsPerCta * (table_stride(LP) * 16 + pix_stride(LP) * 4);
 #define DATR_FWD(PP, BB, MM) \
   msda_fwd_f32_d32<PP, BB, MM><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, ostride, lstride, N, S, M, L, Lq, o)
-#define DATR_FWD4(BB, MM, KK) \
-  msda_fwd_f32_d32<4, BB, MM, KK><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, ostride, lstride, N, S, M, L, Lq, o)
+#define DATR_FWD4(BB, MM, KK, SS) \
+  msda_fwd_f32_d32<4, BB, MM, KK, SS><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, ostride, lstride, N, S, M, L, Lq, o)
   // 4 points (DINO): measured on B200 (profiles/r02d_msda_fwd_variants.txt) -- long calls (encoder) are fastest with
   // 2 samples of loads in flight at 5 CTAs/SM (171 vs 177 us at config 2, 409 vs 433 us at 5 scales), short calls
   // (decoder, a few hundred CTAs per SM wave) with 4 samples in flight at 4 CTAs/SM (19.5 vs 22.5 us)
@@ -664,10 +797,12 @@ int launch_fwd_fast(int mode, const float* v, const int64_t* shapes, const int64
     case 1: DATR_FWD(1, 1, MM); break;  \
     case 2: DATR_FWD(2, 2, MM); break;  \
     case 4:                             \
-      if (short_call) DATR_FWD4(4, MM, 4); else DATR_FWD4(2, MM, 5); \
+      if (store == 1) DATR_FWD4(4, MM, 4, 1); else if (store == 2) DATR_FWD4(4, MM, 4, 2); \
+      else if (short_call) DATR_FWD4(4, MM, 4, 0); else DATR_FWD4(2, MM, 5, 0); \
       break;                            \
     default: DATR_FWD(8, 2, MM); break; \
   }
+  if (store != 0 && P != 4) return fail(DATR_ERR_UNSUPPORTED, "pair-row value maps are implemented for 4 points%s");
   if (mode == 0) { DATR_FWD_P(0) } else if (mode == 1) { DATR_FWD_P(1) } else { DATR_FWD_P(2) }
 #undef DATR_FWD_P
 #undef DATR_FWD4
@@ -675,15 +810,83 @@ int launch_fwd_fast(int mode, const float* v, const int64_t* shapes, const int64
   return after_launch("msda_fwd_f32_d32");
 }
 
+// Backward scatter variant: 0 = red.global.add.v4.f32 per corner, 1 / 2 = TMA reduce per sample with that many staging
+// buffers per warp.  DATR_MSDA_BWD_STAGES overrides the default at load time; datr_msda_set_backward_stages() at run time.
+std::atomic<int> g_bwd_stages{-1};
+int bwd_stages() {
+  int v = g_bwd_stages.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("DATR_MSDA_BWD_STAGES");
+    v = e ? atoi(e) : 0;   // measured: 447 us (0) vs 502 / 513 us (1 / 2) at the config-2 encoder call
+    if (v < 0 || v > 2) v = 0;
+    g_bwd_stages.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      return reinterpret_cast<EncodeTiledFn>(p);
+    return static_cast<EncodeTiledFn>(nullptr);
+  }();
+  return fn;
+}
+
+// One tensor map per level over grad_value [N, S, M, 32]: dims {32, M, W, H, N}, box {32, 1, 2, 2, 1}.  Returns false if
+// the geometry is outside what the TMA variant covers (then the red.global kernel runs).
+bool encode_level_maps(LevelMaps* maps, float* gv, const int64_t* hshapes, const int64_t* hstart, int N, int S, int M, int L) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc || L > kTmaLevels || M > 256) return false;
+  memset(maps, 0, sizeof *maps);
+  for (int l = 0; l < L; ++l) {
+    const int64_t H = hshapes[2 * l], W = hshapes[2 * l + 1], st = hstart[l];
+    if (H < 2 || W < 2 || H > 65535 || W > 65535 || st < 0 || st + H * W > S) return false;
+    const cuuint64_t row = (cuuint64_t)M * 32 * 4;
+    const cuuint64_t gdim[5] = {32, (cuuint64_t)M, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t gstr[4] = {32 * 4, row, (cuuint64_t)W * row, (cuuint64_t)S * row};
+    const cuuint32_t box[5] = {32, 1, 2, 2, 1}, estr[5] = {1, 1, 1, 1, 1};
+    if (enc(&maps->m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, gv + st * (int64_t)M * 32, gdim, gstr, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
+
+// `hshapes` / `hstart`: host copies of spatial_shapes / level_start_index (or null): needed to build the tensor maps of the
+// TMA scatter; without them the red.global kernel runs.
 int launch_bwd_fast(int mode, const float* v, const int64_t* shapes, const int64_t* lstart, const float* lc,
                     const float* at, const float* ref, const float* go, long long ostride, long long lstride, int N, int S,
-                    int M, int L, int Lq, int P, float* gv, float* gl, float* ga, cudaStream_t stream) {
+                    int M, int L, int Lq, int P, float* gv, float* gl, float* ga, cudaStream_t stream,
+                    const int64_t* hshapes = nullptr, const int64_t* hstart = nullptr) {
   const long long ctas = (((long long)N * Lq + kRowsPerCta - 1) / kRowsPerCta) * M;
   if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
-  const size_t smem = kGeomBytes + (size_t)kRowsPerCta * table_stride(L * P) * 48;
+  size_t smem = kGeomBytes + (size_t)kRowsPerCta * table_stride(L * P) * 48;
   if (int rc = allow_big_smem()) return rc;
+  static const LevelMaps no_maps = {};
+  const int stages = bwd_stages();
+  if (stages > 0 && P == 4 && hshapes && hstart) {
+    LevelMaps maps;
+    if (encode_level_maps(&maps, gv, hshapes, hstart, N, S, M, L)) {
+      smem = ((smem + 127) & ~size_t(127)) + (size_t)8 * stages * 4 * 512;
+#define DATR_BWD_TMA(MM, SS) \
+  msda_bwd_f32_d32<4, MM, SS><<<(unsigned)ctas, 256, smem, stream>>>(maps, v, shapes, lstart, lc, at, ref, go, ostride, lstride, N, S, M, L, Lq, gv, gl, ga)
+#define DATR_BWD_TMA_S(MM) if (stages == 1) DATR_BWD_TMA(MM, 1); else DATR_BWD_TMA(MM, 2)
+      if (mode == 0) { DATR_BWD_TMA_S(0); } else if (mode == 1) { DATR_BWD_TMA_S(1); } else { DATR_BWD_TMA_S(2); }
+#undef DATR_BWD_TMA_S
+#undef DATR_BWD_TMA
+      return after_launch("msda_bwd_f32_d32 (TMA scatter)");
+    }
+  }
 #define DATR_BWD(PP, MM) \
-  msda_bwd_f32_d32<PP, MM><<<(unsigned)ctas, 256, smem, stream>>>(v, shapes, lstart, lc, at, ref, go, ostride, lstride, N, S, M, L, Lq, gv, gl, ga)
+  msda_bwd_f32_d32<PP, MM><<<(unsigned)ctas, 256, smem, stream>>>(no_maps, v, shapes, lstart, lc, at, ref, go, ostride, lstride, N, S, M, L, Lq, gv, gl, ga)
 #define DATR_BWD_P(MM)               \
   switch (P) {                       \
     case 1: DATR_BWD(1, MM); break;  \
@@ -746,6 +949,14 @@ int datr_msda_forward(const void* value, const int64_t* shapes, const int64_t* l
 int datr_msda_backward(const void* value, const int64_t* shapes, const int64_t* lstart, const void* loc,
                        const void* attn, const void* grad_out, int N, int S, int M, int D, int L, int Lq, int P,
                        int dtype, void* grad_value, void* grad_loc, void* grad_attn, void* stream_) {
+  return datr_msda_backward_hs(value, shapes, lstart, nullptr, nullptr, loc, attn, grad_out, N, S, M, D, L, Lq, P, dtype,
+                               grad_value, grad_loc, grad_attn, stream_);
+}
+
+int datr_msda_backward_hs(const void* value, const int64_t* shapes, const int64_t* lstart, const int64_t* host_shapes,
+                          const int64_t* host_lstart, const void* loc, const void* attn, const void* grad_out, int N, int S,
+                          int M, int D, int L, int Lq, int P, int dtype, void* grad_value, void* grad_loc, void* grad_attn,
+                          void* stream_) {
   if (int rc = check_common(value, shapes, lstart, loc, attn, N, S, M, D, L, Lq, P, dtype)) return rc;
   if (!grad_out || !grad_value || !grad_loc || !grad_attn) return fail(DATR_ERR_BAD_ARGUMENT, "null gradient pointer%s");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -758,7 +969,7 @@ int datr_msda_backward(const void* value, const int64_t* shapes, const int64_t* 
     return launch_bwd_fast(0, static_cast<const float*>(value), shapes, lstart, static_cast<const float*>(loc),
                            static_cast<const float*>(attn), nullptr, static_cast<const float*>(grad_out), 0, 0, N, S, M, L, Lq, P,
                            static_cast<float*>(grad_value), static_cast<float*>(grad_loc), static_cast<float*>(grad_attn),
-                           stream);
+                           stream, host_shapes, host_lstart);
   const long long ctas = (rows + 7) / 8;
   if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
   if (dtype == DATR_DTYPE_F32)
@@ -789,10 +1000,57 @@ int datr_msda_fused_forward(const void* value, const int64_t* shapes, const int6
                          static_cast<cudaStream_t>(stream_));
 }
 
+int datr_msda_pack_value_pairs(const void* value, const int64_t* shapes, const int64_t* lstart, int N, int S, int M, int L,
+                               int storage, void* pairs, void* stream_) {
+  if (!value || !shapes || !lstart || !pairs) return fail(DATR_ERR_BAD_ARGUMENT, "null pointer argument%s");
+  if (N <= 0 || S <= 0 || M <= 0 || L <= 0 || L > kMaxLevels) return fail(DATR_ERR_BAD_ARGUMENT, "bad dimensions%s");
+  if (storage != DATR_STORE_BF16_PAIRS && storage != DATR_STORE_FP16_PAIRS)
+    return fail(DATR_ERR_BAD_ARGUMENT, "storage must be DATR_STORE_BF16_PAIRS or DATR_STORE_FP16_PAIRS%s");
+  if (!aligned(value, 16) || !aligned(pairs, 16)) return fail(DATR_ERR_ALIGNMENT, "value / pairs must be 16-byte aligned%s");
+  const long long total = (long long)N * S * M * 8;
+  const long long ctas = (total + 255) / 256;
+  if (ctas > 0x7fffffffLL) return fail(DATR_ERR_BAD_ARGUMENT, "grid too large%s");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (storage == DATR_STORE_BF16_PAIRS)
+    msda_pack_pairs<1><<<(unsigned)ctas, 256, 0, stream>>>(static_cast<const float*>(value), shapes, lstart, total, S, M, L,
+                                                           static_cast<uint4*>(pairs));
+  else
+    msda_pack_pairs<2><<<(unsigned)ctas, 256, 0, stream>>>(static_cast<const float*>(value), shapes, lstart, total, S, M, L,
+                                                           static_cast<uint4*>(pairs));
+  return after_launch("msda_pack_pairs");
+}
+
+int datr_msda_fused_forward_pairs(const void* pairs, int storage, const int64_t* shapes, const int64_t* lstart,
+                                  const void* offsets, long long ostride, const void* logits, long long lstride,
+                                  const void* ref, int ref_dim, int N, int S, int M, int D, int L, int Lq, int P, void* out,
+                                  void* stream_) {
+  if (int rc = check_common(pairs, shapes, lstart, offsets, logits, N, S, M, D, L, Lq, P, DATR_DTYPE_F32)) return rc;
+  if (!out) return fail(DATR_ERR_BAD_ARGUMENT, "null output pointer%s");
+  if (storage != DATR_STORE_BF16_PAIRS && storage != DATR_STORE_FP16_PAIRS)
+    return fail(DATR_ERR_BAD_ARGUMENT, "storage must be DATR_STORE_BF16_PAIRS or DATR_STORE_FP16_PAIRS%s");
+  if (int rc = check_fused(ref, ref_dim, D, P, L, DATR_DTYPE_F32)) return rc;
+  if (int rc = check_strides(&ostride, &lstride, M, L, P)) return rc;
+  if (!aligned(pairs, 16) || !aligned(out, 16) || !aligned(offsets, 8))
+    return fail(DATR_ERR_ALIGNMENT, "pairs / output must be 16-byte aligned, offsets 8-byte aligned%s");
+  return launch_fwd_fast(ref_dim == 2 ? 1 : 2, static_cast<const float*>(pairs), shapes, lstart,
+                         static_cast<const float*>(offsets), static_cast<const float*>(logits),
+                         static_cast<const float*>(ref), ostride, lstride, N, S, M, L, Lq, P, static_cast<float*>(out),
+                         static_cast<cudaStream_t>(stream_), storage);
+}
+
 int datr_msda_fused_backward(const void* value, const int64_t* shapes, const int64_t* lstart, const void* offsets,
                              long long ostride, const void* logits, long long lstride, const void* ref, int ref_dim,
                              const void* grad_out, int N, int S, int M, int D, int L, int Lq, int P, int dtype,
                              void* grad_value, void* grad_offsets, void* grad_logits, void* stream_) {
+  return datr_msda_fused_backward_hs(value, shapes, lstart, nullptr, nullptr, offsets, ostride, logits, lstride, ref, ref_dim,
+                                     grad_out, N, S, M, D, L, Lq, P, dtype, grad_value, grad_offsets, grad_logits, stream_);
+}
+
+int datr_msda_fused_backward_hs(const void* value, const int64_t* shapes, const int64_t* lstart, const int64_t* host_shapes,
+                                const int64_t* host_lstart, const void* offsets, long long ostride, const void* logits,
+                                long long lstride, const void* ref, int ref_dim, const void* grad_out, int N, int S, int M,
+                                int D, int L, int Lq, int P, int dtype, void* grad_value, void* grad_offsets,
+                                void* grad_logits, void* stream_) {
   if (int rc = check_common(value, shapes, lstart, offsets, logits, N, S, M, D, L, Lq, P, dtype)) return rc;
   if (!grad_out || !grad_value || !grad_offsets || !grad_logits) return fail(DATR_ERR_BAD_ARGUMENT, "null gradient pointer%s");
   if (int rc = check_fused(ref, ref_dim, D, P, L, dtype)) return rc;
@@ -807,11 +1065,13 @@ int datr_msda_fused_backward(const void* value, const int64_t* shapes, const int
                          static_cast<const float*>(offsets), static_cast<const float*>(logits),
                          static_cast<const float*>(ref), static_cast<const float*>(grad_out), ostride, lstride, N, S, M, L,
                          Lq, P, static_cast<float*>(grad_value), static_cast<float*>(grad_offsets),
-                         static_cast<float*>(grad_logits), stream);
+                         static_cast<float*>(grad_logits), stream, host_shapes, host_lstart);
 }
 
 const char* datr_last_error(void) { return g_err; }
-int datr_abi_version(void) { return 1; }
+int datr_abi_version(void) { return 2; }
+void datr_msda_set_backward_stages(int stages) { g_bwd_stages.store(stages < 0 ? -1 : (stages > 2 ? 2 : stages), std::memory_order_relaxed); }
+int datr_msda_get_backward_stages(void) { return bwd_stages(); }
 uint64_t datr_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 }  // extern "C"

@@ -24,6 +24,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward", "datr_msda_fused_backward", "datr_last_error", "datr_abi_version",
+           "datr_msda_backward_hs", "datr_msda_fused_backward_hs", "datr_msda_pack_value_pairs", "datr_msda_fused_forward_pairs", "datr_msda_set_backward_stages", "datr_msda_get_backward_stages",
            "datr_launch_count", "datr_linear_tf32", "datr_linear_last_error", "datr_linear_launch_count",
            "datr_layernorm256_forward", "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count",
            "datr_colsum", "datr_relu_bwd_colsum", "datr_colsum_last_error", "datr_colsum_launch_count",
@@ -106,6 +107,18 @@ def lib() -> ctypes.CDLL:
         L.datr_msda_fused_forward.argtypes = [vp, i64p, i64p, vp, ll, vp, ll, vp, i, i, i, i, i, i, i, i, i, vp, vp]
         L.datr_msda_fused_backward.restype = i
         L.datr_msda_fused_backward.argtypes = [vp, i64p, i64p, vp, ll, vp, ll, vp, i, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp]
+        L.datr_msda_backward_hs.restype = i
+        L.datr_msda_backward_hs.argtypes = [vp, i64p, i64p, i64p, i64p, vp, vp, vp, i, i, i, i, i, i, i, i, vp, vp, vp, vp]
+        L.datr_msda_fused_backward_hs.restype = i
+        L.datr_msda_fused_backward_hs.argtypes = [vp, i64p, i64p, i64p, i64p, vp, ll, vp, ll, vp, i, vp, i, i, i, i, i, i, i, i,
+                                                  vp, vp, vp, vp]
+        L.datr_msda_pack_value_pairs.restype = i
+        L.datr_msda_pack_value_pairs.argtypes = [vp, i64p, i64p, i, i, i, i, i, vp, vp]
+        L.datr_msda_fused_forward_pairs.restype = i
+        L.datr_msda_fused_forward_pairs.argtypes = [vp, i, i64p, i64p, vp, ll, vp, ll, vp, i, i, i, i, i, i, i, i, vp, vp]
+        L.datr_msda_set_backward_stages.restype = None
+        L.datr_msda_set_backward_stages.argtypes = [i]
+        L.datr_msda_get_backward_stages.restype = i
         L.datr_last_error.restype = ctypes.c_char_p
         L.datr_last_error.argtypes = []
         L.datr_abi_version.restype = i
@@ -150,7 +163,7 @@ def lib() -> ctypes.CDLL:
         L.datr_ema_update.argtypes = [vp, vp, i, ctypes.c_float, ctypes.c_float, vp]
         L.datr_ema_last_error.restype = ctypes.c_char_p
         L.datr_ema_launch_count.restype = ctypes.c_uint64
-        if L.datr_abi_version() != 1:
+        if L.datr_abi_version() != 2:
             raise NativeLibraryError("libdatr_b200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib

@@ -103,6 +103,54 @@ int datr_msda_fused_backward(const void* value, const int64_t* spatial_shapes, c
                              int channels, int num_levels, int num_query, int num_point, int dtype,
                              void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits, void* stream);
 
+/*
+ * The same two backward entry points with HOST copies of spatial_shapes / level_start_index next to the device arrays
+ * (either both or neither; NULL = not available).  With them the library can build one TMA tensor map per level over
+ * grad_value and scatter each sample's 2x2-pixel block with ONE `cp.reduce.async.bulk.tensor` instead of four vector
+ * reductions through the load/store unit (4 points, <= 4 levels of at least 2x2 pixels; selected by
+ * datr_msda_set_backward_stages, off by default); results are the same sums in a different order of additions.  The plain entry points above are these with NULL host arrays.
+ */
+int datr_msda_backward_hs(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                          const int64_t* host_spatial_shapes, const int64_t* host_level_start_index,
+                          const void* sampling_loc, const void* attn_weight, const void* grad_output,
+                          int batch, int spatial_size, int num_heads, int channels,
+                          int num_levels, int num_query, int num_point, int dtype,
+                          void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* stream);
+
+int datr_msda_fused_backward_hs(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                                const int64_t* host_spatial_shapes, const int64_t* host_level_start_index,
+                                const void* sampling_offsets, long long offsets_row_stride,
+                                const void* attn_logits, long long logits_row_stride, const void* reference_points,
+                                int ref_dim, const void* grad_output, int batch, int spatial_size, int num_heads,
+                                int channels, int num_levels, int num_query, int num_point, int dtype,
+                                void* grad_value, void* grad_sampling_offsets, void* grad_attn_logits, void* stream);
+
+/*
+ * Pair-row value maps (B200 layout, no counterpart in the reference).  The forward gather is bound by the number of
+ * 128-byte lines the L1TEX pipe serves (4 per sample with fp32 rows), not by bytes.  datr_msda_pack_value_pairs rewrites
+ * value [batch, spatial_size, heads, 32] fp32 as 16-bit PAIR rows of the same size: the line of (pixel, head) holds, for
+ * each of the 8 lanes that read it, 4 channels of the pixel followed by the same 4 channels of the pixel one column to
+ * the right (zeros in the last column of a level), so a bilinear sample needs TWO lines.  datr_msda_fused_forward_pairs is
+ * datr_msda_fused_forward on such a map (fp32 accumulation and output; 32 channels, 4 points).  Precision class: bf16
+ * storage is inside BASELINE's 1e-2 bar, fp16 storage (saturating) inside 1e-3 for |value| < 65504.
+ */
+enum { DATR_STORE_F32 = 0, DATR_STORE_BF16_PAIRS = 1, DATR_STORE_FP16_PAIRS = 2 };
+
+int datr_msda_pack_value_pairs(const void* value, const int64_t* spatial_shapes, const int64_t* level_start_index,
+                               int batch, int spatial_size, int num_heads, int num_levels, int storage, void* pairs,
+                               void* stream);
+
+int datr_msda_fused_forward_pairs(const void* pairs, int storage, const int64_t* spatial_shapes,
+                                  const int64_t* level_start_index, const void* sampling_offsets,
+                                  long long offsets_row_stride, const void* attn_logits, long long logits_row_stride,
+                                  const void* reference_points, int ref_dim, int batch, int spatial_size, int num_heads,
+                                  int channels, int num_levels, int num_query, int num_point, void* output, void* stream);
+
+/* Scatter variant of the fast backward: 0 = vector reductions, 1 / 2 = TMA reduce with that many staging buffers per
+ * warp (default 0 = the faster one on B200, see csrc/msda.cu; environment DATR_MSDA_BWD_STAGES at load time).  Process-wide. */
+void datr_msda_set_backward_stages(int stages);
+int datr_msda_get_backward_stages(void);
+
 /* Message of the last failing call made by the calling thread ("" if none). */
 const char* datr_last_error(void);
 

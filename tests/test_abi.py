@@ -31,7 +31,7 @@ def test_library_builds_loads_and_exports_all_declared_symbols():
     for name in declared_functions():
         assert hasattr(lib, name), f"{name} declared in include/ but not exported"
     assert set(native.EXPORTS) <= set(declared_functions())
-    assert lib.datr_abi_version() == 1
+    assert lib.datr_abi_version() == 2
 
 
 def test_library_is_sm100a_only():

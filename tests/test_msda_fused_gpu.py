@@ -254,3 +254,118 @@ def test_fused_error_behaviour():
     assert rc == -4 and b"fused entry points cover" in lib.datr_last_error()
     rc = lib.datr_msda_fused_forward(p, p, p, p, 5, p, 0, p, 2, 1, 1, 8, 32, 4, 1, 4, 0, p, None)
     assert rc == -1 and b"row strides" in lib.datr_last_error()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Backward scatter variants (include/datr_msda.h: datr_msda_set_backward_stages) and pair-row value maps
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.fixture
+def scatter_variant():
+    from datr_b200 import native
+    lib = native.lib()
+    yield lib.datr_msda_set_backward_stages
+    lib.datr_msda_set_backward_stages(-1)
+
+
+TMA_CASES = [c for c in CASES if c[4] == 4 and len(c[5]) <= 4 and all(h >= 2 and w >= 2 for h, w in c[5])]
+
+
+@pytest.mark.parametrize("stages", [0, 1, 2])
+@pytest.mark.parametrize("case", TMA_CASES, ids=[c[0] for c in TMA_CASES])
+def test_backward_scatter_variants_match_the_oracle(case, stages, scatter_variant):
+    """Vector reductions (0) and the TMA reduce with 1 / 2 staging buffers per warp: same sums, different order."""
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    _, N, M, Lq, P, levels, ref_dim, seed = case
+    inp = make(N, M, Lq, P, levels, ref_dim, seed)
+    d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    scatter_variant(stages)
+    assert MSDA.host_geometry(d["shapes"], d["level_start"])[0] is not None     # the TMA variants need host geometry
+    gv, goff, glg = MSDA.ms_deform_attn_fused_backward(d["value"], d["shapes"], d["level_start"], d["offsets"],
+                                                       d["logits"], d["ref"], d["grad_out"])
+    torch.cuda.synchronize()
+    want = oracle(inp, P)[1:]
+    for g, w, key in zip((gv, goff, glg), want, ("grad_value", "grad_offsets", "grad_logits")):
+        assert mc.rel_err(g.cpu().numpy().reshape(w.shape), w) < TIGHT, (key, stages)
+
+
+@pytest.mark.parametrize("stages", [1, 2])
+def test_tma_scatter_at_the_map_borders_and_beyond(stages, scatter_variant):
+    """Samples far outside the map (rejected), exactly on its border rows / columns (two of the four corners dropped)
+    and in the interior: the anchored 2x2 box of the TMA reduce carries zero weights where the reference skips a corner
+    (cuh:56-79, :288).  Compared with the vector-reduction kernel on the same inputs and with the oracle."""
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    levels = [(6, 7), (3, 4), (2, 3), (2, 2)]
+    inp = make(2, 8, 40, 4, levels, 2, 77, spread=9.0)
+    inp["ref"][:, :10] = 0.0                   # corner of the map
+    inp["ref"][:, 10:20] = 1.0
+    inp["ref"][:, 20:25] = -3.0                # every sample rejected
+    d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    args = (d["value"], d["shapes"], d["level_start"], d["offsets"], d["logits"], d["ref"], d["grad_out"])
+    scatter_variant(0)
+    base = MSDA.ms_deform_attn_fused_backward(*args)
+    scatter_variant(stages)
+    got = MSDA.ms_deform_attn_fused_backward(*args)
+    torch.cuda.synchronize()
+    want = oracle(inp, 4)[1:]
+    for g, b, w, key in zip(got, base, want, ("grad_value", "grad_offsets", "grad_logits")):
+        assert mc.rel_err(g.cpu().numpy().reshape(w.shape), w) < TIGHT, key
+        assert mc.rel_err(g.cpu().numpy(), b.cpu().numpy()) < 1e-5, key
+    assert torch.equal(got[1], base[1]) and torch.equal(got[2], base[2])   # only grad_value's summation order changes
+
+
+def test_op_backward_takes_the_tma_scatter_and_matches_the_vector_reductions(scatter_variant):
+    """The reference-ABI op (materialised locations / weights) through datr_msda_backward_hs."""
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    levels = [(9, 12), (5, 6), (3, 3), (2, 2)]
+    inp = mc.make_inputs(2, 8, 32, 50, 4, levels, "uniform", 5, np.float32)
+    d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    args = (d["value"], d["shapes"], d["level_start"], d["loc"], d["attn"], d["grad_out"], 64)
+    scatter_variant(0)
+    base = MSDA.ms_deform_attn_backward(*args)
+    scatter_variant(2)
+    got = MSDA.ms_deform_attn_backward(*args)
+    for g, b in zip(got, base):
+        assert mc.rel_err(g.cpu().numpy(), b.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("dtype,bar", [(torch.bfloat16, 1e-2), (torch.float16, 1e-3)])
+@pytest.mark.parametrize("case", [c for c in CASES if c[4] == 4], ids=[c[0] for c in CASES if c[4] == 4])
+def test_pair_row_forward(case, dtype, bar):
+    """Forward on 16-bit pair rows: (a) inside the storage type's precision class against the fp64 oracle on the fp32
+    values (bf16: BASELINE's 1e-2 bar, fp16: 1e-3), (b) equal -- up to fp32 summation order -- to the fp32-row kernel
+    on values rounded to the storage type, i.e. the rounding of the value map is the ONLY difference."""
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    _, N, M, Lq, P, levels, ref_dim, seed = case
+    inp = make(N, M, Lq, P, levels, ref_dim, seed)
+    d = {k: torch.from_numpy(v).cuda() for k, v in inp.items()}
+    pairs = MSDA.pack_value_pairs(d["value"], d["shapes"], d["level_start"], dtype)
+    assert pairs.shape == (N, d["value"].shape[1], M, 64) and pairs.dtype == dtype
+    rest = (d["shapes"], d["level_start"], d["offsets"], d["logits"], d["ref"])
+    got = MSDA.ms_deform_attn_fused_forward(d["value"], *rest, pairs=pairs)
+    rounded = MSDA.ms_deform_attn_fused_forward(d["value"].to(dtype).float(), *rest)
+    torch.cuda.synchronize()
+    want = oracle(inp, P)[0]
+    assert mc.rel_err(got.cpu().numpy().reshape(want.shape), want) < bar
+    assert mc.rel_err(got.cpu().numpy(), rounded.cpu().numpy()) < 2e-6
+
+
+def test_pair_rows_layout():
+    """Lane j of a (pixel, head) line: channels 4j..4j+3 of the pixel, then of its right-hand neighbour (zeros in the
+    last column of a level row)."""
+    from datr_b200 import MultiScaleDeformableAttention as MSDA
+    levels = [(3, 4), (2, 2), (1, 3)]
+    S = sum(h * w for h, w in levels)
+    value = torch.randn(2, S, 4, 32, device="cuda")
+    shapes = torch.tensor(levels, dtype=torch.int64, device="cuda")
+    start = torch.from_numpy(mc.level_start_index(levels)).cuda()
+    pairs = MSDA.pack_value_pairs(value, shapes, start, torch.bfloat16).float().view(2, S, 4, 8, 2, 4)
+    want = value.bfloat16().float().view(2, S, 4, 8, 4)
+    assert torch.equal(pairs[..., 0, :], want)
+    right = torch.zeros_like(want)
+    s0 = 0
+    for h, w in levels:
+        for y in range(h):
+            a = s0 + y * w
+            right[:, a:a + w - 1] = want[:, a + 1:a + w]
+        s0 += h * w
+    assert torch.equal(pairs[..., 1, :], right)

@@ -45,6 +45,10 @@ def main():
              ("cfg4_enc", 1, mc.CFG4_LEVELS, -1, "encoder"), ("cfg4_enc_init+0.3px", 1, mc.CFG4_LEVELS, -1, ("coherent", 0.3))]
     only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--cases=")]
     fused = "--fused" in sys.argv
+    # --bwd-stages=0,1,2: time the backward once per scatter variant (0 = vector reductions, 1 / 2 = TMA reduce) and
+    # compare every variant's gradients with variant 0
+    stages = [int(v) for a in sys.argv if a.startswith("--bwd-stages=") for v in a.split("=", 1)[1].split(",")]
+    from datr_b200 import native
     for name, N, levels, Lq, mode in cases:
         if only and name not in only[0]:
             continue
@@ -68,6 +72,31 @@ def main():
             tb, _ = timeit(lambda: MSDA.ms_deform_attn_fused_backward(*fa, d["grad_out"]), flush=flush)
             print(f"{name:18s} fused cold fwd {tf*1e3:8.1f} us ({fb/tf/1e6:7.1f} GB/s, {fb/tf/1e6/PEAK:5.3f}) "
                   f"bwd {tb*1e3:8.1f} us ({bb/tb/1e6:7.1f} GB/s, {bb/tb/1e6/PEAK:5.3f})", flush=True)
+            if "--pairs" in sys.argv:
+                want = MSDA.ms_deform_attn_fused_forward(*fa)
+                for dt in (torch.bfloat16, torch.float16):
+                    tp, _ = timeit(lambda: MSDA.pack_value_pairs(d["value"], d["shapes"], d["level_start"], dt), flush=flush)
+                    pairs = MSDA.pack_value_pairs(d["value"], d["shapes"], d["level_start"], dt)
+                    tf2, _ = timeit(lambda: MSDA.ms_deform_attn_fused_forward(*fa, pairs=pairs), flush=flush)
+                    got = MSDA.ms_deform_attn_fused_forward(*fa, pairs=pairs)
+                    rounded = MSDA.ms_deform_attn_fused_forward(d["value"].to(dt).float(), *fa[1:])
+                    fb2 = fb - 2 * N * S * 8 * 32       # the value map is read as 2 bytes per element
+                    print(f"{name:18s} fused fwd on {str(dt)[6:]} pair rows {tf2*1e3:8.1f} us ({fb2/tf2/1e6:7.1f} GB/s, {fb2/tf2/1e6/PEAK:5.3f}) "
+                          f"+ pack {tp*1e3:6.1f} us; max rel diff vs fp32 rows {float((got - want).abs().max() / want.abs().max()):.2e}, "
+                          f"vs fp32 rows of rounded values {float((got - rounded).abs().max() / want.abs().max()):.2e}", flush=True)
+        base = None
+        for st in stages:
+            native.lib().datr_msda_set_backward_stages(st)
+            tb, tbm = timeit(lambda: MSDA.ms_deform_attn_backward(*args, d["grad_out"], 64), flush=flush)
+            got = MSDA.ms_deform_attn_backward(*args, d["grad_out"], 64)
+            base = got if base is None else base
+            err = [float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(got, base)]
+            print(f"{name:18s} bwd scatter variant {st} (active {native.lib().datr_msda_get_backward_stages()}): {tb*1e3:8.1f} us "
+                  f"(min {tbm*1e3:8.1f}; {bb/tb/1e6:7.1f} GB/s, {bb/tb/1e6/PEAK:5.3f})  max rel diff vs variant {stages[0]}: "
+                  f"value {err[0]:.2e} loc {err[1]:.2e} attn {err[2]:.2e}", flush=True)
+        if stages:
+            native.lib().datr_msda_set_backward_stages(-1)
+            continue
         for impl, mod in (("ours", MSDA), ("ref", ref)):
             if mod is None:
                 continue
