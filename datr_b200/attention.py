@@ -64,6 +64,85 @@ class _SelfAttention(torch.autograd.Function):
         return dq.view(N, H, T, d), dk.view(N, H, T, d), dv.view(N, H, T, d), None
 
 
+def fused_applicable(qk: torch.Tensor, v: torch.Tensor, num_heads: int, blocked, dropout_p: float) -> bool:
+    """The tensor-core kernel of csrc/attn_fused.cu covers fp32 CUDA tensors, 32 channels per head, no dropout and a
+    [T, T] boolean mask (or none)."""
+    return (qk.is_cuda and qk.dtype == torch.float32 and v.dtype == torch.float32 and qk.dim() == 3 and dropout_p == 0.0
+            and v.shape[-1] == 32 * num_heads and qk.shape[-1] == 2 * v.shape[-1] and qk.is_contiguous() and v.is_contiguous()
+            and (blocked is None or (blocked.dtype == torch.bool and tuple(blocked.shape) == (qk.shape[1], qk.shape[1]))))
+
+
+def pack_mask(blocked, T: int, device) -> torch.Tensor:
+    """[T, T] bool (True = may NOT attend) or None -> bit-packed int32 [T, words] for the fused kernel (keys >= T blocked)."""
+    lib = native.lib()
+    words = lib.datr_attn_mask_words(T)
+    bits = torch.empty((T, words), dtype=torch.int32, device=device)
+    src = blocked.contiguous() if blocked is not None else None
+    with torch.cuda.device(device):
+        rc = lib.datr_attn_pack_mask(src.data_ptr() if src is not None else None, T, bits.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"datr_attn_pack_mask failed (code {rc}): {lib.datr_attn_fused_last_error().decode()}")
+    return bits
+
+
+class _FusedSelfAttention(torch.autograd.Function):
+    """qk [N, T, 2C] (queries in columns [0, C), keys in [C, 2C)), v [N, T, C], mask bits -> [N, T, C].  Forward = ONE
+    tcgen05 kernel (scores and probabilities never leave tensor memory unless a backward will follow: then the
+    probabilities are also written out for the GEMM-based backward of this module)."""
+
+    @staticmethod
+    def forward(ctx, qk, v, bits, H):
+        N, T, C = v.shape
+        d = C // H
+        scale = 1.0 / math.sqrt(d)
+        need_p = qk.requires_grad or v.requires_grad
+        lib = native.lib()
+        with torch.cuda.device(qk.device):
+            out = torch.empty((N, T, C), dtype=torch.float32, device=qk.device)
+            lse = torch.empty((N, H, T), dtype=torch.float32, device=qk.device)
+            p = torch.empty((N * H, T, T), dtype=torch.float32, device=qk.device) if need_p else None
+            rc = lib.datr_attn_fused_forward(qk.data_ptr(), 2 * C, qk.data_ptr() + 4 * C, 2 * C, v.data_ptr(), C,
+                                             bits.data_ptr(), N, H, T, scale, out.data_ptr(), lse.data_ptr(),
+                                             p.data_ptr() if p is not None else None, torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"datr_attn_fused_forward failed (code {rc}): {lib.datr_attn_fused_last_error().decode()}")
+        if need_p:
+            ctx.save_for_backward(qk, v, p)
+        ctx.scale, ctx.shape = scale, (N, H, T, d)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        qk, v, p = ctx.saved_tensors
+        N, H, T, d = ctx.shape
+        C = H * d
+        heads = lambda t: t.reshape(N, T, H, d).permute(0, 2, 1, 3).reshape(N * H, T, d)     # noqa: E731
+        q3, k3, v3, go3 = heads(qk[..., :C]), heads(qk[..., C:]), heads(v), heads(go)
+        fallbacks.note("torch.bmm (cuBLAS) decoder self-attention backward (dV, dP, dQ, dK)", 4)
+        dv = torch.bmm(p.transpose(1, 2), go3)
+        ds = torch.bmm(go3, v3.transpose(1, 2))                           # dP, turned into dS in place
+        lib = native.lib()
+        with torch.cuda.device(go.device):
+            rc = lib.datr_attn_softmax_backward(p.data_ptr(), ds.data_ptr(), ctx.scale, N * H * T, T,
+                                                torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            _raise(lib, rc, "datr_attn_softmax_backward")
+        dqk = torch.empty_like(qk).view(N, T, 2, H, d)
+        dqk[:, :, 0] = torch.bmm(ds, k3).view(N, H, T, d).permute(0, 2, 1, 3)
+        dqk[:, :, 1] = torch.bmm(ds.transpose(1, 2), q3).view(N, H, T, d).permute(0, 2, 1, 3)
+        return dqk.view(N, T, 2 * C), dv.view(N, H, T, d).permute(0, 2, 1, 3).reshape(N, T, C), None, None
+
+
+def fused_self_attention(qk, v, num_heads, blocked=None, bits=None):
+    """softmax(q k^T / sqrt(d), -inf where blocked) v for the packed projections qk [N, T, 2C], v [N, T, C]; returns
+    [N, T, C] (heads concatenated: the input of out_proj).  `bits` = pack_mask(blocked, T) if the caller already has it."""
+    if bits is None:
+        bits = pack_mask(blocked, qk.shape[1], qk.device)
+    return _FusedSelfAttention.apply(qk, v, bits, num_heads)
+
+
 def self_attention(q, k, v, blocked=None):
     """q, k, v [N, H, T, d] fp32 CUDA; blocked [T, T] bool, True = may NOT attend (nn.MultiheadAttention's convention)."""
     return _SelfAttention.apply(q, k, v, blocked)

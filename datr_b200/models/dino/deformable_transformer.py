@@ -40,6 +40,7 @@ from .utils import MLP, _get_activation_fn, gen_encoder_output_proposals, gen_si
 
 
 _OWN_ATTENTION = os.environ.get("DATR_OWN_ATTENTION", "1") != "0"
+_FUSED_ATTENTION = os.environ.get("DATR_FUSED_ATTENTION", "1") != "0"   # 0: batched GEMMs around the softmax kernel
 
 
 def _get_clones(module, N, layer_share=False):
@@ -62,16 +63,21 @@ class PackedSelfAttention(nn.Module):
         nn.init.xavier_uniform_(self.in_proj_weight)
         nn.init.constant_(self.out_proj.bias, 0.0)
 
-    def forward(self, qk_in, v_in, attn_mask=None):
+    def forward(self, qk_in, v_in, attn_mask=None, mask_bits=None):
         """qk_in, v_in: [N, T, C]; attn_mask [T, T] bool with True = blocked (nn.MultiheadAttention's
-        convention) or an additive float mask.  Returns [N, T, C]."""
+        convention) or an additive float mask; mask_bits (optional): attention.pack_mask(attn_mask, T), shared by the
+        layers of a decoder pass.  Returns [N, T, C]."""
         N, T, C = qk_in.shape
         H = self.num_heads
         qk = dl.linear(qk_in, self.in_proj_weight[:2 * C], self.in_proj_bias[:2 * C])
         v = dl.linear(v_in, self.in_proj_weight[2 * C:], self.in_proj_bias[2 * C:])
+        drop = self.dropout if self.training else 0.0
+        if _OWN_ATTENTION and _FUSED_ATTENTION and attention.fused_applicable(qk, v, H, attn_mask, drop):
+            # one tcgen05 kernel on the packed projections: no head-split copies, no score matrix in HBM
+            o = attention.fused_self_attention(qk, v, H, attn_mask, bits=mask_bits)
+            return dl.linear(o, self.out_proj.weight, self.out_proj.bias)
         q, k = qk.view(N, T, 2, H, C // H).permute(2, 0, 3, 1, 4)
         v = v.view(N, T, H, C // H).transpose(1, 2)
-        drop = self.dropout if self.training else 0.0
         if _OWN_ATTENTION and attention.applicable(q, attn_mask, drop):
             # score matrix in HBM: two batched GEMMs around the in-place masked-softmax kernel (datr_b200.attention)
             o = attention.self_attention(q, k, v, attn_mask)
@@ -201,11 +207,12 @@ class DeformableTransformerDecoderLayer(nn.Module):
             return ln(self.norm3, dl.ffn(tgt, self.linear1.weight, self.linear1.bias, self.linear2.weight, self.linear2.bias))
         return ln(self.norm3, tgt + self.dropout4(self.linear2(self.dropout3(self.activation(self.linear1(tgt))))))
 
-    def forward_sa(self, tgt, tgt_query_pos=None, self_attn_mask=None):
+    def forward_sa(self, tgt, tgt_query_pos=None, self_attn_mask=None, self_attn_mask_bits=None):
         if self.self_attn is None:
             return tgt
         qk = self.with_pos_embed(tgt, tgt_query_pos)
-        return ln(self.norm2, tgt + self.dropout2(self.self_attn(qk, tgt, attn_mask=self_attn_mask)))
+        return ln(self.norm2, tgt + self.dropout2(self.self_attn(qk, tgt, attn_mask=self_attn_mask,
+                                                                  mask_bits=self_attn_mask_bits)))
 
     def forward_ca(self, tgt, tgt_query_pos, tgt_reference_points, memory, memory_key_padding_mask,
                    memory_level_start_index, memory_spatial_shapes):
@@ -219,11 +226,12 @@ class DeformableTransformerDecoderLayer(nn.Module):
 
     def forward(self, tgt, tgt_query_pos=None, tgt_query_sine_embed=None, tgt_key_padding_mask=None,
                 tgt_reference_points=None, memory=None, memory_key_padding_mask=None, memory_level_start_index=None,
-                memory_spatial_shapes=None, memory_pos=None, self_attn_mask=None, cross_attn_mask=None):
+                memory_spatial_shapes=None, memory_pos=None, self_attn_mask=None, cross_attn_mask=None,
+                self_attn_mask_bits=None):
         """Batch-first: tgt/query_pos [N,nq,C], reference points [N,nq,L,4], memory [N,S,C]."""
         for step in self.module_seq:
             if step == "sa":
-                tgt = self.forward_sa(tgt, tgt_query_pos, self_attn_mask)
+                tgt = self.forward_sa(tgt, tgt_query_pos, self_attn_mask, self_attn_mask_bits)
             elif step == "ca":
                 tgt = self.forward_ca(tgt, tgt_query_pos, tgt_reference_points, memory, memory_key_padding_mask,
                                       memory_level_start_index, memory_spatial_shapes)
@@ -273,6 +281,11 @@ class TransformerDecoder(nn.Module):
         ref = refpoints_unsigmoid.sigmoid()
         refs, inter = [ref], []
         vr = torch.cat([valid_ratios, valid_ratios], -1)[:, None] if ref.shape[-1] == 4 else valid_ratios[:, None]
+        # the attention mask is the same for every layer: pack it once for the fused self-attention kernel
+        mask_bits = None
+        if (_OWN_ATTENTION and _FUSED_ATTENTION and tgt.is_cuda and tgt.dtype == torch.float32
+                and (tgt_mask is None or tgt_mask.dtype == torch.bool)):
+            mask_bits = attention.pack_mask(tgt_mask, tgt.shape[1], tgt.device)
         for lid, layer in enumerate(self.layers):
             if self.training and self.decoder_query_perturber is not None and lid != 0:
                 ref = self.decoder_query_perturber(ref)
@@ -280,7 +293,8 @@ class TransformerDecoder(nn.Module):
             query_pos = self.ref_point_head(gen_sineembed_for_position(ref_in[:, :, 0, :]))
             out = layer(tgt=out, tgt_query_pos=query_pos, tgt_reference_points=ref_in, memory=memory,
                         memory_key_padding_mask=memory_key_padding_mask, memory_level_start_index=level_start_index,
-                        memory_spatial_shapes=spatial_shapes, memory_pos=pos, self_attn_mask=tgt_mask)
+                        memory_spatial_shapes=spatial_shapes, memory_pos=pos, self_attn_mask=tgt_mask,
+                        self_attn_mask_bits=mask_bits)
             if self.bbox_embed is not None:
                 new_ref = (self.bbox_embed[lid](out) + inverse_sigmoid(ref)).sigmoid()
                 ref = new_ref if (self.rm_detach and "dec" in self.rm_detach) else new_ref.detach()

@@ -65,14 +65,21 @@ class MSDeformAttnMergedFunction(Function):
     projections of the query cost one GEMM forward and one dgrad + one wgrad backward."""
 
     @staticmethod
-    def forward(ctx, value, value_spatial_shapes, value_level_start_index, merged, reference_points, M, L, P):
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, merged, reference_points, M, L, P,
+                pair_dtype=None):
+        """`pair_dtype` (torch.bfloat16 / torch.float16, optional): the forward gathers from 16-bit pair rows packed
+        from `value` (include/datr_msda.h, two line gathers per sample instead of four); the backward still reads the
+        fp32 rows, so the gradients are those of the fp32 op at the rounded-value forward point."""
         N, Lq = merged.shape[:2]
         T = M * L * P
         ctx.dims = (M, L, P)
         offsets = merged[..., :2 * T].view(N, Lq, M, L, P, 2)
         logits = merged[..., 2 * T:].view(N, Lq, M, L * P)
+        pairs = None
+        if pair_dtype is not None and P == 4:
+            pairs = MSDA.pack_value_pairs(value, value_spatial_shapes, value_level_start_index, pair_dtype)
         output = MSDA.ms_deform_attn_fused_forward(value, value_spatial_shapes, value_level_start_index,
-                                                   offsets, logits, reference_points)
+                                                   offsets, logits, reference_points, pairs=pairs)
         ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, merged, reference_points)
         return output
 
@@ -87,4 +94,4 @@ class MSDeformAttnMergedFunction(Function):
         grad_value, _, _ = MSDA.ms_deform_attn_fused_backward(
             value, shapes, level_start, merged[..., :2 * T].view(N, Lq, M, L, P, 2),
             merged[..., 2 * T:].view(N, Lq, M, L * P), ref, grad_output.contiguous(), merged_grad=grad_merged)
-        return grad_value, None, None, grad_merged, None, None, None, None
+        return grad_value, None, None, grad_merged, None, None, None, None, None

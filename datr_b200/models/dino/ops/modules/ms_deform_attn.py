@@ -29,6 +29,16 @@ def set_fused(on: bool) -> None:
     _FUSED = bool(on)
 
 
+# Storage of the value map the fused forward gathers from: "fp32" (the reference's rows, default), or 16-bit pair rows
+# "bf16" / "fp16" (datr_msda_pack_value_pairs: half the line gathers per sample; precision class 1e-2 / 1e-3).
+_VALUE_STORAGE = {"fp32": None, "bf16": torch.bfloat16, "fp16": torch.float16}[os.environ.get("DATR_MSDA_VALUE", "fp32")]
+
+
+def set_value_storage(kind: str) -> None:
+    global _VALUE_STORAGE
+    _VALUE_STORAGE = {"fp32": None, "bf16": torch.bfloat16, "fp16": torch.float16}[kind]
+
+
 def _is_power_of_2(n):
     if not isinstance(n, int) or n < 0:
         raise ValueError(f"invalid input for _is_power_of_2: {n} (type: {type(n)})")
@@ -114,7 +124,7 @@ class MSDeformAttn(nn.Module):
             merged = dl.linear(query, torch.cat((self.sampling_offsets.weight, self.attention_weights.weight), 0),
                                torch.cat((self.sampling_offsets.bias, self.attention_weights.bias), 0))
             sampled = MSDeformAttnMergedFunction.apply(value, input_spatial_shapes, input_level_start_index, merged,
-                                                       reference_points.contiguous(), M, L, P)
+                                                       reference_points.contiguous(), M, L, P, _VALUE_STORAGE)
             return dl.linear(sampled, self.output_proj.weight, self.output_proj.bias, residual=residual)
 
         offsets = dl.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(N, Lq, M, L, P, 2)

@@ -30,6 +30,26 @@ enum { DATR_ATTN_OK = 0, DATR_ATTN_ERR_BAD_ARGUMENT = -1, DATR_ATTN_ERR_CUDA = -
 int datr_attn_softmax_forward(float* s, const uint8_t* blocked, float scale, long long rows, int T, int Tq, void* stream);
 int datr_attn_softmax_backward(const float* p, float* dp, float scale, long long rows, int T, void* stream);
 
+/*
+ * Fused decoder self-attention (csrc/attn_fused.cu): S = Q K^T -> masked softmax -> O = P V in one tcgen05 kernel, the score
+ * tile kept in tensor memory.  q / k / v are row-strided views of the in-projection outputs: element (n, t, h, c) of q lives
+ * at q[(n * T + t) * q_row_stride + h * 32 + c] (32 channels per head; with nn.MultiheadAttention's packed in_proj output
+ * [N, T, 2C]: q = base, k = base + C, both with row stride 2C).  Replaces torch.nn.functional.multi_head_attention_forward's
+ * bmm / softmax / bmm chain (reference models/dino/deformable_transformer.py:900-908).
+ *   datr_attn_mask_words(T)   32-bit words per row of the packed mask (4 per 128-key tile)
+ *   datr_attn_pack_mask       blocked [T, T] bytes (True = may NOT attend; NULL = no mask) -> bits [T, words]
+ *   datr_attn_fused_forward   out [N, T, H*32];  lse [N, H, T] = log sum_j exp(scale * s_ij) over the attendable keys (nullable);
+ *                             p_out [N*H, T, T] = the probabilities (nullable: only the GEMM-based backward needs them)
+ * TF32 products, fp32 accumulation / softmax.
+ */
+int datr_attn_mask_words(int T);
+int datr_attn_pack_mask(const uint8_t* blocked, int T, uint32_t* bits, void* stream);
+int datr_attn_fused_forward(const float* q, long long q_row_stride, const float* k, long long k_row_stride, const float* v,
+                            long long v_row_stride, const uint32_t* mask_bits, int N, int H, int T, float scale, float* out,
+                            float* lse, float* p_out, void* stream);
+const char* datr_attn_fused_last_error(void);
+uint64_t datr_attn_fused_launch_count(void);
+
 const char* datr_attn_last_error(void);
 uint64_t datr_attn_launch_count(void);
 

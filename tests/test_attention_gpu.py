@@ -75,3 +75,69 @@ def test_packed_self_attention_matches_nn_multihead_attention():
     yr.sum().backward()
     for y, gx in res:
         assert rel(y, yr.detach()) < 1e-4 and rel(gx, xb.grad) < 1e-4
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Fused tensor-core attention (csrc/attn_fused.cu)
+# --------------------------------------------------------------------------------------------------------------------
+def _fp64_attention(qk, v, H, blocked):
+    N, T, C2 = qk.shape
+    C, d = C2 // 2, C2 // 2 // H
+    q, k = (t.reshape(N, T, H, d).transpose(1, 2) for t in (qk[..., :C], qk[..., C:]))
+    vv = v.reshape(N, T, H, d).transpose(1, 2)
+    s = q @ k.transpose(-1, -2) / math.sqrt(d)
+    if blocked is not None:
+        s = s.masked_fill(blocked, float("-inf"))
+    p = torch.softmax(s, -1)
+    return (p @ vv).transpose(1, 2).reshape(N, T, C), p, torch.logsumexp(s, -1)
+
+
+@pytest.mark.parametrize("N,H,T,masked", [(2, 8, 1100, True), (1, 8, 900, False), (2, 4, 37, True), (1, 8, 128, True),
+                                           (1, 2, 129, False), (3, 8, 1300, True)])
+def test_fused_forward_matches_fp64_attention(N, H, T, masked):
+    """Output, log-sum-exp and probabilities of the one-kernel attention against fp64 torch arithmetic.  TF32 products
+    (10-bit mantissa) on unit-variance inputs: bar 1e-2 (BASELINE's reduced-precision class), measured ~1e-3."""
+    from datr_b200 import attention, native
+    g = torch.Generator(device="cpu").manual_seed(T + H)
+    C = 32 * H
+    qk = torch.randn(N, T, 2 * C, generator=g).cuda()
+    v = torch.randn(N, T, C, generator=g).cuda()
+    blocked = dn_mask(T, 200 if T > 300 else 20, 10, g).cuda() if masked else None
+    assert attention.fused_applicable(qk, v, H, blocked, 0.0)
+    n0 = native.attn_launch_count()
+    bits = attention.pack_mask(blocked, T, qk.device)
+    out = attention.fused_self_attention(qk, v, H, blocked, bits=bits)
+    assert native.attn_launch_count() == n0 + 2
+    want, p_want, lse_want = _fp64_attention(qk.double(), v.double(), H, blocked)
+    assert rel(out, want) < 1e-2
+    # probabilities / log-sum-exp through the raw entry point
+    lib = native.lib()
+    o2 = torch.empty_like(out)
+    lse = torch.empty(N, H, T, device="cuda")
+    p = torch.full((N * H, T, T), float("nan"), device="cuda")
+    rc = lib.datr_attn_fused_forward(qk.data_ptr(), 2 * C, qk.data_ptr() + 4 * C, 2 * C, v.data_ptr(), C, bits.data_ptr(),
+                                     N, H, T, 1.0 / math.sqrt(32), o2.data_ptr(), lse.data_ptr(), p.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(o2, out)
+    assert rel(p.view(N, H, T, T), p_want) < 1e-2
+    assert float((lse.double() - lse_want).abs().max()) < 2e-2
+    assert torch.allclose(p.sum(-1), torch.ones_like(p[..., 0]), atol=1e-5)
+    if blocked is not None:
+        assert float(p.view(N, H, T, T)[:, :, blocked].abs().max()) == 0.0
+
+
+def test_fused_attention_gradients_match_fp64():
+    from datr_b200 import attention
+    torch.backends.cuda.matmul.allow_tf32 = False
+    N, H, T = 2, 8, 333
+    g = torch.Generator(device="cpu").manual_seed(9)
+    qk = torch.randn(N, T, 512, generator=g).cuda().requires_grad_(True)
+    v = torch.randn(N, T, 256, generator=g).cuda().requires_grad_(True)
+    go = torch.randn(N, T, 256, generator=g).cuda()
+    blocked = dn_mask(T, 40, 10, g).cuda()
+    attention.fused_self_attention(qk, v, H, blocked).backward(go)
+    qd, vd = qk.detach().double().requires_grad_(True), v.detach().double().requires_grad_(True)
+    _fp64_attention(qd, vd, H, blocked)[0].backward(go.double())
+    assert rel(qk.grad, qd.grad) < 1e-2 and rel(v.grad, vd.grad) < 1e-2
