@@ -253,18 +253,228 @@ attn_fwd_tf32(const __grid_constant__ CUtensorMap map_q, const __grid_constant__
   if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Backward.  With LSE_i = log sum_j exp(scale s_ij) from the forward and delta_i = <dO_i, O_i>:
+//     P = exp(scale S - LSE),  dP = dO V^T,  dS = P o (dP - delta),  dQ = scale dS K,  dK = scale dS^T Q,  dV = P^T dO.
+// Two launches of ONE kernel template, each recomputing the score tiles it needs in tensor memory (the products are
+// cheap; nothing of size T x T ever reaches HBM):
+//   kKV = false (CTA = 128 queries, loop over key tiles; rows / TMEM lanes = queries): S = Q K^T and dP = dO V^T, dS written
+//     back over S, dQ += dS K with dS as the TMEM A operand and the K tile as MN-major B operand; also writes delta;
+//   kKV = true (CTA = 128 keys, loop over query tiles; lanes = keys): S^T = K Q^T and dP^T = V dO^T, P^T over S^T and
+//     dS^T over dP^T, dV += P^T dO and dK += dS^T Q with both A operands from tensor memory and dO / Q as MN-major B
+//     operands.  Row statistics become column statistics here: LSE and delta of the tile's 128 queries are staged in
+//     shared memory, the mask comes packed the other way round (bits along the queries).
+// Warps 0-7: elementwise (warp w owns TMEM lanes 32 (w % 4) .. +31 and columns 64 (w / 4) .. +63 of a tile), warp 8: TMA,
+// warp 9: MMA issue.  One CTA per SM (two 128-column score tiles + the accumulators need 320 TMEM columns).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kThreadsBwd = 320;
+constexpr uint32_t kTmemColsBwd = 512;
+struct BwdMaps { CUtensorMap r1, r2, c1, c2, mn1, mn2; };
+
+template <bool kKV>
+struct BwdSmem {
+  static constexpr int kStage = (kKV ? 4 : 3) * kTileBytes;
+  static constexpr int kStats = 2 * kTile * 8;
+  static constexpr int kTotal = 2 * kTileBytes + 2 * kStage + kStats + 1024 + 1024;
+};
+
+template <bool kKV>
+__global__ void __launch_bounds__(kThreadsBwd, 1)
+attn_bwd_tf32(const __grid_constant__ BwdMaps maps, const uint4* __restrict__ mask_bits, int mask_words, int H, int T,
+              float scale, const float* __restrict__ lse, float* __restrict__ delta, const float* __restrict__ dout,
+              const float* __restrict__ outp, float* __restrict__ out1, long long out1_rs, float* __restrict__ out2,
+              long long out2_rs) {
+  using L = BwdSmem<kKV>;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* r1_s = smem;
+  unsigned char* r2_s = smem + kTileBytes;
+  unsigned char* st_s = smem + 2 * kTileBytes;                               // 2 stages of {c1, c2, mn1[, mn2]}
+  float2* stats = reinterpret_cast<float2*>(smem + 2 * kTileBytes + 2 * L::kStage);   // [2][128] {LSE * log2e, delta}
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kTileBytes + 2 * L::kStage + L::kStats);
+  uint64_t* r_full = bars;
+  uint64_t* st_full = bars + 1;    // [2]
+  uint64_t* st_empty = bars + 3;   // [2]
+  uint64_t* sd_full = bars + 5;    // MMA -> elementwise: score tiles complete
+  uint64_t* e_done = bars + 6;     // elementwise -> MMA: A operands in tensor memory
+  uint64_t* acc_full = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r0 = blockIdx.x * kTile, h = blockIdx.y, n = blockIdx.z;
+  const int nt = (T + kTile - 1) / kTile;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  if (warp == 8 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.r1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.c1) : "memory");
+    mbar_init(r_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(st_full + s, 1); mbar_init(st_empty + s, 1); }
+    mbar_init(sd_full, 1);
+    mbar_init(e_done, 8);
+    mbar_init(acc_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) tmem_alloc(tmem_slot, kTmemColsBwd);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_s = tmem_base, tmem_dp = tmem_base + kTile, tmem_a1 = tmem_base + 2 * kTile, tmem_a2 = tmem_a1 + kD;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_expect_tx(r_full, 2 * kTileBytes);
+      tma_load_3d(r1_s, &maps.r1, h * kD, r0, n, r_full);
+      tma_load_3d(r2_s, &maps.r2, h * kD, r0, n, r_full);
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        unsigned char* st = st_s + s * L::kStage;
+        mbar_wait(st_empty + s, ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(st_full + s, L::kStage);
+        tma_load_3d(st, &maps.c1, h * kD, j * kTile, n, st_full + s);
+        tma_load_3d(st + kTileBytes, &maps.c2, h * kD, j * kTile, n, st_full + s);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          tma_load_3d(st + 2 * kTileBytes + c * 4096, &maps.mn1, h * kD, j * kTile + 32 * c, n, st_full + s);
+          if (kKV) tma_load_3d(st + 3 * kTileBytes + c * 4096, &maps.mn2, h * kD, j * kTile + 32 * c, n, st_full + s);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    if (lane == 0) {
+      mbar_wait(r_full, 0);
+      const uint64_t r1d = kmajor_sw128_desc(smem_u32(r1_s)), r2d = kmajor_sw128_desc(smem_u32(r2_s));
+      for (int j = 0; j < nt; ++j) {
+        const int s = j & 1;
+        const uint32_t st = smem_u32(st_s + s * L::kStage);
+        mbar_wait(st_full + s, (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t c1d = kmajor_sw128_desc(st), c2d = kmajor_sw128_desc(st + kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < kD / UMMA_K; ++kk) umma_tf32(tmem_s, r1d + uint64_t(kk * 2), c1d + uint64_t(kk * 2), kIdescS, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < kD / UMMA_K; ++kk) umma_tf32(tmem_dp, r2d + uint64_t(kk * 2), c2d + uint64_t(kk * 2), kIdescS, kk != 0);
+        umma_commit(sd_full);
+        mbar_wait(e_done, j & 1);
+        tc_fence_after();
+        const uint64_t m1d = mnmajor_desc(st + 2 * kTileBytes);
+#pragma unroll
+        for (int kk = 0; kk < kTile / UMMA_K; ++kk)
+          umma_tf32_ts(tmem_a1, tmem_s + uint32_t(kk * UMMA_K), m1d + uint64_t(kk * 64), kIdescPV, (j | kk) != 0);
+        if (kKV) {
+          const uint64_t m2d = mnmajor_desc(st + 3 * kTileBytes);
+#pragma unroll
+          for (int kk = 0; kk < kTile / UMMA_K; ++kk)
+            umma_tf32_ts(tmem_a2, tmem_dp + uint32_t(kk * UMMA_K), m2d + uint64_t(kk * 64), kIdescPV, (j | kk) != 0);
+        }
+        umma_commit(st_empty + s);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // elementwise warps: TMEM lane = row of the CTA's tile, columns [col0, col0 + 64) of every score tile
+    const int quarter = warp & 3, col0 = (warp >> 2) * 64;
+    const int row = r0 + quarter * 32 + lane;
+    const bool live = row < T;
+    const uint32_t lane_addr = uint32_t(quarter * 32) << 16;
+    const uint4* mrow = mask_bits + (size_t)(live ? row : 0) * (mask_words / 4);
+    const int e = threadIdx.x;                                   // 0 .. 255
+    const float sl2 = scale * kLog2e;
+    float my_lse2 = 0.f, my_delta = 0.f;
+    if (!kKV) {
+      // rows are queries: LSE of the row, delta = <dO_row, O_row> over this head's channels (written out for the kKV pass)
+      if (live) {
+        const float4* a = reinterpret_cast<const float4*>(dout + ((size_t)n * T + row) * (size_t)(H * kD) + h * kD);
+        const float4* b = reinterpret_cast<const float4*>(outp + ((size_t)n * T + row) * (size_t)(H * kD) + h * kD);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 x = __ldg(a + i), y = __ldg(b + i);
+          my_delta += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+        }
+        my_lse2 = __ldg(lse + ((size_t)n * H + h) * T + row) * kLog2e;
+        if (col0 == 0) delta[((size_t)n * H + h) * T + row] = my_delta;
+      }
+    }
+    for (int j = 0; j < nt; ++j) {
+      if (kKV) {
+        // columns are queries: stage {LSE * log2e, delta} of the tile's queries
+        if (e < kTile) {
+          const int q = j * kTile + e;
+          float2 sd = make_float2(0.f, 0.f);
+          if (q < T) sd = make_float2(__ldg(lse + ((size_t)n * H + h) * T + q) * kLog2e, __ldg(delta + ((size_t)n * H + h) * T + q));
+          stats[(j & 1) * kTile + e] = sd;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      }
+      const uint4 mw = __ldg(mrow + j);
+      const uint32_t words[4] = {mw.x, mw.y, mw.z, mw.w};
+      mbar_wait(sd_full, j & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int cc = col0 + c * 32;
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tmem_s + lane_addr + uint32_t(cc), sv);
+        tmem_ld32(tmem_dp + lane_addr + uint32_t(cc), dv);
+        const uint32_t blocked = words[cc >> 5];
+        const float2* sc = stats + (j & 1) * kTile + cc;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          float lse2 = my_lse2, dl = my_delta;
+          if (kKV) { const float2 t = sc[i]; lse2 = t.x; dl = t.y; }
+          const float p = ((blocked >> i) & 1u) ? 0.f : exp2f(__uint_as_float(sv[i]) * sl2 - lse2);
+          const float ds = p * (__uint_as_float(dv[i]) - dl);
+          if (kKV) { sv[i] = __float_as_uint(p); dv[i] = __float_as_uint(ds); }
+          else sv[i] = __float_as_uint(ds);
+        }
+        tmem_st32(tmem_s + lane_addr + uint32_t(cc), sv);
+        if (kKV) tmem_st32(tmem_dp + lane_addr + uint32_t(cc), dv);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(e_done);
+    }
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    // epilogue: warps 0-3 write accumulator 1 (dQ * scale, or dV), warps 4-7 accumulator 2 (dK * scale; kKV only)
+    if (col0 == 0 || kKV) {
+      uint32_t o[32];
+      tmem_ld32((col0 == 0 ? tmem_a1 : tmem_a2) + lane_addr, o);
+      if (live) {
+        float* dst = col0 == 0 ? out1 + ((size_t)n * T + row) * (size_t)out1_rs + h * kD
+                               : out2 + ((size_t)n * T + row) * (size_t)out2_rs + h * kD;
+        const float f = (col0 == 0 && kKV) ? 1.f : scale;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(__uint_as_float(o[i]) * f, __uint_as_float(o[i + 1]) * f,
+                                                            __uint_as_float(o[i + 2]) * f, __uint_as_float(o[i + 3]) * f);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc(tmem_base, kTmemColsBwd);
+}
+
 // blocked [T, T] bytes (or null) -> bits [T, words] (words = 4 * ceil(T / 128)), bit i of word w = key 32 w + i may NOT be
 // attended; keys >= T are always blocked
-__global__ void attn_pack_mask(const uint8_t* __restrict__ blocked, int T, int words, uint32_t* __restrict__ bits) {
+// `bits_t` (optional, same shape): the transposed mask, bit i of word w of row r = query 32 w + i may not attend key r
+__global__ void attn_pack_mask(const uint8_t* __restrict__ blocked, int T, int words, uint32_t* __restrict__ bits,
+                               uint32_t* __restrict__ bits_t) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= T * words) return;
   const int r = idx / words, w = idx % words;
-  uint32_t b = 0;
+  uint32_t b = 0, bt = 0;
   for (int i = 0; i < 32; ++i) {
-    const int key = w * 32 + i;
-    if (key >= T || (blocked != nullptr && blocked[(size_t)r * T + key])) b |= 1u << i;
+    const int c = w * 32 + i;
+    if (c >= T || (blocked != nullptr && blocked[(size_t)r * T + c])) b |= 1u << i;
+    if (bits_t != nullptr && (c >= T || (blocked != nullptr && blocked[(size_t)c * T + r]))) bt |= 1u << i;
   }
   bits[idx] = b;
+  if (bits_t != nullptr) bits_t[idx] = bt;
 }
 
 int encode3(CUtensorMap* map, const float* base, long long row_stride, int channels, int T, int N, int box_rows, bool mn_major) {
@@ -290,11 +500,11 @@ extern "C" {
 
 int datr_attn_mask_words(int T) { return 4 * ((T + kTile - 1) / kTile); }
 
-int datr_attn_pack_mask(const uint8_t* blocked, int T, uint32_t* bits, void* stream_) {
+int datr_attn_pack_mask(const uint8_t* blocked, int T, uint32_t* bits, uint32_t* bits_t, void* stream_) {
   if (!bits || T <= 0) return ffail(DATR_ATTN_ERR_BAD_ARGUMENT, "bad argument%s");
   const int words = datr_attn_mask_words(T);
   const int total = T * words;
-  attn_pack_mask<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(blocked, T, words, bits);
+  attn_pack_mask<<<(total + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream_)>>>(blocked, T, words, bits, bits_t);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ffail(DATR_ATTN_ERR_CUDA, "attn_pack_mask launch: %s", cudaGetErrorString(e));
   g_af_launches.fetch_add(1, std::memory_order_relaxed);
@@ -333,6 +543,58 @@ int datr_attn_fused_forward(const float* q, long long q_row_stride, const float*
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return ffail(DATR_ATTN_ERR_CUDA, "attn_fwd_tf32 launch: %s", cudaGetErrorString(e));
   g_af_launches.fetch_add(1, std::memory_order_relaxed);
+  return DATR_ATTN_OK;
+}
+
+int datr_attn_fused_backward(const float* q, long long q_row_stride, const float* k, long long k_row_stride, const float* v,
+                             long long v_row_stride, const uint32_t* mask_bits, const uint32_t* mask_bits_t, int N, int H,
+                             int T, float scale, const float* out, const float* lse, const float* dout, float* delta,
+                             float* dq, long long dq_row_stride, float* dk, long long dk_row_stride, float* dv,
+                             long long dv_row_stride, void* stream_) {
+  if (!q || !k || !v || !mask_bits || !mask_bits_t || !out || !lse || !dout || !delta || !dq || !dk || !dv)
+    return ffail(DATR_ATTN_ERR_BAD_ARGUMENT, "null pointer argument%s");
+  if (N <= 0 || H <= 0 || T <= 0 || T > 65535) return ffail(DATR_ATTN_ERR_BAD_ARGUMENT, "bad dimensions%s");
+  const long long need = (long long)H * kD;
+  const long long strides[6] = {q_row_stride, k_row_stride, v_row_stride, dq_row_stride, dk_row_stride, dv_row_stride};
+  for (long long st : strides)
+    if (st < need || (st & 3)) return ffail(DATR_ATTN_ERR_BAD_ARGUMENT, "row strides must cover H * 32 channels and be multiples of 4 elements%s");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(q) || !al16(k) || !al16(v) || !al16(out) || !al16(dout) || !al16(dq) || !al16(dk) || !al16(dv) || !al16(mask_bits) ||
+      !al16(mask_bits_t))
+    return ffail(DATR_ATTN_ERR_BAD_ARGUMENT, "buffers must be 16-byte aligned%s");
+  const int C = H * kD;
+  CUtensorMap q_k, q_mn, k_k, k_mn, v_k, do_k, do_mn;
+  if (int rc = encode3(&q_k, q, q_row_stride, C, T, N, kTile, false)) return rc;
+  if (int rc = encode3(&q_mn, q, q_row_stride, C, T, N, 32, true)) return rc;
+  if (int rc = encode3(&k_k, k, k_row_stride, C, T, N, kTile, false)) return rc;
+  if (int rc = encode3(&k_mn, k, k_row_stride, C, T, N, 32, true)) return rc;
+  if (int rc = encode3(&v_k, v, v_row_stride, C, T, N, kTile, false)) return rc;
+  if (int rc = encode3(&do_k, dout, C, C, T, N, kTile, false)) return rc;
+  if (int rc = encode3(&do_mn, dout, C, C, T, N, 32, true)) return rc;
+  static std::atomic<uint64_t> opted{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(opted.load(std::memory_order_acquire) & bit)) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_tf32<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<false>::kTotal);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_tf32<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem<true>::kTotal);
+    if (e != cudaSuccess) return ffail(DATR_ATTN_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    opted.fetch_or(bit, std::memory_order_release);
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const dim3 grid((T + kTile - 1) / kTile, H, N);
+  const int words = datr_attn_mask_words(T);
+  // pass 1 (rows = queries): dQ and delta;  rows Q, dO; columns K, V; MN-major K
+  BwdMaps m1 = {q_k, do_k, k_k, v_k, k_mn, k_mn};
+  attn_bwd_tf32<false><<<grid, kThreadsBwd, BwdSmem<false>::kTotal, stream>>>(
+      m1, reinterpret_cast<const uint4*>(mask_bits), words, H, T, scale, lse, delta, dout, out, dq, dq_row_stride, nullptr, 0);
+  // pass 2 (rows = keys): dV and dK;  rows K, V; columns Q, dO; MN-major dO and Q
+  BwdMaps m2 = {k_k, v_k, q_k, do_k, do_mn, q_mn};
+  attn_bwd_tf32<true><<<grid, kThreadsBwd, BwdSmem<true>::kTotal, stream>>>(
+      m2, reinterpret_cast<const uint4*>(mask_bits_t), words, H, T, scale, lse, delta, dout, out, dv, dv_row_stride, dk, dk_row_stride);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return ffail(DATR_ATTN_ERR_CUDA, "attn_bwd_tf32 launch: %s", cudaGetErrorString(e));
+  g_af_launches.fetch_add(2, std::memory_order_relaxed);
   return DATR_ATTN_OK;
 }
 

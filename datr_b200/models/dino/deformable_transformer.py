@@ -43,6 +43,12 @@ _OWN_ATTENTION = os.environ.get("DATR_OWN_ATTENTION", "1") != "0"
 _FUSED_ATTENTION = os.environ.get("DATR_FUSED_ATTENTION", "1") != "0"   # 0: batched GEMMs around the softmax kernel
 
 
+def _fused_attention_on():
+    """The tensor-core attention kernels multiply in TF32: they belong to the 'tf32' mode of datr_b200.linear (the
+    benchmarked mode); the strict-fp32 mode keeps fp32 products (batched GEMMs around the softmax kernel)."""
+    return _OWN_ATTENTION and _FUSED_ATTENTION and dl.get_mode() == "tf32"
+
+
 def _get_clones(module, N, layer_share=False):
     if layer_share:
         return nn.ModuleList([module for _ in range(N)])
@@ -72,7 +78,7 @@ class PackedSelfAttention(nn.Module):
         qk = dl.linear(qk_in, self.in_proj_weight[:2 * C], self.in_proj_bias[:2 * C])
         v = dl.linear(v_in, self.in_proj_weight[2 * C:], self.in_proj_bias[2 * C:])
         drop = self.dropout if self.training else 0.0
-        if _OWN_ATTENTION and _FUSED_ATTENTION and attention.fused_applicable(qk, v, H, attn_mask, drop):
+        if _fused_attention_on() and attention.fused_applicable(qk, v, H, attn_mask, drop):
             # one tcgen05 kernel on the packed projections: no head-split copies, no score matrix in HBM
             o = attention.fused_self_attention(qk, v, H, attn_mask, bits=mask_bits)
             return dl.linear(o, self.out_proj.weight, self.out_proj.bias)
@@ -283,9 +289,9 @@ class TransformerDecoder(nn.Module):
         vr = torch.cat([valid_ratios, valid_ratios], -1)[:, None] if ref.shape[-1] == 4 else valid_ratios[:, None]
         # the attention mask is the same for every layer: pack it once for the fused self-attention kernel
         mask_bits = None
-        if (_OWN_ATTENTION and _FUSED_ATTENTION and tgt.is_cuda and tgt.dtype == torch.float32
+        if (_fused_attention_on() and tgt.is_cuda and tgt.dtype == torch.float32
                 and (tgt_mask is None or tgt_mask.dtype == torch.bool)):
-            mask_bits = attention.pack_mask(tgt_mask, tgt.shape[1], tgt.device)
+            mask_bits = attention.pack_mask(tgt_mask, tgt.shape[1], tgt.device, transposed=torch.is_grad_enabled())
         for lid, layer in enumerate(self.layers):
             if self.training and self.decoder_query_perturber is not None and lid != 0:
                 ref = self.decoder_query_perturber(ref)

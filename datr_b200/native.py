@@ -33,7 +33,7 @@ EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward",
            "datr_linear_wgrad_tf32", "datr_linear_wgrad_last_error", "datr_linear_wgrad_launch_count",
            "datr_zero_masked_rows", "datr_rowmask_last_error", "datr_rowmask_launch_count",
            "datr_attn_softmax_forward", "datr_attn_softmax_backward", "datr_attn_last_error", "datr_attn_launch_count",
-           "datr_attn_mask_words", "datr_attn_pack_mask", "datr_attn_fused_forward", "datr_attn_fused_last_error",
+           "datr_attn_mask_words", "datr_attn_pack_mask", "datr_attn_fused_forward", "datr_attn_fused_backward", "datr_attn_fused_last_error",
            "datr_attn_fused_launch_count",
            "datr_ema_update", "datr_ema_last_error", "datr_ema_launch_count")
 
@@ -165,7 +165,10 @@ def lib() -> ctypes.CDLL:
         L.datr_attn_mask_words.restype = i
         L.datr_attn_mask_words.argtypes = [i]
         L.datr_attn_pack_mask.restype = i
-        L.datr_attn_pack_mask.argtypes = [vp, i, vp, vp]
+        L.datr_attn_pack_mask.argtypes = [vp, i, vp, vp, vp]
+        L.datr_attn_fused_backward.restype = i
+        L.datr_attn_fused_backward.argtypes = [vp, ll, vp, ll, vp, ll, vp, vp, i, i, i, ctypes.c_float, vp, vp, vp, vp,
+                                               vp, ll, vp, ll, vp, ll, vp]
         L.datr_attn_fused_forward.restype = i
         L.datr_attn_fused_forward.argtypes = [vp, ll, vp, ll, vp, ll, vp, i, i, i, ctypes.c_float, vp, vp, vp, vp]
         L.datr_attn_fused_last_error.restype = ctypes.c_char_p

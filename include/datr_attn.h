@@ -37,16 +37,27 @@ int datr_attn_softmax_backward(const float* p, float* dp, float scale, long long
  * [N, T, 2C]: q = base, k = base + C, both with row stride 2C).  Replaces torch.nn.functional.multi_head_attention_forward's
  * bmm / softmax / bmm chain (reference models/dino/deformable_transformer.py:900-908).
  *   datr_attn_mask_words(T)   32-bit words per row of the packed mask (4 per 128-key tile)
- *   datr_attn_pack_mask       blocked [T, T] bytes (True = may NOT attend; NULL = no mask) -> bits [T, words]
+ *   datr_attn_pack_mask       blocked [T, T] bytes (True = may NOT attend; NULL = no mask) -> bits [T, words] and, for the
+ *                             backward, bits_t [T, words] (the mask transposed: bits along the queries)
  *   datr_attn_fused_forward   out [N, T, H*32];  lse [N, H, T] = log sum_j exp(scale * s_ij) over the attendable keys (nullable);
  *                             p_out [N*H, T, T] = the probabilities (nullable: only the GEMM-based backward needs them)
  * TF32 products, fp32 accumulation / softmax.
  */
 int datr_attn_mask_words(int T);
-int datr_attn_pack_mask(const uint8_t* blocked, int T, uint32_t* bits, void* stream);
+int datr_attn_pack_mask(const uint8_t* blocked, int T, uint32_t* bits, uint32_t* bits_t /* nullable: transposed mask */, void* stream);
 int datr_attn_fused_forward(const float* q, long long q_row_stride, const float* k, long long k_row_stride, const float* v,
                             long long v_row_stride, const uint32_t* mask_bits, int N, int H, int T, float scale, float* out,
                             float* lse, float* p_out, void* stream);
+/*
+ *   datr_attn_fused_backward  dq / dk / dv (row-strided like q / k / v) from dout [N, T, H*32], the forward's out and lse; two
+ *                             launches (dQ + delta, then dK + dV), score tiles recomputed in tensor memory; `mask_bits_t` =
+ *                             the transposed packed mask (second output of datr_attn_pack_mask); `delta` [N, H, T] scratch.
+ */
+int datr_attn_fused_backward(const float* q, long long q_row_stride, const float* k, long long k_row_stride, const float* v,
+                             long long v_row_stride, const uint32_t* mask_bits, const uint32_t* mask_bits_t, int N, int H,
+                             int T, float scale, const float* out, const float* lse, const float* dout, float* delta,
+                             float* dq, long long dq_row_stride, float* dk, long long dk_row_stride, float* dv,
+                             long long dv_row_stride, void* stream);
 const char* datr_attn_fused_last_error(void);
 uint64_t datr_attn_fused_launch_count(void);
 

@@ -105,8 +105,9 @@ def test_fused_forward_matches_fp64_attention(N, H, T, masked):
     blocked = dn_mask(T, 200 if T > 300 else 20, 10, g).cuda() if masked else None
     assert attention.fused_applicable(qk, v, H, blocked, 0.0)
     n0 = native.attn_launch_count()
-    bits = attention.pack_mask(blocked, T, qk.device)
-    out = attention.fused_self_attention(qk, v, H, blocked, bits=bits)
+    both = attention.pack_mask(blocked, T, qk.device)
+    bits = both[0]
+    out = attention.fused_self_attention(qk, v, H, blocked, bits=both)
     assert native.attn_launch_count() == n0 + 2
     want, p_want, lse_want = _fp64_attention(qk.double(), v.double(), H, blocked)
     assert rel(out, want) < 1e-2
@@ -128,16 +129,26 @@ def test_fused_forward_matches_fp64_attention(N, H, T, masked):
         assert float(p.view(N, H, T, T)[:, :, blocked].abs().max()) == 0.0
 
 
-def test_fused_attention_gradients_match_fp64():
-    from datr_b200 import attention
+@pytest.mark.parametrize("backward", ["fused", "gemm"])
+@pytest.mark.parametrize("N,H,T,masked", [(2, 8, 333, True), (1, 8, 1100, True), (2, 4, 128, False), (1, 2, 37, True),
+                                           (1, 8, 900, False)])
+def test_fused_attention_gradients_match_fp64(N, H, T, masked, backward, monkeypatch):
+    """dQ, dK, dV of the tensor-core backward (two launches, score tiles rebuilt in tensor memory) and of the GEMM-based
+    backward on the stored probabilities, against fp64 autograd.  TF32 products: bar 1e-2."""
+    from datr_b200 import attention, native
     torch.backends.cuda.matmul.allow_tf32 = False
-    N, H, T = 2, 8, 333
-    g = torch.Generator(device="cpu").manual_seed(9)
-    qk = torch.randn(N, T, 512, generator=g).cuda().requires_grad_(True)
-    v = torch.randn(N, T, 256, generator=g).cuda().requires_grad_(True)
-    go = torch.randn(N, T, 256, generator=g).cuda()
-    blocked = dn_mask(T, 40, 10, g).cuda()
+    monkeypatch.setattr(attention, "_BACKWARD", backward)
+    g = torch.Generator(device="cpu").manual_seed(9 + T)
+    C = 32 * H
+    qk = torch.randn(N, T, 2 * C, generator=g).cuda().requires_grad_(True)
+    v = torch.randn(N, T, C, generator=g).cuda().requires_grad_(True)
+    go = torch.randn(N, T, C, generator=g).cuda()
+    blocked = dn_mask(T, 40 if T > 100 else 20, 10, g).cuda() if masked else None
+    n0 = native.attn_launch_count()
     attention.fused_self_attention(qk, v, H, blocked).backward(go)
+    assert native.attn_launch_count() == n0 + (4 if backward == "fused" else 3)
     qd, vd = qk.detach().double().requires_grad_(True), v.detach().double().requires_grad_(True)
     _fp64_attention(qd, vd, H, blocked)[0].backward(go.double())
-    assert rel(qk.grad, qd.grad) < 1e-2 and rel(v.grad, vd.grad) < 1e-2
+    assert rel(qk.grad[..., :C], qd.grad[..., :C]) < 1e-2, "dq"
+    assert rel(qk.grad[..., C:], qd.grad[..., C:]) < 1e-2, "dk"
+    assert rel(v.grad, vd.grad) < 1e-2, "dv"

@@ -29,6 +29,7 @@ for N, H, T in ((4, 8, 1100), (2, 8, 1100), (4, 8, 900)):
     qk = torch.randn(N, T, 2 * C, device="cuda"); v = torch.randn(N, T, C, device="cuda")
     blocked = dn_mask(T, 200, 10, None).cuda()
     bits = attention.pack_mask(blocked, T, qk.device)
+    attention._BACKWARD = "fused"
     go = torch.randn(N, T, C, device="cuda")
     q4, k4 = (t.reshape(N, T, H, 32).transpose(1, 2) for t in (qk[..., :C], qk[..., C:]))
     v4 = v.reshape(N, T, H, 32).transpose(1, 2)
@@ -38,6 +39,7 @@ for N, H, T in ((4, 8, 1100), (2, 8, 1100), (4, 8, 900)):
         t_old = timeit(lambda: attention.self_attention(q4, k4, v4, blocked))
         t_sdpa = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q4, k4, v4, attn_mask=~blocked))
     qk_g, v_g = qk.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    attention._BACKWARD = "gemm"
     t_fused_p = timeit(lambda: attention.fused_self_attention(qk_g, v_g, H, blocked, bits=bits))
 
     def fb_new():
@@ -47,7 +49,9 @@ for N, H, T in ((4, 8, 1100), (2, 8, 1100), (4, 8, 900)):
         q_, k_ = (t.reshape(N, T, H, 32).transpose(1, 2) for t in (qk_g[..., :C], qk_g[..., C:]))
         attention.self_attention(q_, k_, v_g.reshape(N, T, H, 32).transpose(1, 2), blocked).transpose(1, 2).reshape(N, T, C).backward(go)
     t_fb_new, t_fb_old = timeit(fb_new), timeit(fb_old)
+    attention._BACKWARD = "fused"
+    t_fb_fused = timeit(fb_new)
     flops = 4.0 * N * H * T * T * 32
     print(f"N={N} H={H} T={T}: fused fwd {t_fused:7.1f} us ({flops / t_fused / 1e6:6.1f} TFLOP/s) | fused fwd + probabilities out "
           f"{t_fused_p:7.1f} | bmm+softmax+bmm fwd {t_old:7.1f} | SDPA fwd {t_sdpa:7.1f} | mask pack {t_pack:5.1f} | "
-          f"fwd+bwd: fused fwd + GEMM bwd {t_fb_new:7.1f}, round-1 path {t_fb_old:7.1f}", flush=True)
+          f"fwd+bwd: fused fwd + fused bwd {t_fb_fused:7.1f}, fused fwd + GEMM bwd {t_fb_new:7.1f}, round-1 path {t_fb_old:7.1f}", flush=True)
