@@ -498,6 +498,9 @@ class DeformableTransformer(nn.Module):
         else:
             src_flat, pos_flat, mask_flat, valid_ratios = self._flatten_levels(tuple(srcs), tuple(masks), tuple(pos_embeds))
         spatial_shapes, level_start_index = self._shape_tensors(shapes_list, src_flat.device)
+        # outputs of a graph segment all come back as differentiable (one autograd node per segment); the geometry is
+        # not -- and reference points that "require grad" would push MSDeformAttn off its fused kernels
+        valid_ratios = valid_ratios.detach()
 
         if graphs.ACTIVE is not None and src_flat.is_cuda:
             memory = graphs.ACTIVE.run("encoder", lambda: graphs.EncoderSegment(self.encoder, shapes_list),
@@ -531,6 +534,10 @@ class DeformableTransformer(nn.Module):
         else:
             sel = self._select_queries(memory, mask_flat, refpoint_embed, tgt, tuple(shapes_list))
         refpoint_embed, tgt, tgt_undetach, refpoint_undetach, init_box_proposal, output_memory, coord_all, output_proposals = sel
+        # the decoder's reference boxes carry no gradient (selected proposals are detached, :345 of the reference; the
+        # de-noising boxes are inputs); as the output of a graph segment they would look differentiable
+        if self.two_stage_type == "standard":      # 'no': the learnable refpoint_embed receives gradients through the decoder
+            refpoint_embed = refpoint_embed.detach()
 
         if graphs.ACTIVE is not None and tgt.is_cuda:
             dec_args = (tgt, memory, mask_flat, pos_flat, refpoint_embed, level_start_index, spatial_shapes, valid_ratios)

@@ -52,4 +52,16 @@ with open(out, "w") as f:
         top = sorted(names.items(), key=lambda x: -x[1][0])[:4]
         f.write(f"{(s - t0) / 1e3:7.2f} | {(t - s) / 1e3:7.2f} | {busy / 1e3:7.2f} | {len(evs):5d} | {short:5d} | {key[0]:5s} | "
                 + "; ".join(f"{n} {c[0] / 1e3:.2f}/{c[1]}" for n, c in top) + "\n")
+# ordered kernel list of every group with more than 100 kernels (what a fused kernel per chain would replace)
+detail = os.path.join(ROOT, "gpurun_out", "dino_step_timeline_detail.txt")
+with open(detail, "w") as f:
+    for key, evs in groups:
+        if len(evs) <= 100:
+            continue
+        f.write(f"== group at {(evs[0]['ts'] - t0) / 1e3:.2f} ms, {len(evs)} kernels\n")
+        prev_end = evs[0]["ts"]
+        for e in evs:
+            name = e["name"].replace("void ", "").replace("(anonymous namespace)::", "").replace("at::native::", "")
+            f.write(f"{e['dur']:7.1f} us  gap {max(0.0, e['ts'] - prev_end):5.1f}  {name[:150]}\n")
+            prev_end = e["ts"] + e["dur"]
 print(open(out).read()[:12000])
