@@ -69,7 +69,7 @@ class PackedSelfAttention(nn.Module):
         nn.init.xavier_uniform_(self.in_proj_weight)
         nn.init.constant_(self.out_proj.bias, 0.0)
 
-    def forward(self, qk_in, v_in, attn_mask=None, mask_bits=None):
+    def forward(self, qk_in, v_in, attn_mask=None, mask_bits=None, residual=None):
         """qk_in, v_in: [N, T, C]; attn_mask [T, T] bool with True = blocked (nn.MultiheadAttention's
         convention) or an additive float mask; mask_bits (optional): attention.pack_mask(attn_mask, T), shared by the
         layers of a decoder pass.  Returns [N, T, C]."""
@@ -81,7 +81,7 @@ class PackedSelfAttention(nn.Module):
         if _fused_attention_on() and attention.fused_applicable(qk, v, H, attn_mask, drop):
             # one tcgen05 kernel on the packed projections: no head-split copies, no score matrix in HBM
             o = attention.fused_self_attention(qk, v, H, attn_mask, bits=mask_bits)
-            return dl.linear(o, self.out_proj.weight, self.out_proj.bias)
+            return dl.linear(o, self.out_proj.weight, self.out_proj.bias, residual=residual)
         q, k = qk.view(N, T, 2, H, C // H).permute(2, 0, 3, 1, 4)
         v = v.view(N, T, H, C // H).transpose(1, 2)
         if _OWN_ATTENTION and attention.applicable(q, attn_mask, drop):
@@ -91,7 +91,7 @@ class PackedSelfAttention(nn.Module):
             if attn_mask is not None and attn_mask.dtype == torch.bool:
                 attn_mask = ~attn_mask                      # SDPA: True = may attend
             o = F.scaled_dot_product_attention(q, k, v, attn_mask=attn_mask, dropout_p=drop)
-        return dl.linear(o.transpose(1, 2).reshape(N, T, C), self.out_proj.weight, self.out_proj.bias)
+        return dl.linear(o.transpose(1, 2).reshape(N, T, C), self.out_proj.weight, self.out_proj.bias, residual=residual)
 
 
 def _fusable(layer, *dropouts):
@@ -217,6 +217,9 @@ class DeformableTransformerDecoderLayer(nn.Module):
         if self.self_attn is None:
             return tgt
         qk = self.with_pos_embed(tgt, tgt_query_pos)
+        if _fusable(self, self.dropout2):     # residual add in the output projection's epilogue
+            return ln(self.norm2, self.self_attn(qk, tgt, attn_mask=self_attn_mask, mask_bits=self_attn_mask_bits,
+                                                 residual=tgt))
         return ln(self.norm2, tgt + self.dropout2(self.self_attn(qk, tgt, attn_mask=self_attn_mask,
                                                                   mask_bits=self_attn_mask_bits)))
 

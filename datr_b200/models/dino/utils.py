@@ -94,12 +94,37 @@ def _get_activation_fn(activation, d_model=256, batch_dim=0):
     return table[activation]
 
 
+_DIM_T = {}
+
+
+def _sine_dim_t(device):
+    """10000 ** (2 * (i // 2) / 128), i = 0..127, computed by torch (once per device, outside of graph capture)."""
+    t = _DIM_T.get(str(device))
+    if t is None:
+        idx = torch.arange(128, dtype=torch.float32, device=device)
+        t = _DIM_T[str(device)] = 10000 ** (2 * torch.div(idx, 2, rounding_mode="floor") / 128)
+    return t
+
+
 def gen_sineembed_for_position(pos_tensor):
     """[..., 2|4] normalised (x, y[, w, h]) -> [..., 128 * k] sine embedding ordered (y, x[, w, h]);
-    128 features per coordinate, temperature 10000, sin on even / cos on odd feature indices."""
+    128 features per coordinate, temperature 10000, sin on even / cos on odd feature indices.
+    CUDA fp32 input without gradient (the decoder's detached reference boxes): one kernel (csrc/decoder_ops.cu)."""
     k = pos_tensor.size(-1)
     if k not in (2, 4):
         raise ValueError(f"Unknown pos_tensor shape(-1):{k}")
+    if (pos_tensor.is_cuda and pos_tensor.dtype == torch.float32 and not pos_tensor.requires_grad
+            and (str(pos_tensor.device) in _DIM_T or not torch.cuda.is_current_stream_capturing())):
+        from datr_b200 import native
+        lib = native.lib()
+        src = pos_tensor.contiguous()
+        out = torch.empty(pos_tensor.shape[:-1] + (128 * k,), dtype=torch.float32, device=pos_tensor.device)
+        with torch.cuda.device(pos_tensor.device):
+            rc = lib.datr_sine_embed(src.data_ptr(), _sine_dim_t(pos_tensor.device).data_ptr(), src.numel() // k, k,
+                                     out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"datr_sine_embed failed (code {rc}): {lib.datr_decoder_ops_last_error().decode()}")
+        return out
     idx = torch.arange(128, dtype=torch.float32, device=pos_tensor.device)
     dim_t = 10000 ** (2 * torch.div(idx, 2, rounding_mode="floor") / 128)
     ang = pos_tensor.unsqueeze(-1) * (2 * math.pi) / dim_t                       # [..., k, 128]

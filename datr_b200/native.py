@@ -17,7 +17,7 @@ SOURCES = [os.path.join(_PKG, "csrc", "msda.cu"), os.path.join(_PKG, "csrc", "li
            os.path.join(_PKG, "csrc", "layernorm.cu"), os.path.join(_PKG, "csrc", "colsum.cu"),
            os.path.join(_PKG, "csrc", "conv3x3_tf32.cu"), os.path.join(_PKG, "csrc", "wgrad_tf32.cu"),
            os.path.join(_PKG, "csrc", "rowmask.cu"), os.path.join(_PKG, "csrc", "attn_softmax.cu"),
-           os.path.join(_PKG, "csrc", "attn_fused.cu"),
+           os.path.join(_PKG, "csrc", "attn_fused.cu"), os.path.join(_PKG, "csrc", "decoder_ops.cu"),
            os.path.join(_PKG, "csrc", "ema.cu")]
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
@@ -34,7 +34,7 @@ EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward",
            "datr_zero_masked_rows", "datr_rowmask_last_error", "datr_rowmask_launch_count",
            "datr_attn_softmax_forward", "datr_attn_softmax_backward", "datr_attn_last_error", "datr_attn_launch_count",
            "datr_attn_mask_words", "datr_attn_pack_mask", "datr_attn_fused_forward", "datr_attn_fused_backward", "datr_attn_fused_last_error",
-           "datr_attn_fused_launch_count",
+           "datr_attn_fused_launch_count", "datr_sine_embed", "datr_decoder_ops_last_error", "datr_decoder_ops_launch_count",
            "datr_ema_update", "datr_ema_last_error", "datr_ema_launch_count")
 
 _lock = threading.Lock()
@@ -173,6 +173,10 @@ def lib() -> ctypes.CDLL:
         L.datr_attn_fused_forward.argtypes = [vp, ll, vp, ll, vp, ll, vp, i, i, i, ctypes.c_float, vp, vp, vp, vp]
         L.datr_attn_fused_last_error.restype = ctypes.c_char_p
         L.datr_attn_fused_launch_count.restype = ctypes.c_uint64
+        L.datr_sine_embed.restype = i
+        L.datr_sine_embed.argtypes = [vp, vp, ll, i, vp, vp]
+        L.datr_decoder_ops_last_error.restype = ctypes.c_char_p
+        L.datr_decoder_ops_launch_count.restype = ctypes.c_uint64
         L.datr_ema_update.restype = i
         L.datr_ema_update.argtypes = [vp, vp, i, ctypes.c_float, ctypes.c_float, vp]
         L.datr_ema_last_error.restype = ctypes.c_char_p
@@ -196,7 +200,8 @@ def colsum_launch_count() -> int:
 def all_launch_count() -> int:
     """Every hand-written kernel launch issued through the library by this process."""
     return (launch_count() + linear_launch_count() + layernorm_launch_count() + colsum_launch_count()
-            + conv_launch_count() + wgrad_launch_count() + rowmask_launch_count() + attn_launch_count() + ema_launch_count())
+            + conv_launch_count() + wgrad_launch_count() + rowmask_launch_count() + attn_launch_count() + ema_launch_count()
+            + int(lib().datr_decoder_ops_launch_count()))
 
 
 def ema_launch_count() -> int:
