@@ -287,11 +287,15 @@ class MsdaStep:
         groups = {}
         for kind, key, e0, e1 in timers:
             dt = e0.elapsed_time(e1) * 1e-3
-            if kind == "linear":
+            if kind in ("linear", "linear_bf16"):
                 M, N, K, res = key
-                name = f"linear_tf32 N={N} K={K}" + ("+res" if res else "")
+                bf = kind == "linear_bf16"
+                name = f"linear_{'bf16' if bf else 'tf32'} N={N} K={K}" + ("+res" if res else "")
                 g = groups.setdefault(name, [0.0, 0, 0, 0.0])
-                g[0] += dt; g[1] += 4 * (M * K + N * K + M * N * (2 if res else 1)); g[2] += 1; g[3] += 2.0 * M * N * K
+                # operand bytes: 4 (TF32 kernels read fp32) or 2 (bf16); the output / residual are counted as fp32 (upper bound
+                # for the bf16-output launches)
+                g[0] += dt; g[1] += (2 if bf else 4) * (M * K + N * K) + 4 * M * N * (2 if res else 1); g[2] += 1
+                g[3] += 2.0 * M * N * K
                 continue
             N, S, M, D, L, Lq, P, es = key
             name = f"msda_{kind}_f32_d32<{P}> " + ("encoder" if Lq == S else "decoder")
@@ -313,8 +317,8 @@ class MsdaStep:
         if lin:
             fl, tt = sum(v[3] for v in lin.values()), sum(v[0] for v in lin.values())
             ktop = max(lin, key=lambda k: lin[k][0])
-            tensor = {"what": "all tcgen05 linear launches of the inspected steps (TF32 products: the TF32 pipe peaks at half "
-                              "the bf16 rate the denominator was measured with)",
+            tensor = {"what": "all tcgen05 linear launches of the inspected steps (TF32 and bf16 operands; the TF32 pipe peaks at "
+                              "half the bf16 rate the denominator was measured with)",
                       "tflops": fl / tt / 1e12, "peak": tpeak, "peak_source": tsrc, "tensor_pipe_frac": fl / tt / 1e12 / tpeak,
                       "top_kernel": ktop, "top_kernel_tflops": lin[ktop][3] / lin[ktop][0] / 1e12,
                       "top_kernel_frac": lin[ktop][3] / lin[ktop][0] / 1e12 / tpeak, "share_of_timed_kernels": tt / total}

@@ -19,7 +19,7 @@ from datr_b200.util.misc import NestedTensor
 H_IMG, W_IMG = 800, 1333
 WORKLOAD = ("DINO-4scale ResNet-50 DA training step (forward + losses + backward + gradient all-reduce + clip + AdamW), "
             "synthetic 1333x800, batch_size 2/GPU = 2 source + 2 target images, 900 queries + CDN; fp32 tensors, "
-            "MSDeformAttn fp32, dense layers TF32 products with fp32 accumulation")
+            "MSDeformAttn fp32, dense layers TF32 products with fp32 accumulation, encoder FFN GEMMs bf16 operands with fp32 accumulation")
 
 
 def synth_targets(rng, n_images, num_classes, device):
@@ -44,7 +44,9 @@ class DinoStep:
         # dense contractions run on the tensor cores with TF32 operands / fp32 accumulation (10-bit mantissa, above the
         # bf16 floor BASELINE.json allows); DATR_MATMUL=fp32 restores SIMT fp32 GEMMs (what the parity tests use)
         self.matmul = os.environ.get("DATR_MATMUL", "tf32")
-        self.dtype = "tf32" if self.matmul == "tf32" and device.type == "cuda" else "f32"
+        from datr_b200 import linear as _dl
+        tensor_core = self.matmul == "tf32" and device.type == "cuda"
+        self.dtype = ("tf32+bf16" if _dl._FFN == "bf16" else "tf32") if tensor_core else "f32"
         torch.backends.cuda.matmul.allow_tf32 = self.matmul == "tf32"
         torch.backends.cudnn.allow_tf32 = True
         # static shapes: let cuDNN time its algorithms once for the layers that stay on it (7x7 stem, convolution

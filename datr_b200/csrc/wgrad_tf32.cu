@@ -42,13 +42,29 @@ constexpr int kThreads = 192;
 constexpr int kChunk = 32 * BK * 4;         // bytes of one {32 columns x 32 rows} box
 constexpr int kOnesCols = 16;               // N of the bias-gradient MMA
 
-template <int BN, int STAGES>
+constexpr int kChunkBf = 64 * 64 * 2;       // bf16 operands: bytes of one {64 columns x 64 rows} box
+
+template <int BN, int STAGES, bool kBF16 = false>
 struct Smem {
-  static constexpr int kA = 4 * kChunk, kB = (BN / 32) * kChunk, kStage = kA + kB;
-  static constexpr int kOnes = kChunk;
+  static constexpr int kCh = kBF16 ? kChunkBf : kChunk;
+  static constexpr int kA = kBF16 ? 2 * kChunkBf : 4 * kChunk, kB = kBF16 ? (BN / 64) * kChunkBf : (BN / 32) * kChunk;
+  static constexpr int kStage = kA + kB;
+  static constexpr int kOnes = kCh;
   static constexpr int kBars = 1024;
   static constexpr int kTotal = STAGES * kStage + kOnes + kBars + 1024;
 };
+
+// MN-major 16-bit operand: TMA boxes of {64 columns x 64 rows} with the plain 128-byte swizzle; rows (= the contraction
+// index) are 128 bytes, the swizzle atom is 8 rows (1024 bytes = stride byte offset), 64-column chunks are kChunkBf bytes
+// apart (leading byte offset); each K = 16 MMA consumes 16 rows = 2048 bytes.
+__device__ __forceinline__ uint64_t mnmajor_bf16_desc(uint32_t smem_addr) {
+  return uint64_t((smem_addr >> 4) & 0x3FFF) | (uint64_t(kChunkBf >> 4) << 16) | (uint64_t(1024 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// D = fp32, A = B = bf16, both MN-major
+__host__ __device__ constexpr uint32_t bf16_idesc_mn(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (uint32_t(n >> 3) << 17) | (uint32_t(BM >> 4) << 24);
+}
 
 // MN-major 32-bit operand: the tensor core transposes 32-bit elements in 32-byte units, so the tile uses the
 // "128B swizzle with 32B atoms" (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA layout type SWIZZLE_128B_BASE32B = 1;
@@ -77,12 +93,13 @@ __device__ __forceinline__ void red_add2(float* p, float a, float b) {
 struct ConvGeom { int on, Cin, stride, tiles_x, tiles_y; };
 constexpr int kPW = 16, kPH = 2;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool kBF16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tma_dz, const __grid_constant__ CUtensorMap tma_x,
                   float* __restrict__ dw, float* __restrict__ db, int M, int N, int K, int splits, int rows_per_split,
                   const ConvGeom cg) {
-  using L = Smem<BN, STAGES>;
+  using L = Smem<BN, STAGES, kBF16>;
+  constexpr int BKr = kBF16 ? 64 : BK;       // rows (contraction steps) per pipeline stage
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   float* ones = reinterpret_cast<float*>(smem + STAGES * L::kStage);
@@ -98,9 +115,13 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tma_dz, const __grid_const
   const int n0 = (tile / k_tiles) * BM, k0 = (tile % k_tiles) * BN;
   const int m_begin = split * rows_per_split;
   const int m_end = min(M, m_begin + rows_per_split);
-  const int kblocks = m_end > m_begin ? (m_end - m_begin + BK - 1) / BK : 0;
+  const int kblocks = m_end > m_begin ? (m_end - m_begin + BKr - 1) / BKr : 0;
 
-  for (int i = threadIdx.x; i < kChunk / 4; i += kThreads) ones[i] = 1.0f;
+  if constexpr (kBF16) {
+    for (int i = threadIdx.x; i < kChunkBf / 4; i += kThreads) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;   // bf16 1.0 pairs
+  } else {
+    for (int i = threadIdx.x; i < kChunk / 4; i += kThreads) ones[i] = 1.0f;
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_dz) : "memory");
@@ -120,7 +141,7 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tma_dz, const __grid_const
       if (lane == 0) {
         for (int kb = 0; kb < kblocks; ++kb) {
           const int s = kb % STAGES;
-          const int m = m_begin + kb * BK;
+          const int m = m_begin + kb * BKr;
           mbar_wait(empty + s, ((kb / STAGES) & 1) ^ 1);
           mbar_expect_tx(full + s, L::kStage);
           unsigned char* a = smem + s * L::kStage;
@@ -137,6 +158,13 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tma_dz, const __grid_const
             for (int c = 0; c < BN / 32; ++c) tma_load_4d(a + L::kA + c * kChunk, &tma_x, ci0 + 32 * c, ix, iy, img, full + s);
             continue;
           }
+          if constexpr (kBF16) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) tma_load_2d(a + c * kChunkBf, &tma_dz, n0 + 64 * c, m, full + s);
+#pragma unroll
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(a + L::kA + c * kChunkBf, &tma_x, k0 + 64 * c, m, full + s);
+            continue;
+          }
 #pragma unroll
           for (int c = 0; c < 4; ++c) tma_load_2d(a + c * kChunk, &tma_dz, n0 + 32 * c, m, full + s);
 #pragma unroll
@@ -145,18 +173,28 @@ wgrad_tf32_kernel(const __grid_constant__ CUtensorMap tma_dz, const __grid_const
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = tf32_idesc_mn(BN), idesc1 = tf32_idesc_mn(kOnesCols);
-        const uint64_t od = mnmajor_sw128_desc(smem_u32(ones));
+        constexpr uint32_t idesc = kBF16 ? bf16_idesc_mn(BN) : tf32_idesc_mn(BN);
+        constexpr uint32_t idesc1 = kBF16 ? bf16_idesc_mn(kOnesCols) : tf32_idesc_mn(kOnesCols);
+        const uint64_t od = kBF16 ? mnmajor_bf16_desc(smem_u32(ones)) : mnmajor_sw128_desc(smem_u32(ones));
         for (int kb = 0; kb < kblocks; ++kb) {
           const int s = kb % STAGES;
           mbar_wait(full + s, (kb / STAGES) & 1);
           tc_fence_after();
           const uint32_t a = smem_u32(smem + s * L::kStage);
-          const uint64_t ad = mnmajor_sw128_desc(a), bd = mnmajor_sw128_desc(a + L::kA);
+          if constexpr (kBF16) {
+            const uint64_t ad = mnmajor_bf16_desc(a), bd = mnmajor_bf16_desc(a + L::kA);
 #pragma unroll
-          for (int j = 0; j < BK / UMMA_K; ++j) {             // next 8 rows = +1024 bytes = +64 in the address field
-            umma_tf32(tmem_d, ad + uint64_t(j * 64), bd + uint64_t(j * 64), idesc, (kb | j) != 0);
-            umma_tf32(tmem_d + BN, ad + uint64_t(j * 64), od, idesc1, (kb | j) != 0);
+            for (int j = 0; j < 4; ++j) {                     // next 16 rows = +2048 bytes = +128 in the address field
+              umma_bf16(tmem_d, ad + uint64_t(j * 128), bd + uint64_t(j * 128), idesc, (kb | j) != 0);
+              umma_bf16(tmem_d + BN, ad + uint64_t(j * 128), od, idesc1, (kb | j) != 0);
+            }
+          } else {
+            const uint64_t ad = mnmajor_sw128_desc(a), bd = mnmajor_sw128_desc(a + L::kA);
+#pragma unroll
+            for (int j = 0; j < BK / UMMA_K; ++j) {           // next 8 rows = +1024 bytes = +64 in the address field
+              umma_tf32(tmem_d, ad + uint64_t(j * 64), bd + uint64_t(j * 64), idesc, (kb | j) != 0);
+              umma_tf32(tmem_d + BN, ad + uint64_t(j * 64), od, idesc1, (kb | j) != 0);
+            }
           }
           umma_commit(empty + s);
         }
@@ -215,16 +253,34 @@ int make_map(CUtensorMap* map, const float* base, int rows, int cols) {
   return DATR_LINEAR_OK;
 }
 
-template <int BN, int STAGES>
+int make_map_bf16(CUtensorMap* map, const void* base, int rows, int cols) {
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return wfail(DATR_LINEAR_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable%s");
+  const cuuint64_t gdim[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  const cuuint64_t gstride[1] = {cuuint64_t(cols) * 2};
+  const cuuint32_t box[2] = {64, 64};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_wg_err, sizeof g_wg_err, "cuTensorMapEncodeTiled (bf16) failed (CUresult %d)", int(r));
+    return DATR_LINEAR_ERR_CUDA;
+  }
+  return DATR_LINEAR_OK;
+}
+
+template <int BN, int STAGES, bool kBF16 = false>
 int launch(const CUtensorMap& mdz, const CUtensorMap& mx, float* dw, float* db, int M, int N, int K, cudaStream_t stream,
            const ConvGeom& cg = ConvGeom{0, 0, 0, 0, 0}) {
-  using L = Smem<BN, STAGES>;
+  using L = Smem<BN, STAGES, kBF16>;
+  constexpr int BKr = kBF16 ? 64 : BK;
   static std::atomic<uint64_t> opted{0};
   int dev = 0;
   cudaGetDevice(&dev);
   const uint64_t bit = 1ull << (dev & 63);
   if (!(opted.load(std::memory_order_acquire) & bit)) {
-    const cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    const cudaError_t e = cudaFuncSetAttribute(wgrad_tf32_kernel<BN, STAGES, kBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     opted.fetch_or(bit, std::memory_order_release);
   }
@@ -239,10 +295,10 @@ int launch(const CUtensorMap& mdz, const CUtensorMap& mx, float* dw, float* db, 
   const int max_splits = (M + 4 * BK - 1) / (4 * BK);         // at least 128 rows per slab
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  int rows_per_split = ((M + splits - 1) / splits + BK - 1) / BK * BK;
+  int rows_per_split = ((M + splits - 1) / splits + BKr - 1) / BKr * BKr;
   splits = (M + rows_per_split - 1) / rows_per_split;
-  wgrad_tf32_kernel<BN, STAGES><<<unsigned(tiles * splits), kThreads, L::kTotal, stream>>>(mdz, mx, dw, db, M, N, K, splits,
-                                                                                          rows_per_split, cg);
+  wgrad_tf32_kernel<BN, STAGES, kBF16><<<unsigned(tiles * splits), kThreads, L::kTotal, stream>>>(mdz, mx, dw, db, M, N, K, splits,
+                                                                                                 rows_per_split, cg);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "wgrad_tf32_kernel launch: %s", cudaGetErrorString(e));
   g_wg_launches.fetch_add(1, std::memory_order_relaxed);
@@ -267,6 +323,23 @@ int datr_linear_wgrad_tf32(const float* dz, const float* x, float* dw, float* db
   if (int rc = make_map(&mdz, dz, M, N)) return rc;
   if (int rc = make_map(&mx, x, M, K)) return rc;
   return K > 128 ? launch<256, 4>(mdz, mx, dw, db, M, N, K, stream) : launch<128, 6>(mdz, mx, dw, db, M, N, K, stream);
+}
+
+// bf16 operands (dz [M, N], x [M, K] as bf16), fp32 accumulation, dw [N, K] / db [N] fp32.
+int datr_linear_wgrad_bf16(const void* dz, const void* x, float* dw, float* db, int M, int N, int K, void* stream_) {
+  if (!dz || !x || !dw) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "null pointer argument%s");
+  if (M <= 0 || N <= 0 || K <= 0) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "all dimensions must be positive%s");
+  if (N % 8 != 0 || K % 8 != 0) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "N and K must be multiples of 8 for bf16 operands%s");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(dz) || !al16(x) || !al16(dw)) return wfail(DATR_LINEAR_ERR_ALIGNMENT, "buffers must be 16-byte aligned%s");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, stream);
+  if (e == cudaSuccess && db) e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, stream);
+  if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  CUtensorMap mdz, mx;
+  if (int rc = make_map_bf16(&mdz, dz, M, N)) return rc;
+  if (int rc = make_map_bf16(&mx, x, M, K)) return rc;
+  return K > 128 ? launch<256, 4, true>(mdz, mx, dw, db, M, N, K, stream) : launch<128, 6, true>(mdz, mx, dw, db, M, N, K, stream);
 }
 
 // Weight (and bias) gradient of a 3x3 convolution, padding 1, stride 1 or 2, NHWC tensors:

@@ -216,12 +216,97 @@ class _FFNTF32(torch.autograd.Function):
         return gx, gw1, gb1, gw2, gb2
 
 
+def _launch_bf16(xb, wb, bias, residual, relu, out_bf16, residual_bf16=False):
+    """act(xb wb^T + bias) (+ residual) on the bf16-operand tensor-core kernel (datr_linear_bf16)."""
+    M, K = xb.shape
+    N = wb.shape[0]
+    y = torch.empty((M, N), dtype=torch.bfloat16 if out_bf16 else torch.float32, device=xb.device)
+    lib = native.lib()
+    with torch.cuda.device(xb.device):
+        stream = torch.cuda.current_stream()
+        if _timers is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        rc = lib.datr_linear_bf16(xb.data_ptr(), wb.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                  residual.data_ptr() if residual is not None else None, int(residual_bf16), y.data_ptr(),
+                                  int(out_bf16), M, N, K, int(relu), stream.cuda_stream)
+        if _timers is not None:
+            e1.record(stream)
+            _timers.append(("linear_bf16", (M, N, K, residual is not None), e0, e1))
+    if rc != 0:
+        raise RuntimeError(f"datr_linear_bf16 failed (code {rc}): {lib.datr_linear_last_error().decode()}")
+    return y
+
+
+def _wgrad_bf16(gb, xb, want_db):
+    """dW = gb^T xb (and db = column sums of gb), bf16 operands, fp32 results (datr_linear_wgrad_bf16)."""
+    M, N = gb.shape
+    K = xb.shape[1]
+    lib = native.lib()
+    dw = torch.empty((N, K), dtype=torch.float32, device=gb.device)
+    db = torch.empty(N, dtype=torch.float32, device=gb.device) if want_db else None
+    with torch.cuda.device(gb.device):
+        rc = lib.datr_linear_wgrad_bf16(gb.data_ptr(), xb.data_ptr(), dw.data_ptr(), db.data_ptr() if want_db else None,
+                                        M, N, K, torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"datr_linear_wgrad_bf16 failed (code {rc}): {lib.datr_linear_wgrad_last_error().decode()}")
+    return dw, db
+
+
+class _FFNBF16(torch.autograd.Function):
+    """_FFNTF32 with bf16 operands: the six GEMMs of the block (two forward, two input-gradient, two weight-gradient) read
+    bf16 activations / weights and accumulate in fp32; the [M, d_ffn] hidden activation and its gradient exist only as
+    bf16 (half the HBM traffic of the block); x, y, the residual branch and every parameter gradient stay fp32.
+    Precision class: BASELINE.json's bf16 bar (1e-2)."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        K = w1.shape[1]
+        x2 = _c(x.reshape(-1, K))
+        xb = x2.to(torch.bfloat16)
+        w1b, w2b = w1.to(torch.bfloat16), w2.to(torch.bfloat16)
+        h = _launch_bf16(xb, w1b, _c(b1), None, 1, True)
+        y = _launch_bf16(h, w2b, _c(b2), x2, 0, False)
+        ctx.xshape = x.shape
+        ctx.save_for_backward(xb, w1b, w2b, h)
+        return y.view(x.shape)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        xb, w1b, w2b, h = ctx.saved_tensors
+        g2 = _c(gy.reshape(-1, w2b.shape[0]))
+        gb = g2.to(torch.bfloat16)
+        gw2, gb2 = _wgrad_bf16(gb, h, True)
+        dz1 = _launch_bf16(gb, w2b.t().contiguous(), None, h, 3, True, residual_bf16=True)
+        gw1, gb1 = _wgrad_bf16(dz1, xb, True)
+        gx = _launch_bf16(dz1, w1b.t().contiguous(), None, g2, 0, False).view(ctx.xshape)
+        return gx, gw1, gb1, gw2, gb2
+
+
+# Operand precision of the FFN blocks in 'tf32' mode: "bf16" (default) or "tf32" (DATR_FFN=tf32 / set_ffn_precision)
+import os as _os
+_FFN = _os.environ.get("DATR_FFN", "bf16")
+_FFN_BF16_MIN_ROWS = 8192
+
+
+def set_ffn_precision(kind: str) -> None:
+    global _FFN
+    if kind not in ("bf16", "tf32"):
+        raise ValueError(kind)
+    _FFN = kind
+
+
 def ffn(x, w1, b1, w2, b2):
     """relu(x @ w1.T + b1) @ w2.T + b2 + x  (pre-norm output of the transformer FFN block)."""
     d_ffn, d = w1.shape
     if (_MODE == "tf32" and x.is_cuda and x.dtype == torch.float32 and w1.dtype == torch.float32 and b1 is not None
             and b2 is not None and tuple(w2.shape) == (d, d_ffn) and d % 32 == 0 and d_ffn % 32 == 0
             and torch.is_grad_enabled()):
+        # bf16 operands pay off on long token sequences (encoder: 1.8x on the block at 89 k rows); at decoder sizes the
+        # extra casts of the block outweigh the faster GEMMs (tools/bench_ffn.py)
+        if _FFN == "bf16" and d % 128 == 0 and d_ffn % 256 == 0 and x.numel() // d >= _FFN_BF16_MIN_ROWS:
+            return _FFNBF16.apply(x, w1, b1, w2, b2)
         return _FFNTF32.apply(x, w1, b1, w2, b2)
     return linear(linear(x, w1, b1, relu=True), w2, b2, residual=x)
 

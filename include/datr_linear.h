@@ -52,6 +52,17 @@ int datr_linear_wgrad_tf32(const float* dz, const float* x, float* dw, float* db
 const char* datr_linear_wgrad_last_error(void);
 uint64_t datr_linear_wgrad_launch_count(void);
 
+/*
+ * bf16-operand variants (the "bf16" precision class of BASELINE.json, 1e-2): x / w / dz as bf16 in HBM, fp32 accumulation in
+ * tensor memory, tcgen05.mma.kind::f16.  Same tiling and epilogues as the TF32 kernels; half the operand bytes per FLOP.
+ *   datr_linear_bf16        y = act(x w^T + bias) (+ residual);  y fp32 or bf16 (y_bf16); residual fp32 [M, N], or bf16
+ *                           (residual_bf16) when it is the ReLU-mask source of relu == 3.  K % 64 == 0, N % 4 == 0.
+ *   datr_linear_wgrad_bf16  dw [N, K] = dz^T x, db [N] = column sums of dz (fp32 outputs, zero-filled by the library).
+ */
+int datr_linear_bf16(const void* x, const void* w, const float* bias, const void* residual, int residual_bf16, void* y,
+                     int y_bf16, int M, int N, int K, int relu, void* stream);
+int datr_linear_wgrad_bf16(const void* dz, const void* x, float* dw, float* db, int M, int N, int K, void* stream);
+
 const char* datr_linear_last_error(void);
 
 /* Number of tensor-core linear kernels launched by this process (bench accounting). */

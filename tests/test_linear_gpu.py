@@ -184,6 +184,7 @@ def test_fused_ffn_block(M, d, dff):
     gy = torch.randn(M, d, generator=g).cuda()
     leaves = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
     dl.set_mode("tf32")
+    dl.set_ffn_precision("tf32")
     try:
         y = dl.ffn(*leaves)
         y.backward(gy)
@@ -191,9 +192,96 @@ def test_fused_ffn_block(M, d, dff):
             active = dl.linear(x, w1, b1, relu=True) > 0
     finally:
         dl.set_mode("fp32")
+        dl.set_ffn_precision("bf16")
     ref = [t.double().clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
     yr = ((ref[0] @ ref[1].t() + ref[2]) * active) @ ref[3].t() + ref[4] + ref[0]
     yr.backward(gy.double())
     assert rel(y.detach(), yr.detach()) < REL_TF32
     for got, want in zip(leaves, ref):
         assert rel(got.grad, want.grad) < REL_TF32
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# bf16-operand kernels (datr_linear_bf16 / datr_linear_wgrad_bf16) and the bf16 FFN block
+# --------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K,relu,res,out_bf16", [(44446, 2048, 256, 1, False, True), (3001, 256, 2048, 0, True, False),
+                                                     (130, 128, 64, 0, False, False), (5000, 384, 256, 1, True, False),
+                                                     (257, 2048, 256, 0, False, True), (1100, 256, 512, 0, False, True)])
+def test_bf16_linear_matches_fp64_on_the_same_operands(M, N, K, relu, res, out_bf16):
+    """Products of bf16 numbers are exact in fp32, so against fp64 arithmetic on the SAME bf16 operands only the fp32
+    accumulation order (1e-5) and, for bf16 outputs, the final rounding (2^-9) remain."""
+    from datr_b200 import native
+    from datr_b200.linear import _launch_bf16
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    xb = torch.randn(M, K, generator=g).cuda().bfloat16()
+    wb = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    r = torch.randn(M, N, generator=g).cuda() if res else None
+    n0 = native.linear_launch_count()
+    y = _launch_bf16(xb, wb, bias, r, relu, out_bf16)
+    torch.cuda.synchronize()
+    assert native.linear_launch_count() == n0 + 1
+    assert y.dtype == (torch.bfloat16 if out_bf16 else torch.float32)
+    want = xb.double() @ wb.double().t() + bias.double()
+    if relu:
+        want = want.clamp_min(0)
+    if res:
+        want = want + r.double()
+    assert rel(y, want) < (4e-3 if out_bf16 else 1e-5)
+
+
+def test_bf16_linear_relu_mask_from_a_bf16_activation():
+    """relu == 3: the dgrad epilogue masks with (h > 0) read from the saved bf16 activation and writes bf16."""
+    from datr_b200.linear import _launch_bf16
+    g = torch.Generator(device="cpu").manual_seed(3)
+    M, N, K = 3001, 2048, 256
+    gb = torch.randn(M, K, generator=g).cuda().bfloat16()
+    wb = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().bfloat16()
+    h = torch.randn(M, N, generator=g).cuda().clamp_min(0).bfloat16()
+    dz = _launch_bf16(gb, wb, None, h, 3, True, residual_bf16=True)
+    want = (gb.double() @ wb.double().t()) * (h.double() > 0)
+    assert rel(dz, want) < 4e-3
+    assert float(dz[h == 0].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(44446, 256, 2048), (5000, 2048, 256), (130, 128, 128), (1000, 384, 512), (63, 64, 64)])
+def test_bf16_weight_and_bias_gradient_kernel(M, N, K):
+    from datr_b200 import native
+    from datr_b200.linear import _wgrad_bf16
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    dz = torch.randn(M, N, generator=g).cuda().bfloat16()
+    x = torch.randn(M, K, generator=g).cuda().bfloat16()
+    n0 = native.wgrad_launch_count()
+    dw, db = _wgrad_bf16(dz, x, True)
+    torch.cuda.synchronize()
+    assert native.wgrad_launch_count() == n0 + 1
+    assert rel(dw, dz.double().t() @ x.double()) < 2e-5
+    assert rel(db, dz.double().sum(0)) < 2e-5
+
+
+@pytest.mark.parametrize("M,d,dff", [(9000, 256, 2048), (8200, 256, 512)])
+def test_bf16_ffn_block(M, d, dff):
+    """The FFN block with bf16 operands against fp64 autograd on the fp32 inputs: BASELINE's bf16 bar (1e-2) on the
+    output, and on the gradients with the block's own active set (the ReLU mask of the bf16 hidden activation)."""
+    from datr_b200 import linear as dl
+    g = torch.Generator(device="cpu").manual_seed(M + dff)
+    x = torch.randn(M, d, generator=g).cuda()
+    w1 = (torch.randn(dff, d, generator=g) / d ** 0.5).cuda(); b1 = torch.randn(dff, generator=g).cuda()
+    w2 = (torch.randn(d, dff, generator=g) / dff ** 0.5).cuda(); b2 = torch.randn(d, generator=g).cuda()
+    gy = torch.randn(M, d, generator=g).cuda()
+    leaves = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    dl.set_mode("tf32")
+    try:
+        assert dl._FFN == "bf16"
+        y = dl.ffn(*leaves)
+        y.backward(gy)
+        with torch.no_grad():
+            active = dl._launch_bf16(x.bfloat16(), w1.bfloat16(), b1, None, 1, True) > 0
+    finally:
+        dl.set_mode("fp32")
+    ref = [t.double().clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    yr = ((ref[0] @ ref[1].t() + ref[2]) * active) @ ref[3].t() + ref[4] + ref[0]
+    yr.backward(gy.double())
+    assert rel(y.detach(), yr.detach()) < 1e-2
+    for got, want, name in zip(leaves, ref, ("dx", "dw1", "db1", "dw2", "db2")):
+        assert rel(got.grad, want.grad) < 1e-2, name
