@@ -71,6 +71,7 @@ class DinoStep:
             # flattening a feature map to [N, HW, C] tokens becomes a view
             self.model.to(memory_format=torch.channels_last)
         self.criterion.train()
+        self.criterion.fold_weighted_sum = True
         broadcast_parameters(self.model)
         # backbone gradients are produced last: they sit at the end of the flat buffer, and the exchange of everything
         # else starts from a backward hook while the ResNet backward is still running (parallel.py)
@@ -107,6 +108,13 @@ class DinoStep:
         out = self.model(NestedTensor(images, mask), targets)
         losses = self.criterion(out, targets)
         # engine.py:99 `sum(loss_dict[k] * weight_dict[k] ...)` as one stack + dot (2 kernels instead of ~120)
+        if "_weighted_total" in losses:       # the criterion segment already summed the weighted losses (graph replay)
+            loss = losses["_weighted_total"]
+            loss.backward()
+            self.grads.all_reduce()
+            self.grads.clip_(self.args.clip_max_norm)
+            self.opt.step()
+            return loss
         wd = self.criterion.weight_dict
         keys = [k for k in losses if k in wd]
         if self._loss_w is None or self._loss_keys != keys:
@@ -215,7 +223,7 @@ class TeacherStep(DinoStep):
         wd = self.criterion.weight_dict
         loss_src = self.criterion(source_out, targets, target_domain_flag=False)           # :240
         loss_tgt = self.criterion(valid_out, pseudo_list, target_domain_flag=True)         # :243
-        total_src = sum(loss_src[k] * wd[k] for k in loss_src if k in wd)
+        total_src = loss_src["_weighted_total"] if "_weighted_total" in loss_src else sum(loss_src[k] * wd[k] for k in loss_src if k in wd)
         total_tgt = sum(loss_tgt[k] * wd[k] for k in loss_tgt if k in wd)
         loss = total_src + total_tgt * wd["loss_self_training"]                             # :257
         loss.backward()

@@ -44,6 +44,8 @@ class StepGraphs:
         self.capture_inference = True          # no-grad passes get forward-only graphs (False: they run eagerly)
         import os
         self.skip = set(filter(None, os.environ.get("DATR_GRAPH_SKIP", "").split(",")))   # segment names kept eager
+        self.alias_inputs = os.environ.get("DATR_GRAPH_ALIAS", "1") != "0"
+        self.stable_storages = set()           # storage addresses of the static outputs of the captured training segments
 
     def begin_step(self):
         self.calls.clear()
@@ -77,7 +79,12 @@ class StepGraphs:
             module = make_module()
             n0 = _native_launches()
             if grad:
-                sample = tuple(a.detach().clone().requires_grad_(a.requires_grad) for a in args)
+                # static inputs: private clones -- except for arguments that live in the static output buffers of a segment
+                # captured earlier (same address at every replay): those are captured in place, so a replay finds
+                # `static_input.data_ptr() == arg.data_ptr()` and skips the device copy + its launch (the criterion segment
+                # alone has ~50 such inputs; DATR_GRAPH_ALIAS=0 restores the clones)
+                sample = tuple((a.detach() if self._stable(a) else a.detach().clone()).requires_grad_(a.requires_grad)
+                               for a in args)
                 graphed = torch.cuda.make_graphed_callables(module, sample, num_warmup_iters=self.warmup_iters,
                                                             allow_unused_input=True)
                 # warm-up iterations + one capture each ran forward and backward eagerly/under capture once
@@ -90,7 +97,16 @@ class StepGraphs:
         graphed, per_pair = entry
         self.replayed_native_launches += per_pair
         out = graphed(*args)
+        if self.alias_inputs and grad:
+            for o in (out if isinstance(out, (tuple, list)) else (out,)):
+                if isinstance(o, torch.Tensor) and o.is_cuda:
+                    self.stable_storages.add(o.untyped_storage().data_ptr())
         return (out, graphed) if want_module else out
+
+    def _stable(self, a):
+        """True if `a` aliases the static output storage of a segment captured earlier in this process."""
+        return (self.alias_inputs and isinstance(a, torch.Tensor) and a.is_cuda
+                and a.untyped_storage().data_ptr() in self.stable_storages)
 
 
 class _InferenceGraph:

@@ -701,6 +701,17 @@ class SetCriterion(nn.Module):
             return losses, indices_list
         return losses
 
+    def _weighted_losses_from(self, outputs, targets, pre, num_boxes, target_domain_flag, training, helpers):
+        """(loss names, their values packed into one detached tensor, sum_k weight_dict[k] * loss_k)."""
+        losses = self._losses_from(outputs, targets, pre, num_boxes, target_domain_flag, training, False, helpers)
+        keys = tuple(losses)
+        vals = torch.stack([losses[k].reshape(()) for k in keys])
+        cache = self.__dict__.setdefault("_weight_vectors", {})
+        ck = (keys, str(vals.device))
+        if ck not in cache:       # first built during the (uncaptured) warm-up passes of the segment
+            cache[ck] = torch.tensor([float(self.weight_dict.get(k, 0.0)) for k in keys], dtype=vals.dtype, device=vals.device)
+        return keys, vals.detach(), torch.dot(vals, cache[ck])
+
     def forward(self, outputs, targets, return_indices=False, target_domain_flag=False):
         """outputs: the model's dict; targets: list of {'labels','boxes'} per (source or pseudo-labelled) image.
         With target_domain_flag the *_target keys are scored instead (self-training)."""
@@ -751,6 +762,15 @@ class SetCriterion(nn.Module):
                 and not target_domain_flag):
             # every loss of the step as one captured segment: the matched indices, targets and predictions are its
             # tensor inputs, everything host-side (matching, num_boxes, index helpers) happened above
+            if getattr(self, "fold_weighted_sum", False):
+                # engine.py:99's weighted sum inside the segment: ONE differentiable output (the total) and one packed,
+                # detached tensor of the individual losses, instead of ~40 scalar outputs whose stack / gradient copies
+                # would be launched one by one between the criterion's forward and backward graphs
+                keys, packed, total = graphs.ACTIVE.call("criterion", None, self._weighted_losses_from, outputs, targets, pre,
+                                                         num_boxes, target_domain_flag, self.training, helpers)
+                losses = {k: packed[i] for i, k in enumerate(keys)}
+                losses["_weighted_total"] = total
+                return losses
             return graphs.ACTIVE.call("criterion", None, self._losses_from, outputs, targets, pre, num_boxes,
                                       target_domain_flag, self.training, False, helpers)
         return self._losses_from(outputs, targets, pre, num_boxes, target_domain_flag, self.training, return_indices, helpers)

@@ -64,4 +64,11 @@ with open(detail, "w") as f:
             name = e["name"].replace("void ", "").replace("(anonymous namespace)::", "").replace("at::native::", "")
             f.write(f"{e['dur']:7.1f} us  gap {max(0.0, e['ts'] - prev_end):5.1f}  {name[:150]}\n")
             prev_end = e["ts"] + e["dur"]
+# host side: CPU ops / runtime calls longer than 80 us, in order (where the host makes the GPU wait)
+host = os.path.join(ROOT, "gpurun_out", "dino_step_timeline_host.txt")
+with open(host, "w") as f:
+    cpu = [e for e in trace if e.get("cat") in ("cpu_op", "cuda_runtime", "user_annotation", "python_function") and e.get("dur", 0) > 80]
+    cpu.sort(key=lambda e: e["ts"])
+    for e in cpu:
+        f.write(f"{(e['ts'] - t0) / 1e3:8.2f} ms  {e['dur'] / 1e3:7.2f} ms  {e.get('cat'):14s} {e['name'][:120]}\n")
 print(open(out).read()[:12000])
