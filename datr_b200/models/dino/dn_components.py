@@ -15,6 +15,12 @@ from datr_b200.util.misc import inverse_sigmoid
 _rand_like = torch.rand_like
 _randint_like = torch.randint_like
 
+# CUDA tensors: draw the label noise without a host synchronisation (same distribution, different consumption of the random
+# stream than the reference).  DATR_DN_SYNC_FREE=0 / SYNC_FREE = False reproduces the reference's draws one by one (what the
+# parity tools and golden tests use); CPU tensors always take the reference's sequence.
+import os as _os
+SYNC_FREE = _os.environ.get("DATR_DN_SYNC_FREE", "1") != "0"
+
 
 def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, label_enc):
     """-> (input_query_label [B,pad,C], input_query_bbox [B,pad,4] (logits), attn_mask [pad+nq,pad+nq] bool
@@ -48,8 +54,16 @@ def prepare_for_cdn(dn_args, training, num_queries, num_classes, hidden_dim, lab
     noisy_boxes = gt_boxes.clone()
 
     if label_noise_ratio > 0:
-        flip = torch.nonzero(_rand_like(noisy_labels.float()) < label_noise_ratio * 0.5).view(-1)
-        noisy_labels.scatter_(0, flip, _randint_like(flip, 0, num_classes))
+        if SYNC_FREE and noisy_labels.is_cuda:
+            # the same noise law (every label replaced by a uniform class with probability ratio / 2) without the
+            # device->host synchronisation of nonzero(): that sync sits at the very start of the forward pass and drains the
+            # GPU once per step (17.8 ms of host wait per step in tools/host_profile.py), so the host can never enqueue ahead
+            flip = _rand_like(noisy_labels.float()) < label_noise_ratio * 0.5
+            noisy_labels = torch.where(flip, _randint_like(noisy_labels, 0, num_classes), noisy_labels)
+        else:
+            # the reference's own sequence of random draws (dn_components.py:60-63): nonzero + a draw per flipped label
+            flip = torch.nonzero(_rand_like(noisy_labels.float()) < label_noise_ratio * 0.5).view(-1)
+            noisy_labels.scatter_(0, flip, _randint_like(flip, 0, num_classes))
 
     pad_size = most * reps
     # rows [g*2T, g*2T+T) of the repeated set are positives of group g, the next T rows negatives

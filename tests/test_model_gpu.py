@@ -38,6 +38,7 @@ def small():
 def cpu_noise(monkeypatch):
     """Feed the de-noising query generator the CPU random stream the golden run used."""
     from datr_b200.models.dino import dn_components as dn
+    monkeypatch.setattr(dn, "SYNC_FREE", False)      # the goldens carry the reference's sequence of random draws
     monkeypatch.setattr(dn, "_rand_like", lambda t, **k: torch.rand(t.shape, dtype=k.get("dtype", t.dtype)).to(t.device))
     monkeypatch.setattr(dn, "_randint_like", lambda t, *a, **k: torch.randint_like(t.cpu(), *a, **k).to(t.device))
 

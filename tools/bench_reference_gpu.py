@@ -298,7 +298,9 @@ def main():
         wl.model.load_state_dict(sd, strict=True)
         if mode == "fp32":
             set_precision(False, False)
+        from datr_b200.models.dino import dn_components as _dn
         if not a.skip_parity:
+            _dn.SYNC_FREE = False          # parity pass: the reference's own sequence of de-noising draws
             wl.model.global_proto = None
             samples = NestedTensor(wl.images.copy_(images), wl.mask.copy_(mask))
             wl.grads.zero()
@@ -307,6 +309,7 @@ def main():
                 p.grad = None
             ours[mode] = r
             compare(f"ours_{mode}_vs_reference_fp32", r, ref_runs["fp32"], report)
+        _dn.SYNC_FREE = True
         if mode == "tf32" and not a.skip_timing:
             wl.grads = __import__("datr_b200.parallel", fromlist=["FlatGradients"]).FlatGradients(wl.model, late=lambda n: n.startswith("backbone"))
             wl.model._on_backbone_output_grad = wl.grads.reduce_early
