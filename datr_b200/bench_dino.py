@@ -77,8 +77,15 @@ class DinoStep:
         # else starts from a backward hook while the ResNet backward is still running (parallel.py)
         self.grads = FlatGradients(self.model, late=lambda n: n.startswith("backbone"))
         self.model._on_backbone_output_grad = self.grads.reduce_early
-        self.opt = torch.optim.AdamW(param_groups(self.model, args.lr, args.lr_backbone), lr=args.lr,
-                                     weight_decay=args.weight_decay, fused=device.type == "cuda")
+        # clip + AdamW as ONE kernel over all parameters (datr_b200.optim, include/datr_adamw.h); DATR_OPTIMIZER=torch keeps
+        # torch.nn.utils.clip_grad_norm_-style scaling + torch.optim.AdamW(fused=True)
+        self.flat_opt = device.type == "cuda" and os.environ.get("DATR_OPTIMIZER", "flat") == "flat"
+        if self.flat_opt:
+            from datr_b200.optim import FlatAdamW
+            self.opt = FlatAdamW(param_groups(self.model, args.lr, args.lr_backbone), self.grads, weight_decay=args.weight_decay)
+        else:
+            self.opt = torch.optim.AdamW(param_groups(self.model, args.lr, args.lr_backbone), lr=args.lr,
+                                         weight_decay=args.weight_decay, fused=device.type == "cuda")
         rng = np.random.default_rng(42 + rank)                  # main.py:138: seed + rank
         n = 2 * batch_size
         self.host_images = torch.from_numpy(rng.standard_normal((n, 3, height, width)).astype(np.float32))
@@ -112,8 +119,7 @@ class DinoStep:
             loss = losses["_weighted_total"]
             loss.backward()
             self.grads.all_reduce()
-            self.grads.clip_(self.args.clip_max_norm)
-            self.opt.step()
+            self._optimise()
             return loss
         wd = self.criterion.weight_dict
         keys = [k for k in losses if k in wd]
@@ -123,9 +129,16 @@ class DinoStep:
         loss = torch.dot(torch.stack([losses[k].reshape(()) for k in keys]), self._loss_w)
         loss.backward()
         self.grads.all_reduce()
-        self.grads.clip_(self.args.clip_max_norm)
-        self.opt.step()
+        self._optimise()
         return loss
+
+    def _optimise(self):
+        """engine.py:108-111: clip_grad_norm_(max_norm) + optimizer.step() on the all-reduced gradients."""
+        if self.flat_opt:
+            self.opt.clip_and_step(self.args.clip_max_norm)
+        else:
+            self.grads.clip_(self.args.clip_max_norm)
+            self.opt.step()
 
     def step(self):
         self.last_loss = self._step(self.images, self.mask, self.targets)
@@ -228,8 +241,7 @@ class TeacherStep(DinoStep):
         loss = total_src + total_tgt * wd["loss_self_training"]                             # :257
         loss.backward()
         self.grads.all_reduce()
-        self.grads.clip_(self.args.clip_max_norm)
-        self.opt.step()
+        self._optimise()
         self.teacher.update(self.model)                                                     # main_teacher.py:384
         return loss
 

@@ -38,12 +38,40 @@ class FrozenBatchNorm2d(nn.Module):
         super()._load_from_state_dict(state_dict, prefix, *rest)
 
     def scale_shift(self):
+        folded = self.__dict__.get("_folded")
+        if folded is not None:          # computed for all layers of the body at once (fold_frozen_bn), valid for this pass
+            return folded
         scale = self.weight * (self.running_var + 1e-5).rsqrt()
         return scale, self.bias - self.running_mean * scale
 
     def forward(self, x):
         scale, shift = self.scale_shift()
         return torch.addcmul(shift.view(1, -1, 1, 1), x, scale.view(1, -1, 1, 1))
+
+
+class fold_frozen_bn:
+    """Context: (scale, shift) of every FrozenBatchNorm2d below `module` with five multi-tensor launches instead of five
+    tiny kernels per layer (265 launches for ResNet-50), same operations in the same order; recomputed at every pass, so
+    buffers changed by a checkpoint load or an EMA copy are always seen, also by a CUDA graph captured over the pass."""
+
+    def __init__(self, module):
+        self.bns = [m for m in module.modules() if isinstance(m, FrozenBatchNorm2d)]
+
+    def __enter__(self):
+        bns = self.bns
+        if bns and bns[0].weight.is_cuda:
+            inv = torch._foreach_add([b.running_var for b in bns], 1e-5)
+            torch._foreach_rsqrt_(inv)
+            scale = torch._foreach_mul([b.weight for b in bns], inv)
+            shift = torch._foreach_sub([b.bias for b in bns], torch._foreach_mul([b.running_mean for b in bns], scale))
+            for b, sc, sh in zip(bns, scale, shift):
+                b.__dict__["_folded"] = (sc, sh)
+        return self
+
+    def __exit__(self, *exc):
+        for b in self.bns:
+            b.__dict__.pop("_folded", None)
+        return False
 
 
 def _pointwise_on_tensor_cores(x):
@@ -153,13 +181,14 @@ class _Body(nn.Module):
 
     def forward(self, x):
         out = {}
-        x = F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, stride=2, padding=1)
-        for i in range(1, self._last + 1):
-            name = f"layer{i}"
-            # stem and layer1 never train (BackboneBase): no autograd graph through them
-            x = getattr(self, name)(x)
-            if name in self.return_layers:
-                out[self.return_layers[name]] = x
+        with fold_frozen_bn(self):
+            x = F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, stride=2, padding=1)
+            for i in range(1, self._last + 1):
+                name = f"layer{i}"
+                # stem and layer1 never train (BackboneBase): no autograd graph through them
+                x = getattr(self, name)(x)
+                if name in self.return_layers:
+                    out[self.return_layers[name]] = x
         return out
 
 

@@ -313,8 +313,11 @@ def main():
         if mode == "tf32" and not a.skip_timing:
             wl.grads = __import__("datr_b200.parallel", fromlist=["FlatGradients"]).FlatGradients(wl.model, late=lambda n: n.startswith("backbone"))
             wl.model._on_backbone_output_grad = wl.grads.reduce_early
-            wl.opt = torch.optim.AdamW(__import__("datr_b200.parallel", fromlist=["param_groups"]).param_groups(wl.model, 1e-4, 1e-5),
-                                       lr=1e-4, weight_decay=1e-4, fused=True)
+            _groups = __import__("datr_b200.parallel", fromlist=["param_groups"]).param_groups(wl.model, 1e-4, 1e-5)
+            if getattr(wl, "flat_opt", False):
+                wl.opt = __import__("datr_b200.optim", fromlist=["FlatAdamW"]).FlatAdamW(_groups, wl.grads, weight_decay=1e-4)
+            else:
+                wl.opt = torch.optim.AdamW(_groups, lr=1e-4, weight_decay=1e-4, fused=True)
             wl.images.copy_(images)
             for _ in range(4):
                 wl.step()
