@@ -424,6 +424,8 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line (NCCL prints its version)
         dist.init_process_group("nccl", device_id=device)
+        # one process per GPU on one host: share the cores instead of every rank spawning a full intra-op pool
+        torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))
 
     def barrier():
         if world > 1:

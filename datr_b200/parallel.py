@@ -25,6 +25,10 @@ import torch
 import torch.distributed as dist
 
 
+import os as _os
+_EARLY = _os.environ.get("DATR_EARLY_REDUCE", "1") != "0"     # 0: one all-reduce after the whole backward
+
+
 class FlatGradients:
     def __init__(self, model: torch.nn.Module, process_group=None, gather: bool = False, late=None):
         """`late(name) -> bool` marks the parameters whose gradients are produced LAST by the backward pass (the backbone in
@@ -91,7 +95,7 @@ class FlatGradients:
         work already enqueued on the current stream and runs beside what is enqueued next).  Call it from a backward hook
         once the gradients of every non-late parameter are final; all_reduce() finishes the job.  No-op on one rank, in
         gather mode, without a late part, or if it already ran in this step."""
-        if self.world_size == 1 or self.gather or self._early_handle is not None or self.split in (0, self.numel):
+        if self.world_size == 1 or self.gather or self._early_handle is not None or self.split in (0, self.numel) or not _EARLY:
             return
         self._early_handle = dist.all_reduce(self.flat[:self.split], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
