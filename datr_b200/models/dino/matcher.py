@@ -13,6 +13,12 @@ from torch import nn
 from datr_b200.util.box_ops import box_cxcywh_to_xyxy, boxes_well_formed, generalized_box_iou
 
 
+# Solve the assignments of a step on the GPU (csrc/lsa.cu) instead of scipy on a host copy of the cost matrix: same
+# algorithm, identical assignments, no host synchronisation.  DATR_MATCHER=host keeps scipy.
+import os as _os
+DEVICE_SOLVER = _os.environ.get("DATR_MATCHER", "device") != "host"
+
+
 def _cost_matrix(outputs, targets, w_class, w_bbox, w_giou, alpha, gamma=2.0, deferred_check=None):
     """deferred_check: a list that receives the device-side result of the degenerate-box asserts instead of
     synchronising on them here (BatchedMatch checks it on the host together with the cost matrix)."""
@@ -63,8 +69,12 @@ class BatchedMatch:
     matching the sets one by one (the reference does 7 matchings with 7 syncs per step, dino.py:723-933 /
     matcher.py:91)."""
 
+    _problem_tables = {}      # (device, n_sets, bs, nq, sizes) -> (int64 [P, 5] device table, max boxes, output length)
+    _pending_checks = []      # (pinned flag, event) of earlier steps' degenerate-box checks (device mode: read one step late)
+
     def __init__(self, matcher, outputs_list, targets):
         self.targets, self.n_sets = targets, len(outputs_list)
+        self.flat_dev = None
         self.logits = [o["pred_logits"] for o in outputs_list]
         self.bs = self.logits[0].shape[0]
         stacked = {"pred_logits": torch.cat(self.logits, 0), "pred_boxes": torch.cat([o["pred_boxes"] for o in outputs_list], 0)}
@@ -80,7 +90,9 @@ class BatchedMatch:
                 self.world = torch.distributed.get_world_size()
                 nb = torch.as_tensor([n_boxes], dtype=torch.float, device=dev)
                 torch.distributed.all_reduce(nb)
-            if dev.type == "cuda":
+            if dev.type == "cuda" and DEVICE_SOLVER and self._solve_on_device(C, ok[0], nb, n_boxes):
+                pass
+            elif dev.type == "cuda":
                 self.C = torch.empty(C.shape, dtype=C.dtype, pin_memory=True)
                 self.C.copy_(C, non_blocking=True)
                 self.ok = torch.empty(1, dtype=torch.bool, pin_memory=True)
@@ -96,6 +108,59 @@ class BatchedMatch:
         self.n_boxes = float(n_boxes)
         self.consumed = False
 
+    def _solve_on_device(self, C, ok, nb, n_boxes) -> bool:
+        """All assignments of the step in ONE kernel launch on the cost matrix where it is (csrc/lsa.cu: scipy's algorithm,
+        identical assignments), no device->host copy, no synchronisation: result() returns device index tensors at once.
+        The degenerate-box assert of util/box_ops.py:48-49 is read back one step late."""
+        from datr_b200 import native
+        bs, nq = self.bs, C.shape[1]
+        sizes = tuple(int(n) for n in self.sizes)
+        if not sizes or max(sizes) > nq or max(sizes) > 2048 or sum(sizes) == 0:
+            return False
+        dev = self.device
+        key = (str(dev), self.n_sets, bs, nq, sizes)
+        hit = BatchedMatch._problem_tables.get(key)
+        if hit is None:
+            if torch.cuda.is_current_stream_capturing():
+                return False
+            T = sum(sizes)
+            rows, off = [], 0
+            for g in range(self.n_sets):
+                col = 0
+                for i, n in enumerate(sizes):
+                    rows.append([((g * bs + i) * nq) * T + col, T, nq, n, off])
+                    col += n
+                    off += 2 * n
+            if len(BatchedMatch._problem_tables) > 64:
+                BatchedMatch._problem_tables.clear()
+            hit = BatchedMatch._problem_tables[key] = (torch.tensor(rows, dtype=torch.int64, device=dev), max(sizes), off)
+        table, max_nt, total = hit
+        C = C.contiguous()
+        flat = torch.empty(total, dtype=torch.int64, device=dev)
+        lib = native.lib()
+        with torch.cuda.device(dev):
+            rc = lib.datr_lsa_solve(C.data_ptr(), table.data_ptr(), table.shape[0], nq, max_nt, flat.data_ptr(),
+                                    torch.cuda.current_stream(dev).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"datr_lsa_solve failed (code {rc}): {lib.datr_lsa_last_error().decode()}")
+        self.flat_dev, self.C, self.event = flat, None, None
+        # deferred degenerate-box check: flags of earlier steps whose copy has completed are examined now
+        still = []
+        for flag, ev in BatchedMatch._pending_checks:
+            if ev.query():
+                assert bool(flag[0]), "degenerate boxes (x1 < x0 or y1 < y0) reached the matcher"   # util/box_ops.py:48-49
+            else:
+                still.append((flag, ev))
+        flag = torch.empty(1, dtype=torch.bool, pin_memory=True)
+        flag.copy_(ok.reshape(1), non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        BatchedMatch._pending_checks = still[-8:] + [(flag, ev)]
+        self.ok = None
+        # num_boxes: host-known on one rank; after the all-reduce it stays on the device (a 0-dim tensor)
+        self.nb_dev = torch.clamp(nb[0] / self.world, min=1.0) if nb is not None else None
+        return True
+
     def matches(self, outputs_list, targets) -> bool:
         """True if this prefetched match was started for exactly these prediction tensors and targets (and has not
         been used yet: graph-replayed outputs are the same tensor objects every step)."""
@@ -104,6 +169,15 @@ class BatchedMatch:
 
     def result(self):
         self.consumed = True
+        if self.flat_dev is not None:          # solved on the device: nothing to wait for
+            out, off = [], 0
+            for _ in range(self.n_sets):
+                cur = []
+                for n in self.sizes:
+                    cur.append((self.flat_dev[off:off + n], self.flat_dev[off + n:off + 2 * n]))
+                    off += 2 * n
+                out.append(cur)
+            return out, (self.nb_dev if self.nb_dev is not None else max(self.n_boxes / self.world, 1.0))
         if self.event is not None:
             self.event.synchronize()
         assert bool(self.ok[0]), "degenerate boxes (x1 < x0 or y1 < y0) reached the matcher"   # util/box_ops.py:48-49

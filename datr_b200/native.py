@@ -17,7 +17,7 @@ SOURCES = [os.path.join(_PKG, "csrc", "msda.cu"), os.path.join(_PKG, "csrc", "li
            os.path.join(_PKG, "csrc", "layernorm.cu"), os.path.join(_PKG, "csrc", "colsum.cu"),
            os.path.join(_PKG, "csrc", "conv3x3_tf32.cu"), os.path.join(_PKG, "csrc", "wgrad_tf32.cu"),
            os.path.join(_PKG, "csrc", "rowmask.cu"), os.path.join(_PKG, "csrc", "attn_softmax.cu"),
-           os.path.join(_PKG, "csrc", "attn_fused.cu"), os.path.join(_PKG, "csrc", "decoder_ops.cu"), os.path.join(_PKG, "csrc", "adamw.cu"),
+           os.path.join(_PKG, "csrc", "attn_fused.cu"), os.path.join(_PKG, "csrc", "decoder_ops.cu"), os.path.join(_PKG, "csrc", "adamw.cu"), os.path.join(_PKG, "csrc", "lsa.cu"),
            os.path.join(_PKG, "csrc", "ema.cu")]
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
@@ -36,6 +36,7 @@ EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward",
            "datr_attn_mask_words", "datr_attn_pack_mask", "datr_attn_fused_forward", "datr_attn_fused_backward", "datr_attn_fused_last_error",
            "datr_attn_fused_launch_count", "datr_sine_embed", "datr_decoder_ops_last_error", "datr_decoder_ops_launch_count",
            "datr_adamw_step", "datr_adamw_last_error", "datr_adamw_launch_count",
+           "datr_lsa_solve", "datr_lsa_last_error", "datr_lsa_launch_count",
            "datr_ema_update", "datr_ema_last_error", "datr_ema_launch_count")
 
 _lock = threading.Lock()
@@ -187,6 +188,10 @@ def lib() -> ctypes.CDLL:
         L.datr_adamw_step.argtypes = [vp, vp, i, vp, fl, fl, fl, fl, fl, vp]
         L.datr_adamw_last_error.restype = ctypes.c_char_p
         L.datr_adamw_launch_count.restype = ctypes.c_uint64
+        L.datr_lsa_solve.restype = i
+        L.datr_lsa_solve.argtypes = [vp, vp, i, i, i, vp, vp]
+        L.datr_lsa_last_error.restype = ctypes.c_char_p
+        L.datr_lsa_launch_count.restype = ctypes.c_uint64
         L.datr_ema_update.restype = i
         L.datr_ema_update.argtypes = [vp, vp, i, ctypes.c_float, ctypes.c_float, vp]
         L.datr_ema_last_error.restype = ctypes.c_char_p
@@ -211,7 +216,8 @@ def all_launch_count() -> int:
     """Every hand-written kernel launch issued through the library by this process."""
     return (launch_count() + linear_launch_count() + layernorm_launch_count() + colsum_launch_count()
             + conv_launch_count() + wgrad_launch_count() + rowmask_launch_count() + attn_launch_count() + ema_launch_count()
-            + int(lib().datr_decoder_ops_launch_count()) + int(lib().datr_adamw_launch_count()))
+            + int(lib().datr_decoder_ops_launch_count()) + int(lib().datr_adamw_launch_count())
+            + int(lib().datr_lsa_launch_count()))
 
 
 def ema_launch_count() -> int:
