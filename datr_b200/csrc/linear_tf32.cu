@@ -422,13 +422,7 @@ int datr_linear_bf16(const void* x, const void* w, const float* bias, const void
   if (!al16(x) || !al16(w) || !al16(y) || (bias && !al16(bias)) || (residual && !al16(residual)))
     return lfail(DATR_LINEAR_ERR_ALIGNMENT, "buffers must be 16-byte aligned%s");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  CUtensorMap mx, mw;
   const bool wide = N > 256 && (N % 256 == 0 || N % 256 > 128);
-  if (int rc = make_map(&mx, x, M, K, BM, true)) return rc;
-  if (int rc = make_map(&mw, w, N, K, wide ? 256 : 128, true)) return rc;
-  const int flags = (y_bf16 ? 1 : 0) | (residual_bf16 ? 2 : 0);
-  CUtensorMap my, mr;
-  const CUtensorMap *pmy = nullptr, *pmr = nullptr;
   if (y_bf16) {
     // bf16 outputs leave through TMA stores of {64 columns x 32 rows} boxes; the only residual they take is the bf16 ReLU mask
     if (N % (wide ? 256 : 128) != 0) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "bf16 outputs need N to be a multiple of the tile width (128 / 256)%s");
@@ -436,14 +430,22 @@ int datr_linear_bf16(const void* x, const void* w, const float* bias, const void
       return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "bf16 outputs take no residual except the bf16 ReLU mask of relu == 3%s");
     if (relu == 3 && !residual) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "relu == 3 needs the saved activation%s");
     if (relu != 0 && relu != 1 && relu != 3) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "bf16 outputs support relu 0, 1 and 3%s");
+  } else if (residual_bf16) {
+    return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "a bf16 residual is the ReLU mask of a bf16 output only%s");
+  }
+  CUtensorMap mx, mw;
+  if (int rc = make_map(&mx, x, M, K, BM, true)) return rc;
+  if (int rc = make_map(&mw, w, N, K, wide ? 256 : 128, true)) return rc;
+  const int flags = (y_bf16 ? 1 : 0) | (residual_bf16 ? 2 : 0);
+  CUtensorMap my, mr;
+  const CUtensorMap *pmy = nullptr, *pmr = nullptr;
+  if (y_bf16) {
     if (int rc = make_map(&my, y, M, N, 32, true)) return rc;
     pmy = &my;
     if (residual) {
       if (int rc = make_map(&mr, residual, M, N, 32, true)) return rc;
       pmr = &mr;
     }
-  } else if (residual_bf16) {
-    return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "a bf16 residual is the ReLU mask of a bf16 output only%s");
   }
   return wide ? launch<256, 3, true>(mx, mw, bias, static_cast<const float*>(residual), static_cast<float*>(y), M, N, K, relu, stream, flags, pmy, pmr)
               : launch<128, 5, true>(mx, mw, bias, static_cast<const float*>(residual), static_cast<float*>(y), M, N, K, relu, stream, flags, pmy, pmr);

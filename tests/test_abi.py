@@ -66,6 +66,24 @@ def test_bad_arguments_return_error_codes_without_touching_the_gpu():
     assert lib.datr_ema_update(None, None, 1, 0.5, 0.5, None) == -1
     assert lib.datr_zero_masked_rows(p, p, 4, 3, None) == -1
     assert lib.datr_layernorm256_forward(p, p, p, 1e-5, p, p, p, 0, None) == -1
+    # round-2 entry points
+    assert lib.datr_attn_fused_forward(None, 512, None, 512, None, 256, None, 1, 8, 16, 0.1, None, None, None, None) == -1
+    assert lib.datr_attn_fused_forward(p, 100, p, 512, p, 256, p, 1, 8, 16, 0.1, p, None, None, None) == -1       # row stride < H * 32
+    assert b"row strides" in lib.datr_attn_fused_last_error()
+    assert lib.datr_attn_pack_mask(None, 0, None, None, None) == -1
+    assert lib.datr_attn_mask_words(1100) == 36 and lib.datr_attn_mask_words(128) == 4
+    assert lib.datr_linear_bf16(p, p, None, None, 0, p, 0, 8, 64, 96, 0, None) == -1 and b"64" in lib.datr_linear_last_error()
+    assert lib.datr_linear_bf16(p, p, None, p, 0, p, 1, 8, 256, 64, 0, None) == -1                               # bf16 output + fp32 residual
+    assert lib.datr_linear_wgrad_bf16(None, p, p, None, 8, 64, 64, None) == -1
+    assert lib.datr_sine_embed(p, p, 4, 3, p, None) == -1
+    assert lib.datr_adamw_step(None, None, 1, None, 0.9, 0.999, 1e-8, 0.1, 0.03, None) == -1
+    assert lib.datr_adamw_step(p, p, 1, None, 0.9, 0.999, 1e-8, 0.0, 0.03, None) == -1                           # bias correction must be > 0
+    assert lib.datr_lsa_solve(None, None, 1, 900, 10, None, None) == -1
+    assert lib.datr_lsa_solve(p, p, 1, 10, 900, p, None) == -4 and b"more boxes" in lib.datr_lsa_last_error()
+    assert lib.datr_msda_pack_value_pairs(p, p, p, 1, 1, 1, 1, 7, p, None) == -1 and b"storage" in lib.datr_last_error()
+    lib.datr_msda_set_backward_stages(2)
+    assert lib.datr_msda_get_backward_stages() == 2
+    lib.datr_msda_set_backward_stages(-1)
 
 
 def test_shim_refuses_cpu_tensors_like_the_reference():
