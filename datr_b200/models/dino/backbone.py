@@ -179,10 +179,30 @@ class _Body(nn.Module):
         self.return_layers = dict(return_layers)
         self._last = last
 
+    def _stem(self, x):
+        """conv1 -> bn1 -> ReLU -> MaxPool2d(3, 2, 1).  On NHWC CUDA tensors without gradient (the stem is frozen in every
+        DATR configuration) the last three run as one kernel (datr_bn_relu_maxpool_nhwc)."""
+        y = self.conv1(x)
+        if (y.is_cuda and y.dtype == torch.float32 and not y.requires_grad and isinstance(self.bn1, FrozenBatchNorm2d)
+                and y.is_contiguous(memory_format=torch.channels_last) and y.shape[1] % 4 == 0):
+            from datr_b200 import native
+            n, c, h, w = y.shape
+            scale, shift = self.bn1.scale_shift()
+            out = torch.empty((n, c, (h - 1) // 2 + 1, (w - 1) // 2 + 1), dtype=torch.float32, device=y.device,
+                              memory_format=torch.channels_last)
+            lib = native.lib()
+            with torch.cuda.device(y.device):
+                rc = lib.datr_bn_relu_maxpool_nhwc(y.data_ptr(), scale.contiguous().data_ptr(), shift.contiguous().data_ptr(),
+                                                   n, h, w, c, out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            if rc != 0:
+                raise RuntimeError(f"datr_bn_relu_maxpool_nhwc failed (code {rc}): {lib.datr_decoder_ops_last_error().decode()}")
+            return out
+        return F.max_pool2d(F.relu(self.bn1(y)), 3, stride=2, padding=1)
+
     def forward(self, x):
         out = {}
         with fold_frozen_bn(self):
-            x = F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, stride=2, padding=1)
+            x = self._stem(x)
             for i in range(1, self._last + 1):
                 name = f"layer{i}"
                 # stem and layer1 never train (BackboneBase): no autograd graph through them

@@ -34,6 +34,24 @@ class PositionEmbeddingSineHW(nn.Module):
         if self.normalize:
             y = y / (y[:, -1:, :] + 1e-6) * self.scale
             x = x / (x[:, :, -1:] + 1e-6) * self.scale
+        if y.is_cuda and (str(y.device) in self.__dict__.get("_dim_t", {}) or not torch.cuda.is_current_stream_capturing()):
+            # one kernel for both axes (csrc/decoder_ops.cu) instead of ~20 ATen launches per level; no gradient involved
+            from datr_b200 import native
+            tabs = self.__dict__.setdefault("_dim_t", {})
+            if str(y.device) not in tabs:
+                i = torch.arange(self.num_pos_feats, dtype=torch.float32, device=y.device)
+                e = 2 * torch.div(i, 2, rounding_mode="floor") / self.num_pos_feats
+                tabs[str(y.device)] = (self.temperatureH ** e, self.temperatureW ** e)
+            th, tw = tabs[str(y.device)]
+            y, x = y.contiguous(), x.contiguous()
+            pos = torch.empty(y.shape + (2 * self.num_pos_feats,), dtype=torch.float32, device=y.device)
+            lib = native.lib()
+            with torch.cuda.device(y.device):
+                rc = lib.datr_pos_embed_hw(y.data_ptr(), x.data_ptr(), th.data_ptr(), tw.data_ptr(), y.numel(),
+                                           self.num_pos_feats, pos.data_ptr(), torch.cuda.current_stream().cuda_stream)
+            if rc != 0:
+                raise RuntimeError(f"datr_pos_embed_hw failed (code {rc}): {lib.datr_decoder_ops_last_error().decode()}")
+            return pos.permute(0, 3, 1, 2)
         pos = torch.cat((self._axis(y, self.temperatureH), self._axis(x, self.temperatureW)), dim=3)
         return pos.permute(0, 3, 1, 2)
 

@@ -34,7 +34,7 @@ EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward",
            "datr_zero_masked_rows", "datr_rowmask_last_error", "datr_rowmask_launch_count",
            "datr_attn_softmax_forward", "datr_attn_softmax_backward", "datr_attn_last_error", "datr_attn_launch_count",
            "datr_attn_mask_words", "datr_attn_pack_mask", "datr_attn_fused_forward", "datr_attn_fused_backward", "datr_attn_fused_last_error",
-           "datr_attn_fused_launch_count", "datr_sine_embed", "datr_decoder_ops_last_error", "datr_decoder_ops_launch_count",
+           "datr_attn_fused_launch_count", "datr_sine_embed", "datr_pos_embed_hw", "datr_bn_relu_maxpool_nhwc", "datr_decoder_ops_last_error", "datr_decoder_ops_launch_count",
            "datr_adamw_step", "datr_adamw_last_error", "datr_adamw_launch_count",
            "datr_lsa_solve", "datr_lsa_last_error", "datr_lsa_launch_count",
            "datr_ema_update", "datr_ema_last_error", "datr_ema_launch_count")
@@ -181,6 +181,10 @@ def lib() -> ctypes.CDLL:
         L.datr_attn_fused_launch_count.restype = ctypes.c_uint64
         L.datr_sine_embed.restype = i
         L.datr_sine_embed.argtypes = [vp, vp, ll, i, vp, vp]
+        L.datr_pos_embed_hw.restype = i
+        L.datr_pos_embed_hw.argtypes = [vp, vp, vp, vp, ll, i, vp, vp]
+        L.datr_bn_relu_maxpool_nhwc.restype = i
+        L.datr_bn_relu_maxpool_nhwc.argtypes = [vp, vp, vp, i, i, i, i, vp, vp]
         L.datr_decoder_ops_last_error.restype = ctypes.c_char_p
         L.datr_decoder_ops_launch_count.restype = ctypes.c_uint64
         L.datr_adamw_step.restype = i
