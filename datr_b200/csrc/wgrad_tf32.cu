@@ -292,7 +292,11 @@ int launch(const CUtensorMap& mdz, const CUtensorMap& mx, float* dw, float* db, 
   // 256 x 256, 173 -> 162 us at 256 x 2048), two waves when it has many (N = 2048: 136 vs 157 us).
   const int waves = N <= 256 ? 1 : 2;
   int splits = (waves * sms + tiles - 1) / tiles;
-  const int max_splits = (M + 4 * BK - 1) / (4 * BK);         // at least 128 rows per slab
+  // at least 128 rows per slab; 512 for the wide decoder-size gradients (M = 4 400, N x K = 2048 x 256: 37.6 -> 30.6 us,
+  // 256 x 2048: 39.3 -> 28.7 us, tools/bench_wgrad_small.py); DATR_WGRAD_MIN_ROWS overrides (tuning hook)
+  static const int forced_rows = getenv("DATR_WGRAD_MIN_ROWS") ? atoi(getenv("DATR_WGRAD_MIN_ROWS")) : 0;
+  const int min_rows = forced_rows > 0 ? forced_rows : ((long long)N * K >= 2048LL * 256 ? 16 * BK : 4 * BK);
+  const int max_splits = (M + min_rows - 1) / min_rows;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int rows_per_split = ((M + splits - 1) / splits + BKr - 1) / BKr * BKr;
