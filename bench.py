@@ -86,7 +86,7 @@ def gpu_baseline_record():
     """The reference model itself on a B200 of this pool (tools/bench_reference_gpu.py; committed measurement)."""
     out = {}
     for tag in ("4scale", "5scale"):
-        p = os.path.join(ROOT, "profiles", f"r02q_reference_gpu_{tag}_init.json")
+        p = os.path.join(ROOT, "profiles", f"r02bb_reference_gpu_{tag}_init.json")
         if os.path.exists(p):
             try:
                 d = json.load(open(p))
@@ -98,7 +98,7 @@ def gpu_baseline_record():
     if out:
         out["what"] = ("UNMODIFIED reference DINO (baseline/_ref) + its own MSDeformAttn CUDA extension rebuilt for sm_100a "
                        "(oracle/_ref), eager engine.py step on one B200 of this pool, identical synthetic batch; measured by "
-                       "tools/bench_reference_gpu.py in an earlier gpurun call (profiles/r02q_reference_gpu_*_init.json), "
+                       "tools/bench_reference_gpu.py in an earlier gpurun call (profiles/r02bb_reference_gpu_*_init.json), "
                        "NOT in this run; --gpu-baseline re-measures it live")
     return out or None
 
