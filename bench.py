@@ -51,6 +51,8 @@ FALLBACK_HBM_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallba
 # forward 116.2 + 29.4 MB, backward 238.5 + 98.9 MB; the plain-op kernels of profiles/r01b_msda_ncu_full.txt moved
 # 142.6 / 340.9 MB)
 TRAFFIC_NCU = {"msda_fwd_f32_d32": 145.6e6, "msda_bwd_f32_d32": 337.4e6}
+# algorithmic bytes of the 2-image encoder call those captures profiled: forward 159.29 MB, backward 273.08 MB
+TRAFFIC_ALGO = {"msda_fwd_f32_d32": 159.29e6, "msda_bwd_f32_d32": 273.08e6}
 
 
 def hbm_peak():
@@ -324,8 +326,13 @@ class MsdaStep:
                       "top_kernel_frac": lin[ktop][3] / lin[ktop][0] / 1e12 / tpeak, "share_of_timed_kernels": tt / total}
             for k in lin:
                 per_kernel[k]["tensor_pipe_frac"] = per_kernel[k]["tflops"] / tpeak
+        # ncu's DRAM traffic was captured on a 2-image call; launches of the joint encoder pass carry 4 images: scale to
+        # the launch the algorithmic bytes describe (both are linear in the batch)
+        traffic = TRAFFIC_NCU.get(top.split("<")[0])
+        if traffic is not None and top.endswith("encoder"):
+            traffic = traffic * (b / n) / (TRAFFIC_ALGO.get(top.split("<")[0], b / n))
         return {"bound": "hbm", "kernel": top, "achieved": b / t / 1e9, "peak": peak, "peak_source": peak_src, "tensor": tensor,
-                "unit": "GB/s", "frac": b / t / 1e9 / peak, "traffic": TRAFFIC_NCU.get(top.split("<")[0]),
+                "unit": "GB/s", "frac": b / t / 1e9 / peak, "traffic": traffic,
                 "algorithmic_bytes_per_launch": b / n, "avg_launch_us": t / n * 1e6, "share_of_step": t / total,
                 "handwritten_kernel_ms_per_step": None, "per_kernel": per_kernel}
 
