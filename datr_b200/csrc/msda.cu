@@ -771,6 +771,13 @@ int allow_big_smem() {
   DATR_OPT_TMA(1); DATR_OPT_TMA(2);
 #undef DATR_OPT_TMA
 #undef DATR_OPT
+  // tuning hook: preferred shared-memory carve-out (percent of the 228 KB) of the DINO-configuration kernels
+  if (const char* c = getenv("DATR_MSDA_CARVEOUT")) {
+    const int pct = atoi(c);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(msda_bwd_f32_d32<4, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(msda_bwd_f32_d32<4, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(msda_bwd_f32_d32<4, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
   if (e != cudaSuccess) return fail(DATR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   done.fetch_or(bit, std::memory_order_release);
   return DATR_OK;
