@@ -14,6 +14,23 @@ from torchvision.ops.boxes import batched_nms
 from datr_b200.util import box_ops
 
 
+_CONSTANTS = {}
+
+
+def _device_constant(array, dtype, device):
+    """A small host array as a device tensor, uploaded once per distinct content: a pageable host->device copy is ordered
+    behind everything already enqueued on the stream and blocks the host until then (the per-class thresholds and the
+    image-index lists of the self-training step were re-uploaded per image and step: two such stalls per step)."""
+    a = np.asarray(array)                      # (0-dim arrays stay 0-dim: a scalar threshold)
+    key = (a.tobytes(), str(a.dtype), a.shape, dtype, str(device))
+    t = _CONSTANTS.get(key)
+    if t is None:
+        if len(_CONSTANTS) > 256:
+            _CONSTANTS.clear()
+        t = _CONSTANTS[key] = torch.as_tensor(a, dtype=dtype, device=device)
+    return t
+
+
 def get_unlabel_img(nestedtensor):
     """Target-domain (second) half of a NestedTensor batch: images [B/2, 3, H, W]  (:15-20)."""
     images, _ = nestedtensor.decompose()
@@ -28,7 +45,7 @@ def get_pseudo_label_via_threshold(results, threshold=0.8):
     thr = np.asarray(threshold, dtype=np.float64)
     for n, result in enumerate(results):
         scores, labels = result["scores"], result["labels"]
-        table = torch.as_tensor(thr, dtype=torch.float64, device=scores.device)
+        table = _device_constant(thr, torch.float64, scores.device)
         keep = scores >= (table[labels] if table.dim() else table)
         kept = labels[keep]
         if len(kept) > 0:
@@ -77,6 +94,9 @@ def spilt_output(output_dict):
 def get_valid_output(target_outputs, target_pseudo_labels_dict, idx):
     """Target outputs restricted to the images `idx` that have pseudo labels, and the pseudo labels as a list
     (:103-146)."""
+    first = next((v for k, v in target_outputs.items() if "pred" in k), None)
+    if first is not None and first.is_cuda and isinstance(idx, (list, tuple)):
+        idx = _device_constant(np.asarray(idx, dtype=np.int64), torch.int64, first.device)     # same advanced indexing, no upload
     pick = lambda d: {"pred_logits": d["pred_logits"][idx, :, :], "pred_boxes": d["pred_boxes"][idx, :, :]}
     valid = {}
     for k, v in target_outputs.items():
