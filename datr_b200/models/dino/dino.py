@@ -24,7 +24,7 @@ from torch import nn
 
 from datr_b200 import graphs
 from datr_b200.util import box_ops
-from datr_b200.util.misc import (NestedTensor, accuracy, get_world_size, inverse_sigmoid,
+from datr_b200.util.misc import (NestedTensor, accuracy, get_world_size, inverse_sigmoid, upload,
                                  is_dist_avail_and_initialized, nested_tensor_from_tensor_list)
 from ..registry import MODULE_BUILD_FUNCS
 from .backbone import build_backbone
@@ -425,7 +425,7 @@ class SetCriterion(nn.Module):
         if cached is not None and cached[0] == counts and cached[1].device == logits.device:
             n_tgt = cached[1]
         else:
-            n_tgt = torch.as_tensor(counts, device=logits.device)
+            n_tgt = upload(counts, device=logits.device)
             self._n_tgt = (counts, n_tgt)
         n_pred = (logits.argmax(-1) != logits.shape[-1] - 1).sum(1)
         return {"cardinality_error": F.l1_loss(n_pred.float(), n_tgt.float())}
@@ -503,7 +503,7 @@ class SetCriterion(nn.Module):
             toff = np.concatenate([np.full(lens[i], offs[i], dtype=np.int64) for g in range(groups) for i in range(bs)])
             if len(cache) > 64:
                 cache.clear()
-            cache[key] = (torch.as_tensor(gb, device=device), torch.as_tensor(toff, device=device))
+            cache[key] = (upload(gb, device=device), upload(toff, device=device))
         return cache[key]
 
     def _batched_helpers(self, outputs, targets, pre):
@@ -523,7 +523,7 @@ class SetCriterion(nn.Module):
         helpers = {"m": self._family_helpers("m", counts, lens, len(sets), device)}
         cached = getattr(self, "_n_tgt", None)
         if cached is None or cached[0] != counts or cached[1].device != device:
-            self._n_tgt = cached = (counts, torch.as_tensor(counts, device=device))
+            self._n_tgt = cached = (counts, upload(counts, device=device))
         helpers["n_tgt"] = cached[1]
         dn_meta = outputs.get("dn_meta")
         if self.training and dn_meta and "output_known_lbs_bboxes" in dn_meta:
@@ -746,7 +746,7 @@ class SetCriterion(nn.Module):
             num_boxes = nb      # counted (and all-reduced) by BatchedMatch without a host->device copy or a sync here
         else:
             n_local = sum(len(t["labels"]) for t in targets) if indices is not None else 1
-            num_boxes = torch.as_tensor([n_local], dtype=torch.float, device=outputs["pred_logits"].device)
+            num_boxes = upload([n_local], dtype=torch.float, device=outputs["pred_logits"].device)
             if is_dist_avail_and_initialized():
                 torch.distributed.all_reduce(num_boxes)
             if indices is None:

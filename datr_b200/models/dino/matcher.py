@@ -11,6 +11,7 @@ from scipy.optimize import linear_sum_assignment
 from torch import nn
 
 from datr_b200.util.box_ops import box_cxcywh_to_xyxy, boxes_well_formed, generalized_box_iou
+from datr_b200.util.misc import upload
 
 
 # Solve the assignments of a step on the GPU (csrc/lsa.cu) instead of scipy on a host copy of the cost matrix: same
@@ -88,7 +89,7 @@ class BatchedMatch:
             nb = None
             if torch.distributed.is_available() and torch.distributed.is_initialized():
                 self.world = torch.distributed.get_world_size()
-                nb = torch.as_tensor([n_boxes], dtype=torch.float, device=dev)
+                nb = upload([n_boxes], dtype=torch.float, device=dev)
                 torch.distributed.all_reduce(nb)
             if dev.type == "cuda" and DEVICE_SOLVER and self._solve_on_device(C, ok[0], nb, n_boxes):
                 pass
@@ -133,7 +134,7 @@ class BatchedMatch:
                     off += 2 * n
             if len(BatchedMatch._problem_tables) > 64:
                 BatchedMatch._problem_tables.clear()
-            hit = BatchedMatch._problem_tables[key] = (torch.tensor(rows, dtype=torch.int64, device=dev), max(sizes), off)
+            hit = BatchedMatch._problem_tables[key] = (upload(rows, dtype=torch.int64, device=dev), max(sizes), off)
         table, max_nt, total = hit
         C = C.contiguous()
         flat = torch.empty(total, dtype=torch.int64, device=dev)

@@ -88,3 +88,15 @@ def get_rank():
 
 def is_main_process():
     return get_rank() == 0
+
+
+def upload(data, dtype=None, device=None):
+    """Small host data (lists of ints / floats) as a device tensor WITHOUT stalling the host: a pageable host->device copy
+    (torch.as_tensor(list, device="cuda")) is ordered behind everything already enqueued on the stream and blocks the
+    calling thread until then -- with per-step target counts that is one pipeline drain per call.  Staging through pinned
+    memory makes the copy asynchronous (the caching host allocator keeps the staging buffer alive until it has run)."""
+    t = torch.as_tensor(data, dtype=dtype)
+    device = torch.device(device) if device is not None else t.device
+    if device.type != "cuda":
+        return t.to(device)
+    return t.pin_memory().to(device, non_blocking=True)
