@@ -38,6 +38,9 @@ _JOINT_ENCODER = os.environ.get("DATR_JOINT_ENCODER", "1") != "0"
 _JOINT_DECODER = os.environ.get("DATR_JOINT_DECODER", "1") != "0"
 
 
+_OWN_GROUPNORM = os.environ.get("DATR_OWN_GROUPNORM", "1") != "0"
+
+
 class DINO(nn.Module):
     """Backbone -> input projections -> (CDN queries) -> deformable transformer -> class / box heads,
     plus in training mode the image-level discriminator, class prototypes and a second transformer pass
@@ -200,14 +203,19 @@ class DINO(nn.Module):
             n, cin, h, w = x.shape
             if conv.kernel_size == (1, 1) and conv.stride == (1, 1) and cin % 32 == 0:
                 y = dl.linear(x.permute(0, 2, 3, 1).reshape(-1, cin), conv.weight.reshape(conv.out_channels, cin), conv.bias)
-                y = norm(y.view(n, h, w, conv.out_channels).permute(0, 3, 1, 2))
-                # ATen's CUDA GroupNorm hands back an NCHW-contiguous tensor: return to NHWC once, here, so that the
-                # discriminator convolutions and the token flattening downstream work on views
-                return y.contiguous(memory_format=torch.channels_last)
+                return DINO._group_norm(norm, y.view(n, h, w, conv.out_channels).permute(0, 3, 1, 2))
             if dconv.use_kernel(x, conv):
-                y = norm(dconv.conv3x3_bias_act(x, conv.weight, conv.bias, conv.stride[0], 0))
-                return y.contiguous(memory_format=torch.channels_last)
+                return DINO._group_norm(norm, dconv.conv3x3_bias_act(x, conv.weight, conv.bias, conv.stride[0], 0))
         return proj(x)
+
+    @staticmethod
+    def _group_norm(norm, y):
+        """GroupNorm of an NHWC map on the NHWC kernel (datr_b200.groupnorm); ATen's CUDA GroupNorm is NCHW and hands back
+        an NCHW-contiguous tensor, which then returns to NHWC once so that everything downstream works on views."""
+        from datr_b200 import groupnorm as gn
+        if isinstance(norm, nn.GroupNorm) and gn.applicable(norm, y) and _OWN_GROUPNORM:
+            return gn.group_norm_nhwc(norm, y)
+        return norm(y).contiguous(memory_format=torch.channels_last)
 
     def _project_levels(self, features, poss, full_mask):
         srcs, masks = [], []

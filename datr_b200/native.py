@@ -17,7 +17,7 @@ SOURCES = [os.path.join(_PKG, "csrc", "msda.cu"), os.path.join(_PKG, "csrc", "li
            os.path.join(_PKG, "csrc", "layernorm.cu"), os.path.join(_PKG, "csrc", "colsum.cu"),
            os.path.join(_PKG, "csrc", "conv3x3_tf32.cu"), os.path.join(_PKG, "csrc", "wgrad_tf32.cu"),
            os.path.join(_PKG, "csrc", "rowmask.cu"), os.path.join(_PKG, "csrc", "attn_softmax.cu"),
-           os.path.join(_PKG, "csrc", "attn_fused.cu"), os.path.join(_PKG, "csrc", "decoder_ops.cu"), os.path.join(_PKG, "csrc", "adamw.cu"), os.path.join(_PKG, "csrc", "lsa.cu"),
+           os.path.join(_PKG, "csrc", "attn_fused.cu"), os.path.join(_PKG, "csrc", "decoder_ops.cu"), os.path.join(_PKG, "csrc", "adamw.cu"), os.path.join(_PKG, "csrc", "lsa.cu"), os.path.join(_PKG, "csrc", "groupnorm.cu"),
            os.path.join(_PKG, "csrc", "ema.cu")]
 INCLUDE_DIR = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libdatr_b200.so")
@@ -37,6 +37,7 @@ EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward",
            "datr_attn_fused_launch_count", "datr_sine_embed", "datr_pos_embed_hw", "datr_bn_relu_maxpool_nhwc", "datr_decoder_ops_last_error", "datr_decoder_ops_launch_count",
            "datr_adamw_step", "datr_adamw_last_error", "datr_adamw_launch_count",
            "datr_lsa_solve", "datr_lsa_last_error", "datr_lsa_launch_count",
+           "datr_groupnorm_nhwc_forward", "datr_groupnorm_nhwc_backward", "datr_groupnorm_last_error", "datr_groupnorm_launch_count",
            "datr_ema_update", "datr_ema_last_error", "datr_ema_launch_count")
 
 _lock = threading.Lock()
@@ -196,6 +197,12 @@ def lib() -> ctypes.CDLL:
         L.datr_lsa_solve.argtypes = [vp, vp, i, i, i, vp, vp]
         L.datr_lsa_last_error.restype = ctypes.c_char_p
         L.datr_lsa_launch_count.restype = ctypes.c_uint64
+        L.datr_groupnorm_nhwc_forward.restype = i
+        L.datr_groupnorm_nhwc_forward.argtypes = [vp, vp, vp, i, ll, i, i, ctypes.c_float, vp, vp, vp, vp, vp]
+        L.datr_groupnorm_nhwc_backward.restype = i
+        L.datr_groupnorm_nhwc_backward.argtypes = [vp, vp, vp, vp, vp, i, ll, i, i, vp, vp, vp, vp, vp]
+        L.datr_groupnorm_last_error.restype = ctypes.c_char_p
+        L.datr_groupnorm_launch_count.restype = ctypes.c_uint64
         L.datr_ema_update.restype = i
         L.datr_ema_update.argtypes = [vp, vp, i, ctypes.c_float, ctypes.c_float, vp]
         L.datr_ema_last_error.restype = ctypes.c_char_p
@@ -221,7 +228,7 @@ def all_launch_count() -> int:
     return (launch_count() + linear_launch_count() + layernorm_launch_count() + colsum_launch_count()
             + conv_launch_count() + wgrad_launch_count() + rowmask_launch_count() + attn_launch_count() + ema_launch_count()
             + int(lib().datr_decoder_ops_launch_count()) + int(lib().datr_adamw_launch_count())
-            + int(lib().datr_lsa_launch_count()))
+            + int(lib().datr_lsa_launch_count()) + int(lib().datr_groupnorm_launch_count()))
 
 
 def ema_launch_count() -> int:
