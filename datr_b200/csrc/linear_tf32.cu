@@ -57,6 +57,13 @@ __device__ __forceinline__ void store_bf16x4(float* y, size_t off, const float4&
       make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
 }
 
+// MN-major 32-bit B tile: {32 columns x 32 rows} boxes 4096 bytes apart (leading byte offset), swizzle atom of 4 rows
+// (512 bytes = stride byte offset), layout type SWIZZLE_128B_BASE32B, descriptor version 1 (see wgrad_tf32.cu)
+__device__ __forceinline__ uint64_t mnmajor_b_desc(uint32_t smem_addr) {
+  return uint64_t((smem_addr >> 4) & 0x3FFF) | (uint64_t(4096 >> 4) << 16) | (uint64_t(512 >> 4) << 32) |
+         (uint64_t(1) << 46) | (uint64_t(1) << 61);
+}
+
 constexpr int kStoreTile = 8192;   // bf16-output epilogue: per warp, up to two {64 columns x 32 rows} boxes of 4 KB
 
 template <int BN, int STAGES, bool kBF16 = false>
@@ -75,7 +82,11 @@ struct Smem {
 // kBF16: operands are bf16 in HBM (64 elements per 128-byte swizzle row, tcgen05.mma.kind::f16 with K = 16: the same
 // bytes per pipeline stage feed twice the FLOPs, which is what the shared-memory-port-bound TF32 loop lacks); accumulation
 // stays fp32.  `flags` bit 0: the output is written as bf16; bit 1: `residual` (the ReLU-mask source of relu == 3) is bf16.
-template <int BN, int STAGES, bool kBF16 = false>
+// kBT (TF32 only): the weight operand is given TRANSPOSED, w_t [K, N] row-major -- what the input gradient of a Linear
+// needs (dx = dy . W with W stored [N_fwd, K_fwd]): its tiles are MN-major B operands (TMA boxes of {32 columns x 32 rows}
+// with the 32-byte-atom swizzle, transposed-operand bit of the instruction descriptor, as in wgrad_tf32.cu), so the
+// backward no longer materialises W^T with a copy kernel per layer and step.
+template <int BN, int STAGES, bool kBF16 = false, bool kBT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w,
                    const float* __restrict__ bias, const float* __restrict__ residual, float* __restrict__ y,
@@ -127,13 +138,18 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_const
           // all pull the same W lines out of the same L2 slices at the same time (the sum is order-independent)
           const int kk = (kb + tile) % kblocks;
           tma_load_2d(a, &tma_x, kk * BKe, m0, full + s);
-          tma_load_2d(a + L::kA, &tma_w, kk * BKe, n0, full + s);
+          if constexpr (kBT) {
+#pragma unroll
+            for (int c = 0; c < BN / 32; ++c) tma_load_2d(a + L::kA + c * 4096, &tma_w, n0 + 32 * c, kk * BK, full + s);
+          } else {
+            tma_load_2d(a + L::kA, &tma_w, kk * BKe, n0, full + s);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = kBF16 ? bf16_idesc<BN>() : tf32_idesc<BN>();
+      constexpr uint32_t idesc = kBF16 ? bf16_idesc<BN>() : (kBT ? (tf32_idesc<BN>() | (1u << 16)) : tf32_idesc<BN>());
       uint32_t it = 0, ti = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++ti) {
         const uint32_t as = ti & 1;
@@ -145,10 +161,12 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_const
           mbar_wait(full + s, (it / STAGES) & 1);
           tc_fence_after();
           const uint32_t a = smem_u32(smem + s * L::kStage);
-          const uint64_t ad = kmajor_sw128_desc(a), bd = kmajor_sw128_desc(a + L::kA);
+          const uint64_t ad = kmajor_sw128_desc(a);
+          const uint64_t bd = kBT ? mnmajor_b_desc(a + L::kA) : kmajor_sw128_desc(a + L::kA);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) { // +32 bytes along K inside the swizzle row = +2 in the address field
             if constexpr (kBF16) umma_bf16(tmem_d, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0);
+            else if constexpr (kBT) umma_tf32(tmem_d, ad + uint64_t(k * 2), bd + uint64_t(k * 64), idesc, (kb | k) != 0);   // 8 rows of w_t = +1024 bytes
             else umma_tf32(tmem_d, ad + uint64_t(k * 2), bd + uint64_t(k * 2), idesc, (kb | k) != 0);
           }
           umma_commit(empty + s);                // frees the stage once these MMAs have read it
@@ -356,7 +374,7 @@ int make_map(CUtensorMap* map, const void* base, int rows, int cols, int box_row
   return DATR_LINEAR_OK;
 }
 
-template <int BN, int STAGES, bool kBF16 = false>
+template <int BN, int STAGES, bool kBF16 = false, bool kBT = false>
 int launch(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const float* residual, float* y, int M, int N,
            int K, int relu, cudaStream_t stream, int flags = 0, const CUtensorMap* my = nullptr, const CUtensorMap* mr = nullptr) {
   using L = Smem<BN, STAGES, kBF16>;
@@ -366,7 +384,7 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, cons
   cudaGetDevice(&dev);
   const uint64_t bit = 1ull << (dev & 63);
   if (!(opted.load(std::memory_order_acquire) & bit)) {
-    const cudaError_t e = cudaFuncSetAttribute(linear_tf32_kernel<BN, STAGES, kBF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    const cudaError_t e = cudaFuncSetAttribute(linear_tf32_kernel<BN, STAGES, kBF16, kBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return lfail(DATR_LINEAR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     opted.fetch_or(bit, std::memory_order_release);
   }
@@ -378,7 +396,7 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, cons
   }
   const long long tiles = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
   const unsigned grid = unsigned(tiles < sms ? tiles : sms);
-  linear_tf32_kernel<BN, STAGES, kBF16><<<grid, kThreads, L::kTotal, stream>>>(mx, mw, bias, residual, y, M, N, K, relu, flags, my ? *my : no_map,
+  linear_tf32_kernel<BN, STAGES, kBF16, kBT><<<grid, kThreads, L::kTotal, stream>>>(mx, mw, bias, residual, y, M, N, K, relu, flags, my ? *my : no_map,
                                                                                mr ? *mr : no_map);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return lfail(DATR_LINEAR_ERR_CUDA, "linear_tf32_kernel launch: %s", cudaGetErrorString(e));
@@ -408,6 +426,37 @@ int datr_linear_tf32(const float* x, const float* w, const float* bias, const fl
   if (int rc = make_map(&mw, w, N, K, wide ? 256 : 128)) return rc;
   return wide ? launch<256, 3>(mx, mw, bias, residual, y, M, N, K, relu, stream)
               : launch<128, 5>(mx, mw, bias, residual, y, M, N, K, relu, stream);
+}
+
+// y = act(x . w_t + bias) + residual with the weight given transposed, w_t [K, N] row-major (TF32 products): the input
+// gradient of a Linear without a transposed copy of its weight.
+int datr_linear_tf32_bt(const float* x, const float* w_t, const float* bias, const float* residual, float* y, int M, int N,
+                        int K, int relu, void* stream_) {
+  if (!x || !w_t || !y) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "null pointer argument%s");
+  if (M <= 0 || N <= 0 || K <= 0) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "all dimensions must be positive%s");
+  if (K % BK != 0) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "K must be a multiple of 32%s");
+  if (N % 4 != 0) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "N must be a multiple of 4%s");
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (!al16(x) || !al16(w_t) || !al16(y) || (bias && !al16(bias)) || (residual && !al16(residual)))
+    return lfail(DATR_LINEAR_ERR_ALIGNMENT, "buffers must be 16-byte aligned%s");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  EncodeTiledFn enc = encode_fn();
+  if (!enc) return lfail(DATR_LINEAR_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable%s");
+  CUtensorMap mx, mw;
+  if (int rc = make_map(&mx, x, M, K, BM)) return rc;
+  const cuuint64_t gdim[2] = {cuuint64_t(N), cuuint64_t(K)};
+  const cuuint64_t gstride[1] = {cuuint64_t(N) * 4};
+  const cuuint32_t box[2] = {32, 32}, estr[2] = {1, 1};
+  const CUresult r = enc(&mw, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(w_t), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_lin_err, sizeof g_lin_err, "cuTensorMapEncodeTiled (transposed weight) failed (CUresult %d)", int(r));
+    return DATR_LINEAR_ERR_CUDA;
+  }
+  const bool wide = N > 256 && (N % 256 == 0 || N % 256 > 128);
+  return wide ? launch<256, 3, false, true>(mx, mw, bias, residual, y, M, N, K, relu, stream)
+              : launch<128, 5, false, true>(mx, mw, bias, residual, y, M, N, K, relu, stream);
 }
 
 // bf16 operands (x [M, K], w [N, K] as bf16), fp32 accumulation; y fp32 or bf16 (y_bf16); `residual` [M, N] fp32, or bf16

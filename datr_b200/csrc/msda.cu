@@ -859,10 +859,16 @@ bool encode_level_maps(LevelMaps* maps, float* gv, const int64_t* hshapes, const
     const cuuint64_t gdim[5] = {32, (cuuint64_t)M, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     const cuuint64_t gstr[4] = {32 * 4, row, (cuuint64_t)W * row, (cuuint64_t)S * row};
     const cuuint32_t box[5] = {32, 1, 2, 2, 1}, estr[5] = {1, 1, 1, 1, 1};
-    if (enc(&maps->m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, gv + st * (int64_t)M * 32, gdim, gstr, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return false;
+    CUresult r = enc(&maps->m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, gv + st * (int64_t)M * 32, gdim, gstr, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {     // no context on this thread yet: bind it, retry
+      cudaFree(nullptr);
+      r = enc(&maps->m[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, gv + st * (int64_t)M * 32, gdim, gstr, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) return false;
   }
   return true;
 }

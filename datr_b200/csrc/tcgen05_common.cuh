@@ -131,7 +131,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda)
-inline EncodeTiledFn encode_fn() {
+inline EncodeTiledFn raw_encode_fn() {
   static EncodeTiledFn fn = [] {
     void* p = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -142,5 +142,23 @@ inline EncodeTiledFn encode_fn() {
   }();
   return fn;
 }
+
+// The driver call needs a current context on the calling thread.  A thread that has only used the runtime's device guard
+// (autograd's backward worker whose first CUDA work is one of our launches) may have none yet: bind the primary context
+// through the runtime and retry once.
+inline CUresult encode_tiled_with_context(CUtensorMap* m, CUtensorMapDataType t, cuuint32_t rank, void* base, const cuuint64_t* gd,
+                                          const cuuint64_t* gs, const cuuint32_t* box, const cuuint32_t* es,
+                                          CUtensorMapInterleave il, CUtensorMapSwizzle sw, CUtensorMapL2promotion l2,
+                                          CUtensorMapFloatOOBfill oob) {
+  EncodeTiledFn raw = raw_encode_fn();
+  CUresult r = raw(m, t, rank, base, gd, gs, box, es, il, sw, l2, oob);
+  if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED || r == CUDA_ERROR_CONTEXT_IS_DESTROYED) {
+    cudaFree(nullptr);
+    r = raw(m, t, rank, base, gd, gs, box, es, il, sw, l2, oob);
+  }
+  return r;
+}
+
+inline EncodeTiledFn encode_fn() { return raw_encode_fn() ? &encode_tiled_with_context : static_cast<EncodeTiledFn>(nullptr); }
 
 }  // namespace datr_tc

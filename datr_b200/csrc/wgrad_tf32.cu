@@ -309,6 +309,21 @@ int launch(const CUtensorMap& mdz, const CUtensorMap& mx, float* dw, float* db, 
   return DATR_LINEAR_OK;
 }
 
+// dW / db are accumulated with reductions: zero-fill them on the stream -- with ONE memset when db directly follows dW in
+// memory (the Python binding allocates them that way: ~150 launches fewer per training step)
+int zero_outputs(float* dw, float* db, int N, int K, cudaStream_t stream) {
+  const size_t nw = (size_t)N * K;
+  cudaError_t e;
+  if (db == dw + nw) {
+    e = cudaMemsetAsync(dw, 0, sizeof(float) * (nw + (size_t)N), stream);
+  } else {
+    e = cudaMemsetAsync(dw, 0, sizeof(float) * nw, stream);
+    if (e == cudaSuccess && db) e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, stream);
+  }
+  if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  return DATR_LINEAR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -320,9 +335,7 @@ int datr_linear_wgrad_tf32(const float* dz, const float* x, float* dw, float* db
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al16(dz) || !al16(x) || !al16(dw)) return wfail(DATR_LINEAR_ERR_ALIGNMENT, "buffers must be 16-byte aligned%s");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, stream);
-  if (e == cudaSuccess && db) e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, stream);
-  if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  if (int rc = zero_outputs(dw, db, N, K, stream)) return rc;
   CUtensorMap mdz, mx;
   if (int rc = make_map(&mdz, dz, M, N)) return rc;
   if (int rc = make_map(&mx, x, M, K)) return rc;
@@ -337,9 +350,7 @@ int datr_linear_wgrad_bf16(const void* dz, const void* x, float* dw, float* db, 
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al16(dz) || !al16(x) || !al16(dw)) return wfail(DATR_LINEAR_ERR_ALIGNMENT, "buffers must be 16-byte aligned%s");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)N * K, stream);
-  if (e == cudaSuccess && db) e = cudaMemsetAsync(db, 0, sizeof(float) * (size_t)N, stream);
-  if (e != cudaSuccess) return wfail(DATR_LINEAR_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  if (int rc = zero_outputs(dw, db, N, K, stream)) return rc;
   CUtensorMap mdz, mx;
   if (int rc = make_map_bf16(&mdz, dz, M, N)) return rc;
   if (int rc = make_map_bf16(&mx, x, M, K)) return rc;

@@ -82,6 +82,29 @@ def _launch(x2, w, bias, residual2, relu):
     return y
 
 
+def _launch_bt(x2, w_t, bias, residual2, relu):
+    """act(x2 @ w_t + bias) + residual for a weight given transposed, w_t [K, N] (datr_linear_tf32_bt): the input gradient
+    of a Linear straight from its [N_fwd, K_fwd] weight, no transposed copy."""
+    M, K = x2.shape
+    N = w_t.shape[1]
+    y = torch.empty((M, N), dtype=torch.float32, device=x2.device)
+    lib = native.lib()
+    with torch.cuda.device(x2.device):
+        stream = torch.cuda.current_stream()
+        if _timers is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        rc = lib.datr_linear_tf32_bt(x2.data_ptr(), w_t.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                     residual2.data_ptr() if residual2 is not None else None, y.data_ptr(), M, N, K,
+                                     int(relu), stream.cuda_stream)
+        if _timers is not None:
+            e1.record(stream)
+            _timers.append(("linear", (M, N, K, residual2 is not None), e0, e1))
+    if rc != 0:
+        raise RuntimeError(f"datr_linear_tf32_bt failed (code {rc}): {lib.datr_linear_last_error().decode()}")
+    return y
+
+
 def _c(t):
     return t if t.is_contiguous() and t.data_ptr() % 16 == 0 else t.contiguous()
 
@@ -105,13 +128,20 @@ def _colsum(g2, y_act=None):
     return dz, db
 
 
+def _dw_db(N, K, want_db, device):
+    """dW [N, K] and db [N] carved from one buffer, db right behind dW: the library then zero-fills both with one memset."""
+    if not want_db:
+        return torch.empty((N, K), dtype=torch.float32, device=device), None
+    buf = torch.empty(N * K + N, dtype=torch.float32, device=device)
+    return buf[:N * K].view(N, K), buf[N * K:]
+
+
 def _wgrad(g2, x2, want_db):
     """dW = g2^T x2 (and db = column sums of g2) on the tcgen05 weight-gradient kernel (csrc/wgrad_tf32.cu)."""
     M, N = g2.shape
     K = x2.shape[1]
     lib = native.lib()
-    dw = torch.empty((N, K), dtype=torch.float32, device=g2.device)
-    db = torch.empty(N, dtype=torch.float32, device=g2.device) if want_db else None
+    dw, db = _dw_db(N, K, want_db, g2.device)
     with torch.cuda.device(g2.device):
         rc = lib.datr_linear_wgrad_tf32(g2.data_ptr(), x2.data_ptr(), dw.data_ptr(), db.data_ptr() if want_db else None,
                                         M, N, K, torch.cuda.current_stream().cuda_stream)
@@ -171,7 +201,7 @@ class _LinearTF32(torch.autograd.Function):
         gx = gw = None
         if ctx.needs_input_grad[0]:
             if N % 32 == 0 and K % 4 == 0:
-                gx = _launch(g2, _c(w.t()), None, None, False).view(ctx.xshape)
+                gx = _launch_bt(g2, w, None, None, 0).view(ctx.xshape)
             else:
                 fallbacks.note(f"torch.matmul (cuBLAS) dgrad N={N} K={K}")
                 gx = (g2 @ w).view(ctx.xshape)
@@ -210,9 +240,9 @@ class _FFNTF32(torch.autograd.Function):
         x2, w1, w2, h = ctx.saved_tensors
         g2 = _c(gy.reshape(-1, w2.shape[0]))
         gw2, gb2 = _wgrad(g2, h, True)
-        dz1 = _launch(g2, _c(w2.t()), None, h, 3)
+        dz1 = _launch_bt(g2, w2, None, h, 3)
         gw1, gb1 = _wgrad(dz1, x2, True)
-        gx = _launch(dz1, _c(w1.t()), None, g2, 0).view(ctx.xshape)
+        gx = _launch_bt(dz1, w1, None, g2, 0).view(ctx.xshape)
         return gx, gw1, gb1, gw2, gb2
 
 
@@ -243,8 +273,7 @@ def _wgrad_bf16(gb, xb, want_db):
     M, N = gb.shape
     K = xb.shape[1]
     lib = native.lib()
-    dw = torch.empty((N, K), dtype=torch.float32, device=gb.device)
-    db = torch.empty(N, dtype=torch.float32, device=gb.device) if want_db else None
+    dw, db = _dw_db(N, K, want_db, gb.device)
     with torch.cuda.device(gb.device):
         rc = lib.datr_linear_wgrad_bf16(gb.data_ptr(), xb.data_ptr(), dw.data_ptr(), db.data_ptr() if want_db else None,
                                         M, N, K, torch.cuda.current_stream().cuda_stream)

@@ -59,6 +59,11 @@ uint64_t datr_linear_wgrad_launch_count(void);
  *                           (residual_bf16) when it is the ReLU-mask source of relu == 3.  K % 64 == 0, N % 4 == 0.
  *   datr_linear_wgrad_bf16  dw [N, K] = dz^T x, db [N] = column sums of dz (fp32 outputs, zero-filled by the library).
  */
+/* datr_linear_tf32 with the weight given transposed, w_t [K, N] row-major: y = act(x w_t + bias) + residual.  The input
+ * gradient of a Linear (dx = dy W, W stored [N_fwd, K_fwd]) without materialising W^T. */
+int datr_linear_tf32_bt(const float* x, const float* w_t, const float* bias, const float* residual, float* y,
+                        int M, int N, int K, int relu, void* stream);
+
 int datr_linear_bf16(const void* x, const void* w, const float* bias, const void* residual, int residual_bf16, void* y,
                      int y_bf16, int M, int N, int K, int relu, void* stream);
 int datr_linear_wgrad_bf16(const void* dz, const void* x, float* dw, float* db, int M, int N, int K, void* stream);

@@ -285,3 +285,20 @@ def test_bf16_ffn_block(M, d, dff):
     assert rel(y.detach(), yr.detach()) < 1e-2
     for got, want, name in zip(leaves, ref, ("dx", "dw1", "db1", "dw2", "db2")):
         assert rel(got.grad, want.grad) < 1e-2, name
+
+
+@pytest.mark.parametrize("M,N,K,relu,res", [(44446, 256, 256, 0, False), (3001, 2048, 256, 3, True), (5000, 256, 2048, 0, True),
+                                            (130, 384, 256, 0, False), (1100, 64, 32, 0, False), (257, 512, 1024, 0, False)])
+def test_transposed_weight_linear_matches_the_plain_kernel_and_fp64(M, N, K, relu, res):
+    """datr_linear_tf32_bt (weight as [K, N], MN-major B tiles): the input-gradient GEMM without a transposed weight copy."""
+    from datr_b200.linear import _launch, _launch_bt
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).cuda()
+    w_t = (torch.randn(K, N, generator=g) / K ** 0.5).cuda()
+    r = torch.randn(M, N, generator=g).cuda() if res else None
+    got = _launch_bt(x, w_t, None, r, relu)
+    plain = _launch(x, w_t.t().contiguous(), None, r, relu)
+    want = x.double() @ w_t.double()
+    want = want * (r.double() > 0) if relu == 3 else (want + r.double() if res else want)
+    assert rel(got, want) < REL_TF32
+    assert rel(got, plain) < 1e-6
