@@ -86,7 +86,7 @@ struct Smem {
 // needs (dx = dy . W with W stored [N_fwd, K_fwd]): its tiles are MN-major B operands (TMA boxes of {32 columns x 32 rows}
 // with the 32-byte-atom swizzle, transposed-operand bit of the instruction descriptor, as in wgrad_tf32.cu), so the
 // backward no longer materialises W^T with a copy kernel per layer and step.
-template <int BN, int STAGES, bool kBF16 = false, bool kBT = false>
+template <int BN, int STAGES, bool kBF16 = false, bool kBT = false, bool kMask = false>
 __global__ void __launch_bounds__(kThreads, 1)
 linear_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_constant__ CUtensorMap tma_w,
                    const float* __restrict__ bias, const float* __restrict__ residual, float* __restrict__ y,
@@ -270,8 +270,17 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_const
       const uint32_t as = ti & 1;
       const int row0 = m0 + lane_base + tr;
       float4 res[8];
+      [[maybe_unused]] float4 msk[kMask ? 8 : 1];
       auto fetch_residual = [&](int c) {
         const int col = n0 + c + tc;
+        if constexpr (kMask) {                                // the mask rows travel with the residual rows, one chunk ahead
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int row = row0 + 4 * j;
+            msk[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < M && col + 4 <= N) msk[j] = __ldg(reinterpret_cast<const float4*>(bias + (size_t)row * N + col));
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int row = row0 + 4 * j;
@@ -312,7 +321,7 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_const
         if (col < N) {
           const bool vec = col + 4 <= N;
           float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (bias) {
+          if (bias && !kMask) {                               // kMask (relu == 4): `bias` carries the [M, N] ReLU-mask source
             if (vec) b4 = __ldg(reinterpret_cast<const float4*>(bias + col));
             else { b4.x = __ldg(bias + col); if (col + 1 < N) b4.y = __ldg(bias + col + 1); if (col + 2 < N) b4.z = __ldg(bias + col + 2); }
           }
@@ -331,18 +340,24 @@ linear_tf32_kernel(const __grid_constant__ CUtensorMap tma_x, const __grid_const
             } else if (vec) {
               t.x += res[j].x; t.y += res[j].y; t.z += res[j].z; t.w += res[j].w;
               if (relu == 2) { t.x = fmaxf(t.x, 0.f); t.y = fmaxf(t.y, 0.f); t.z = fmaxf(t.z, 0.f); t.w = fmaxf(t.w, 0.f); }
+              if constexpr (kMask) {         // (x W + residual) kept where the mask source is positive
+                const float4 m4 = msk[j];
+                t.x = m4.x > 0.f ? t.x : 0.f; t.y = m4.y > 0.f ? t.y : 0.f;
+                t.z = m4.z > 0.f ? t.z : 0.f; t.w = m4.w > 0.f ? t.w : 0.f;
+              }
               if (out_bf16) store_bf16x4(y, off, t); else *reinterpret_cast<float4*>(y + off) = t;
             } else {
               const float ov[4] = {t.x, t.y, t.z, t.w};
               for (int e = 0; e < 4 && col + e < N; ++e) {
                 const float r1 = residual ? __ldg(residual + off + e) : 0.f;
-                const float o1 = relu == 3 ? (r1 > 0.f ? ov[e] : 0.f) : ov[e] + r1;
+                float o1 = relu == 3 ? (r1 > 0.f ? ov[e] : 0.f) : ov[e] + r1;
+                if (kMask && !(__ldg(bias + off + e) > 0.f)) o1 = 0.f;
                 y[off + e] = relu == 2 ? fmaxf(o1, 0.f) : o1;
               }
             }
           }
         }
-        if (residual && c + 32 < kCols) fetch_residual(c + 32);
+        if ((residual || kMask) && c + 32 < kCols) fetch_residual(c + 32);
       }
     }
   }
@@ -374,7 +389,7 @@ int make_map(CUtensorMap* map, const void* base, int rows, int cols, int box_row
   return DATR_LINEAR_OK;
 }
 
-template <int BN, int STAGES, bool kBF16 = false, bool kBT = false>
+template <int BN, int STAGES, bool kBF16 = false, bool kBT = false, bool kMask = false>
 int launch(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, const float* residual, float* y, int M, int N,
            int K, int relu, cudaStream_t stream, int flags = 0, const CUtensorMap* my = nullptr, const CUtensorMap* mr = nullptr) {
   using L = Smem<BN, STAGES, kBF16>;
@@ -384,7 +399,7 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, cons
   cudaGetDevice(&dev);
   const uint64_t bit = 1ull << (dev & 63);
   if (!(opted.load(std::memory_order_acquire) & bit)) {
-    const cudaError_t e = cudaFuncSetAttribute(linear_tf32_kernel<BN, STAGES, kBF16, kBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    const cudaError_t e = cudaFuncSetAttribute(linear_tf32_kernel<BN, STAGES, kBF16, kBT, kMask>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return lfail(DATR_LINEAR_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     opted.fetch_or(bit, std::memory_order_release);
   }
@@ -396,7 +411,7 @@ int launch(const CUtensorMap& mx, const CUtensorMap& mw, const float* bias, cons
   }
   const long long tiles = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
   const unsigned grid = unsigned(tiles < sms ? tiles : sms);
-  linear_tf32_kernel<BN, STAGES, kBF16, kBT><<<grid, kThreads, L::kTotal, stream>>>(mx, mw, bias, residual, y, M, N, K, relu, flags, my ? *my : no_map,
+  linear_tf32_kernel<BN, STAGES, kBF16, kBT, kMask><<<grid, kThreads, L::kTotal, stream>>>(mx, mw, bias, residual, y, M, N, K, relu, flags, my ? *my : no_map,
                                                                                mr ? *mr : no_map);
   const cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return lfail(DATR_LINEAR_ERR_CUDA, "linear_tf32_kernel launch: %s", cudaGetErrorString(e));
@@ -430,8 +445,26 @@ int datr_linear_tf32(const float* x, const float* w, const float* bias, const fl
 
 // y = act(x . w_t + bias) + residual with the weight given transposed, w_t [K, N] row-major (TF32 products): the input
 // gradient of a Linear without a transposed copy of its weight.
+static int linear_bt(const float* x, const float* w_t, const float* bias, const float* residual, float* y, int M, int N,
+                     int K, int relu, void* stream_);
+
 int datr_linear_tf32_bt(const float* x, const float* w_t, const float* bias, const float* residual, float* y, int M, int N,
                         int K, int relu, void* stream_) {
+  if (relu < 0 || relu > 3) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "relu must be 0..3%s");
+  return linear_bt(x, w_t, bias, residual, y, M, N, K, relu, stream_);
+}
+
+// y = (x . w_t + residual) where mask > 0, else 0 (mask [M, N]; residual optional): the input gradient of a layer whose
+// input is a ReLU output with further consumers -- their gradient arrives as `residual`, the ReLU's own backward mask (its
+// output is the layer's saved input) is applied here, so neither the accumulation nor the mask is a separate pass.
+int datr_linear_tf32_bt_masked(const float* x, const float* w_t, const float* residual, const float* mask, float* y, int M,
+                               int N, int K, void* stream_) {
+  if (!mask) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "null mask%s");
+  return linear_bt(x, w_t, mask, residual, y, M, N, K, 4, stream_);      // the kernel reads the mask through `bias`
+}
+
+static int linear_bt(const float* x, const float* w_t, const float* bias, const float* residual, float* y, int M, int N,
+                     int K, int relu, void* stream_) {
   if (!x || !w_t || !y) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "null pointer argument%s");
   if (M <= 0 || N <= 0 || K <= 0) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "all dimensions must be positive%s");
   if (K % BK != 0) return lfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "K must be a multiple of 32%s");
@@ -455,6 +488,9 @@ int datr_linear_tf32_bt(const float* x, const float* w_t, const float* bias, con
     return DATR_LINEAR_ERR_CUDA;
   }
   const bool wide = N > 256 && (N % 256 == 0 || N % 256 > 128);
+  if (relu == 4)
+    return wide ? launch<256, 3, false, true, true>(mx, mw, bias, residual, y, M, N, K, relu, stream)
+                : launch<128, 5, false, true, true>(mx, mw, bias, residual, y, M, N, K, relu, stream);
   return wide ? launch<256, 3, false, true>(mx, mw, bias, residual, y, M, N, K, relu, stream)
               : launch<128, 5, false, true>(mx, mw, bias, residual, y, M, N, K, relu, stream);
 }

@@ -46,9 +46,32 @@ class StepGraphs:
         self.skip = set(filter(None, os.environ.get("DATR_GRAPH_SKIP", "").split(",")))   # segment names kept eager
         self.alias_inputs = os.environ.get("DATR_GRAPH_ALIAS", "1") != "0"
         self.stable_storages = set()           # storage addresses of the static outputs of the captured training segments
+        # id(parameter) -> persistent gradient buffer (a FlatGradients view): the captured backward of a segment adds the
+        # parameter gradients into these buffers itself (one multi-tensor launch inside the graph) and hands autograd
+        # nothing, instead of one eager `grad += new` kernel per parameter after every replay (DATR_GRAPH_SINKS=0: off)
+        self.grad_sinks = {}
+        self.sink_grads = os.environ.get("DATR_GRAPH_SINKS", "1") != "0"
 
     def begin_step(self):
         self.calls.clear()
+
+    def set_grad_sinks(self, flat):
+        """Register the gradient buffers of `flat` (datr_b200.parallel.FlatGradients, gather=False: every .grad is a
+        persistent view, zeroed once per step) as the destinations of the in-graph gradient accumulation.  Call it before
+        the first training step; segments captured earlier keep handing their gradients to autograd."""
+        if getattr(flat, "gather", False):
+            return
+        moved = any(id(p) in self.grad_sinks and self.grad_sinks[id(p)].data_ptr() != v.data_ptr()
+                    for p, v in zip(flat.params, flat.views))
+        if moved:
+            # a new gradient buffer for parameters whose segments were captured against the old one: those captures add
+            # into memory nobody reads any more, so the training graphs are dropped and captured again on next use
+            self.grad_sinks.clear()
+            for k in [k for k in self.cache if k[2]]:
+                del self.cache[k]
+                self.per_segment[k[:2]] = max(0, self.per_segment.get(k[:2], 1) - 1)
+        for p, v in zip(flat.params, flat.views):
+            self.grad_sinks[id(p)] = v
 
     def call(self, name, owner, fn, *args):
         """Run `fn(*args)` (args: any pytree of tensors and hashable constants; `owner`: the nn.Module whose
@@ -85,8 +108,7 @@ class StepGraphs:
                 # alone has ~50 such inputs; DATR_GRAPH_ALIAS=0 restores the clones)
                 sample = tuple((a.detach() if self._stable(a) else a.detach().clone()).requires_grad_(a.requires_grad)
                                for a in args)
-                graphed = torch.cuda.make_graphed_callables(module, sample, num_warmup_iters=self.warmup_iters,
-                                                            allow_unused_input=True)
+                graphed = _TrainingGraph(module, sample, self.warmup_iters, self.grad_sinks if self.sink_grads else {})
                 # warm-up iterations + one capture each ran forward and backward eagerly/under capture once
                 per_pair = (_native_launches() - n0) // (self.warmup_iters + 1)
             else:
@@ -107,6 +129,119 @@ class StepGraphs:
         """True if `a` aliases the static output storage of a segment captured earlier in this process."""
         return (self.alias_inputs and isinstance(a, torch.Tensor) and a.is_cuda
                 and a.untyped_storage().data_ptr() in self.stable_storages)
+
+
+class _TrainingGraph:
+    """Forward and backward CUDA graphs of one module -- the capture protocol of torch.cuda.make_graphed_callables (side-
+    stream warm-up, forward capture, backward capture of torch.autograd.grad into static gradient tensors sharing one
+    memory pool, replay from a torch.autograd.Function) with one difference: parameters listed in `sinks`
+    (id(parameter) -> persistent gradient buffer) get their gradient ADDED INTO that buffer inside the captured backward,
+    by multi-tensor launches, and the autograd node returns None for them.  torch's version hands the static gradient of
+    every parameter to AccumulateGrad, i.e. one eager `grad += new` kernel per parameter per replay (640 per DINO step)."""
+
+    def __init__(self, module, sample_args, warmup_iters, sinks):
+        from torch.utils import _pytree as pytree
+        self.module = module
+        self.training = module.training
+        n_args = len(sample_args)
+        params = tuple(module.parameters())
+        surface = tuple(sample_args) + params
+        req = tuple(t for t in surface if t.requires_grad)
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup_iters):
+                outs = pytree.tree_leaves(module(*sample_args))
+                outs = tuple(o for o in outs if isinstance(o, torch.Tensor) and o.requires_grad)
+                if outs and req:
+                    torch.autograd.grad(outs, req, tuple(torch.empty_like(o) for o in outs), only_inputs=True,
+                                        allow_unused=True)
+                del outs
+        cur.wait_stream(side)
+        pool = torch.cuda.graph_pool_handle()
+        fwd, bwd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(fwd, pool=pool):
+            out = module(*sample_args)
+        static_outputs, out_spec = pytree.tree_flatten(out)
+        static_outputs = tuple(static_outputs)
+        static_grad_outputs = tuple(torch.empty_like(o) if o.requires_grad else None for o in static_outputs)
+        outs_req = tuple(o for o in static_outputs if o.requires_grad)
+        n_sunk = 0
+        grads = ()
+        probe = None
+        self.side_launches = 0
+        if outs_req and req:
+            from . import linear as dl
+            branch = dl.SideWgrad(torch.cuda.Stream(), dl.SIDE_WGRAD_MAX_ROWS) if dl.SIDE_WGRAD_MAX_ROWS > 0 else None
+            with torch.cuda.graph(bwd, pool=pool):
+                dl._SIDE = branch        # small weight-gradient launches become a parallel branch of this graph
+                try:
+                    grads = torch.autograd.grad(outs_req, req, tuple(g for g in static_grad_outputs if g is not None),
+                                                only_inputs=True, allow_unused=True)
+                finally:
+                    dl._SIDE = None
+                if branch is not None and branch.used:
+                    torch.cuda.current_stream().wait_stream(branch.stream)
+                    self.side_launches = branch.used
+                dst, src = [], []
+                kept = []
+                for t, g in zip(req, grads):
+                    sink = sinks.get(id(t)) if g is not None else None
+                    if sink is not None and sink.shape == g.shape and sink.dtype == g.dtype:
+                        if not dst:
+                            probe = (t, sink)
+                        dst.append(sink)
+                        src.append(g)
+                        kept.append(None)
+                    else:
+                        kept.append(g)
+                if dst:
+                    torch._foreach_add_(dst, src)
+                n_sunk = len(dst)
+                grads = tuple(kept)
+                del dst, src, kept
+        it = iter(grads)
+        static_grad_inputs = tuple(next(it) if t.requires_grad else None for t in surface) if grads else (None,) * len(surface)
+        self.n_sunk = n_sunk
+        self._keep = (fwd, bwd, static_outputs, static_grad_outputs, static_grad_inputs, surface)
+        has_bwd = bool(outs_req and req)
+
+        class Graphed(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, *inputs):
+                for i in range(n_args):
+                    if surface[i].data_ptr() != inputs[i].data_ptr():
+                        surface[i].copy_(inputs[i])
+                fwd.replay()
+                return tuple(o.detach() for o in static_outputs)
+
+            @staticmethod
+            @torch.autograd.function.once_differentiable
+            def backward(ctx, *gouts):
+                if not has_bwd:
+                    return (None,) * len(surface)
+                for s, g in zip(static_grad_outputs, gouts):
+                    if s is not None and s.data_ptr() != g.data_ptr():
+                        s.copy_(g)
+                if probe is not None and (probe[0].grad is None or probe[0].grad.data_ptr() != probe[1].data_ptr()):
+                    raise RuntimeError("datr_b200.graphs: this segment's backward adds its parameter gradients into the "
+                                       "FlatGradients buffer registered at capture, but .grad no longer points there "
+                                       "(zero_grad(set_to_none=True) or `p.grad = None`?); keep the views in place "
+                                       "(FlatGradients.zero()) or set DATR_GRAPH_SINKS=0")
+                bwd.replay()
+                return tuple(g.detach() if g is not None else None for g in static_grad_inputs)
+
+        self._fn, self._params, self._out_spec = Graphed, params, out_spec
+
+    def __getattr__(self, name):            # FnSegment bookkeeping (out_spec, out_consts, out_n) lives on the module
+        return getattr(self.__dict__["module"], name)
+
+    def __call__(self, *args):
+        from torch.utils import _pytree as pytree
+        if self.module.training != self.training:
+            return self.module(*args)
+        return pytree.tree_unflatten(list(self._fn.apply(*(tuple(args) + self._params))), self._out_spec)
 
 
 class _InferenceGraph:

@@ -15,6 +15,8 @@ The mode switch keeps the two numerics classes apart: "fp32" (default; SIMT fp32
 There is no fallback inside the "tf32" path: if the CUDA library is missing the call raises."""
 from __future__ import annotations
 
+import os as _os
+
 import torch
 import torch.nn.functional as F
 
@@ -105,6 +107,52 @@ def _launch_bt(x2, w_t, bias, residual2, relu):
     return y
 
 
+def _launch_bt_masked(x2, w_t, residual2, mask2):
+    """(x2 @ w_t + residual2) where mask2 > 0, else 0 (datr_linear_tf32_bt_masked): input gradient + the gradient of a
+    parallel branch + the ReLU backward of the tensor both branches read, in one kernel."""
+    M, K = x2.shape
+    N = w_t.shape[1]
+    y = torch.empty((M, N), dtype=torch.float32, device=x2.device)
+    lib = native.lib()
+    with torch.cuda.device(x2.device):
+        stream = torch.cuda.current_stream()
+        if _timers is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        rc = lib.datr_linear_tf32_bt_masked(x2.data_ptr(), w_t.data_ptr(), residual2.data_ptr() if residual2 is not None else None,
+                                            mask2.data_ptr(), y.data_ptr(), M, N, K, stream.cuda_stream)
+        if _timers is not None:
+            e1.record(stream)
+            _timers.append(("linear", (M, N, K, residual2 is not None), e0, e1))
+    if rc != 0:
+        raise RuntimeError(f"datr_linear_tf32_bt_masked failed (code {rc}): {lib.datr_linear_last_error().decode()}")
+    return y
+
+
+class GradCarrier:
+    """Hands the gradient of a skip connection from the layer that closes it to the layer that opened it, inside one
+    backward pass: y = relu(conv3(..conv1(x)..) + x) (a ResNet bottleneck).  The closing layer's backward deposits the
+    gradient of its `residual` argument here instead of returning it to autograd; the opening layer's backward picks it up
+    as the residual of its input-gradient GEMM, so `dx = dgrad + skip gradient` costs no pass of its own."""
+    __slots__ = ("g",)
+
+    def __init__(self):
+        self.g = None
+
+
+class GradChain:
+    """Running sum of the input gradients of `n` layers that read the SAME tensor and whose backward passes run one after
+    the other (decoder: the six value projections of the encoder memory, deformable_transformer.py:1011-1016 in the
+    reference).  Each layer's input-gradient GEMM takes the sum so far as its residual; the layer that completes the count
+    returns the total to autograd, the others return nothing -- n - 1 accumulation passes over the tensor disappear, and
+    since none of these gradients is needed before the end of the backward pass, a captured backward runs the whole
+    backward of such a layer on the parallel branch (SideWgrad)."""
+    __slots__ = ("n", "seen", "g")
+
+    def __init__(self, n):
+        self.n, self.seen, self.g = n, 0, None
+
+
 def _c(t):
     return t if t.is_contiguous() and t.data_ptr() % 16 == 0 else t.contiguous()
 
@@ -150,6 +198,35 @@ def _wgrad(g2, x2, want_db):
     return dw, db
 
 
+class SideWgrad:
+    """Set as `linear._SIDE` by graphs._TrainingGraph while it captures a segment's backward: weight-gradient launches of
+    at most `max_rows` rows go to `stream`, a parallel branch of the captured graph.  At decoder sizes (4 400 rows) a
+    weight-gradient kernel occupies a few dozen SMs and nothing downstream of the input-gradient chain waits for it; on
+    one stream it still serialises with that chain.  The capture joins the branch before it consumes the gradients."""
+
+    def __init__(self, stream, max_rows):
+        self.stream, self.max_rows, self.used = stream, max_rows, 0
+
+
+_SIDE = None
+SIDE_WGRAD_MAX_ROWS = int(_os.environ.get("DATR_WGRAD_SIDE_ROWS", "16384"))      # 0: every launch stays on the main branch
+
+
+def _wgrad_branch(fn, g2, x2, want_db):
+    side = _SIDE
+    if (side is None or g2.shape[0] > side.max_rows or not g2.is_cuda
+            or torch.cuda.current_stream() == side.stream):          # already on the branch (a chained layer)
+        return fn(g2, x2, want_db)
+    side.stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side.stream):
+        out = fn(g2, x2, want_db)
+    # both operands were allocated on the main branch: their memory must not be handed out again while this branch reads it
+    g2.record_stream(side.stream)
+    x2.record_stream(side.stream)
+    side.used += 1
+    return out
+
+
 def _zero_rows(t2, mask):
     from .rowmask import _zero
     _zero(t2, mask)
@@ -157,7 +234,15 @@ def _zero_rows(t2, mask):
 
 class _LinearTF32(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu, zero_rows=None):
+    def forward(ctx, x, weight, bias, residual, relu, zero_rows=None, skip_out=None, skip_in=None, mask_input_grad=False,
+                grad_premasked=False, chain=None):
+        """skip_out / skip_in (GradCarrier): this layer closes / opened a skip connection whose gradient travels through
+        the carrier.  mask_input_grad: x is a ReLU output and the gradient returned for it is already multiplied by
+        (x > 0) -- valid when EVERY consumer of x does so and the ReLU's own layer is told `grad_premasked` (relu == 2
+        layers only), which then skips its mask pass."""
+        ctx.skip_out, ctx.skip_in = skip_out if residual is not None else None, skip_in
+        ctx.mask_input_grad, ctx.grad_premasked = bool(mask_input_grad), bool(grad_premasked)
+        ctx.chain = chain               # GradChain: x's gradient is accumulated across the layers sharing the chain
         K = weight.shape[1]
         x2 = _c(x.reshape(-1, K))
         w = _c(weight)
@@ -175,6 +260,22 @@ class _LinearTF32(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
+        side = _SIDE
+        if ctx.chain is None or side is None or not ctx.needs_input_grad[0] or not gy.is_cuda:
+            return _LinearTF32._backward(ctx, gy)
+        # nothing in the rest of this backward pass waits for a chained layer: its whole backward joins the parallel branch
+        main = torch.cuda.current_stream()
+        side.stream.wait_stream(main)
+        with torch.cuda.stream(side.stream):
+            out = _LinearTF32._backward(ctx, gy)
+        for t in (gy,) + tuple(ctx.saved_tensors) + (ctx.zero_rows,):
+            if t is not None:
+                t.record_stream(side.stream)
+        side.used += 1
+        return out
+
+    @staticmethod
+    def _backward(ctx, gy):
         x2, w, y, r2 = ctx.saved_tensors
         N, K = w.shape
         g2 = _c(gy.reshape(-1, N))
@@ -186,12 +287,14 @@ class _LinearTF32(torch.autograd.Function):
         want_gw = ctx.needs_input_grad[1]
         fused = _WGRAD and want_gw and N % 4 == 0 and K % 4 == 0      # dW and db from one tensor-core kernel
         gb = None
-        if ctx.relu == 2:     # ReLU after the residual add: the mask applies to both branches
+        if ctx.relu == 2 and not ctx.grad_premasked:     # ReLU after the residual add: the mask applies to both branches
             if want_gb and not fused:
                 g2, gb = _colsum(g2, y)
             else:
                 g2 = torch.ops.aten.threshold_backward(g2, y, 0.0)
         gres = g2.view(ctx.rshape) if ctx.has_res else None
+        if ctx.skip_out is not None:
+            ctx.skip_out.g, gres = g2, None
         if ctx.relu == 1:     # ReLU mask (+ bias gradient) in one pass
             act = y if r2 is None else y - r2
             if want_gb and not fused:
@@ -200,20 +303,41 @@ class _LinearTF32(torch.autograd.Function):
                 g2 = torch.ops.aten.threshold_backward(g2, act, 0.0)
         gx = gw = None
         if ctx.needs_input_grad[0]:
+            skip = None
+            if ctx.skip_in is not None:
+                skip, ctx.skip_in.g = ctx.skip_in.g, None
+            if ctx.chain is not None:
+                assert skip is None
+                skip = ctx.chain.g
             if N % 32 == 0 and K % 4 == 0:
-                gx = _launch_bt(g2, w, None, None, 0).view(ctx.xshape)
+                if ctx.mask_input_grad:
+                    gx = _launch_bt_masked(g2, w, skip, x2)
+                else:
+                    gx = _launch_bt(g2, w, None, skip, 0)
             else:
                 fallbacks.note(f"torch.matmul (cuBLAS) dgrad N={N} K={K}")
-                gx = (g2 @ w).view(ctx.xshape)
+                gx = g2 @ w
+                if skip is not None:
+                    gx = gx + skip
+                if ctx.mask_input_grad:
+                    gx = torch.ops.aten.threshold_backward(gx, x2, 0.0)
+            gx = gx.view(ctx.xshape)
+            if ctx.chain is not None:
+                ch = ctx.chain
+                ch.seen += 1
+                if ch.seen == ch.n:     # the last layer of the chain returns the total
+                    ch.seen, ch.g = 0, None
+                else:
+                    ch.g, gx = gx.view(-1, K), None
         if fused:
-            gw, gb = _wgrad(g2, x2, want_gb)
+            gw, gb = _wgrad_branch(_wgrad, g2, x2, want_gb)
         else:
             if want_gb and gb is None:
                 gb = _colsum(g2)[1]
             if want_gw:
                 fallbacks.note(f"torch.matmul (cuBLAS) wgrad N={N} K={K}")
                 gw = g2.t() @ x2
-        return gx, gw, gb, gres, None, None
+        return gx, gw, gb, gres, None, None, None, None, None, None, None
 
 
 class _FFNTF32(torch.autograd.Function):
@@ -239,9 +363,9 @@ class _FFNTF32(torch.autograd.Function):
     def backward(ctx, gy):
         x2, w1, w2, h = ctx.saved_tensors
         g2 = _c(gy.reshape(-1, w2.shape[0]))
-        gw2, gb2 = _wgrad(g2, h, True)
+        gw2, gb2 = _wgrad_branch(_wgrad, g2, h, True)
         dz1 = _launch_bt(g2, w2, None, h, 3)
-        gw1, gb1 = _wgrad(dz1, x2, True)
+        gw1, gb1 = _wgrad_branch(_wgrad, dz1, x2, True)
         gx = _launch_bt(dz1, w1, None, g2, 0).view(ctx.xshape)
         return gx, gw1, gb1, gw2, gb2
 
@@ -314,7 +438,6 @@ class _FFNBF16(torch.autograd.Function):
 
 
 # Operand precision of the FFN blocks in 'tf32' mode: "bf16" (default) or "tf32" (DATR_FFN=tf32 / set_ffn_precision)
-import os as _os
 _FFN = _os.environ.get("DATR_FFN", "bf16")
 _FFN_BF16_MIN_ROWS = 8192
 
@@ -340,12 +463,24 @@ def ffn(x, w1, b1, w2, b2):
     return linear(linear(x, w1, b1, relu=True), w2, b2, residual=x)
 
 
-def linear(x, weight, bias=None, relu=False, residual=None, zero_rows=None):
+def linear(x, weight, bias=None, relu=False, residual=None, zero_rows=None, skip_out=None, skip_in=None,
+           mask_input_grad=False, grad_premasked=False, chain=None):
     """relu False/0: x @ weight.T + bias + residual;  True/1: relu(x @ weight.T + bias) + residual;
     2: relu(x @ weight.T + bias + residual).  Tensor-core kernel in 'tf32' mode for eligible shapes, else torch.
     `zero_rows` (bool [*x.shape[:-1]], True = padding; plain Linear only): those rows of the result are set to zero,
-    as `masked_fill(mask[..., None], 0)` after the Linear would."""
+    as `masked_fill(mask[..., None], 0)` after the Linear would.
+    skip_out / skip_in / mask_input_grad / grad_premasked / chain: backward-pass fusion of skip connections, ReLU masks and
+    shared-input gradient sums (_LinearTF32.forward, GradChain); tensor-core path only -- the caller checks `eligible`."""
     relu = int(relu)
+    if skip_out is not None or skip_in is not None or mask_input_grad or grad_premasked or chain is not None:
+        if not (_MODE == "tf32" and eligible(x, weight)):
+            raise ValueError("backward-pass fusion flags need the tensor-core path")
+        if zero_rows is not None:
+            if relu or residual is not None or zero_rows.dtype != torch.bool or zero_rows.shape != x.shape[:-1]:
+                raise ValueError("zero_rows applies to a plain Linear")
+            zero_rows = zero_rows.contiguous()
+        return _LinearTF32.apply(x, weight, bias, residual, relu, zero_rows, skip_out, skip_in, mask_input_grad, grad_premasked,
+                                 chain)
     if zero_rows is not None:
         if relu or residual is not None:
             raise ValueError("zero_rows applies to a plain Linear")

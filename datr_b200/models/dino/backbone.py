@@ -79,7 +79,17 @@ def _pointwise_on_tensor_cores(x):
             and x.is_contiguous(memory_format=torch.channels_last))
 
 
-def _conv1x1_bn(x, conv, bn, relu, residual=None):
+# Backward-pass fusion inside a ResNet stage (DATR_RESNET_FUSED_BWD=0: autograd's separate passes).  Between two
+# bottlenecks WITHOUT a downsample branch the gradient of a block output y = relu(bn3(conv3(.)) + x) has exactly two
+# consumers, the next block's conv1 and its skip connection; autograd adds the two gradients (one pass over the map) and
+# the block then applies its ReLU mask (another pass).  Here the next block's conv3 hands its skip gradient to its conv1
+# (linear.GradCarrier), whose input-gradient GEMM adds it and applies (x > 0) in the epilogue
+# (datr_linear_tf32_bt_masked); the producing block is told its gradient arrives masked.
+import os as _os
+_FUSED_BWD = _os.environ.get("DATR_RESNET_FUSED_BWD", "1") != "0"
+
+
+def _conv1x1_bn(x, conv, bn, relu, residual=None, **fuse):
     """FrozenBN(conv1x1(x)) [+ residual] with optional ReLU on an NHWC tensor, as one fused GEMM over pixels."""
     assert conv.kernel_size == (1, 1) and conv.padding == (0, 0) and conv.groups == 1 and conv.bias is None
     if conv.stride != (1, 1):
@@ -89,7 +99,7 @@ def _conv1x1_bn(x, conv, bn, relu, residual=None):
     scale, shift = bn.scale_shift()
     weight = conv.weight.reshape(cout, cin) * scale[:, None]
     res = residual.permute(0, 2, 3, 1).reshape(-1, cout) if residual is not None else None
-    y = dl.linear(x.permute(0, 2, 3, 1).reshape(-1, cin), weight, shift, relu=relu, residual=res)
+    y = dl.linear(x.permute(0, 2, 3, 1).reshape(-1, cin), weight, shift, relu=relu, residual=res, **fuse)
     return y.view(n, h, w, cout).permute(0, 3, 1, 2)
 
 
@@ -107,11 +117,20 @@ class Bottleneck(nn.Module):
         self.downsample = downsample
         self.stride = stride
 
-    def forward(self, x):
+    def forward(self, x, fuse_in=False, fuse_out=False):
+        """fuse_in: x is the output of the previous bottleneck of the stage, consumed by this block only, and that block
+        was called with fuse_out -- the gradient returned for x carries the previous block's ReLU mask.  Both flags are
+        set by run_stage() and only on the tensor-core path."""
         if _pointwise_on_tensor_cores(x):
             # NHWC activations: the three 1x1 convolutions are GEMMs over pixels; FrozenBN folds into weight / bias
             # and ReLU / the residual add ride in the tcgen05 kernel's epilogue (datr_b200.linear); 3x3 stays cuDNN
-            y = _conv1x1_bn(x, self.conv1, self.bn1, relu=1)
+            fuse_in = fuse_in and self.downsample is None and x.requires_grad and torch.is_grad_enabled()
+            carrier = dl.GradCarrier() if fuse_in else None
+            first = dict(skip_in=carrier, mask_input_grad=True) if fuse_in else {}
+            last = dict(skip_out=carrier) if fuse_in else {}
+            if fuse_out:
+                last["grad_premasked"] = True
+            y = _conv1x1_bn(x, self.conv1, self.bn1, relu=1, **first)
             if dconv.use_kernel(y, self.conv2):
                 # conv2 + FrozenBN + ReLU: im2col-free implicit GEMM (4-D TMA box per tap, datr_b200.conv)
                 scale, shift = self.bn2.scale_shift()
@@ -120,7 +139,8 @@ class Bottleneck(nn.Module):
                 y = F.relu(self.bn2(self.conv2(y)))
             if self.downsample is not None:
                 x = _conv1x1_bn(x, self.downsample[0], self.downsample[1], relu=0)
-            return _conv1x1_bn(y, self.conv3, self.bn3, relu=2, residual=x)
+            return _conv1x1_bn(y, self.conv3, self.bn3, relu=2, residual=x, **last)
+        assert not (fuse_in or fuse_out), "backward-pass fusion is a property of the tensor-core path"
         y = F.relu(self.bn1(self.conv1(x)))
         y = F.relu(self.bn2(self.conv2(y)))
         y = self.bn3(self.conv3(y))
@@ -161,6 +181,23 @@ class ResNet(nn.Module):
 
     def stem(self, x):
         return F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, stride=2, padding=1)
+
+
+def run_stage(stage, x):
+    """One ResNet stage (nn.Sequential of bottlenecks).  On the tensor-core path with gradients, consecutive blocks fuse
+    the accumulation of the skip gradient and the ReLU backward between them into the next block's input-gradient GEMM
+    (see _FUSED_BWD); otherwise this is stage(x)."""
+    blocks = list(stage)
+    trains = any(p.requires_grad for p in stage.parameters())
+    if not (_FUSED_BWD and trains and torch.is_grad_enabled() and _pointwise_on_tensor_cores(x)
+            and all(isinstance(b, Bottleneck) for b in blocks)):
+        return stage(x)
+    for j, blk in enumerate(blocks):
+        # block j hands a masked gradient to block j-1 iff block j has no downsample branch (x feeds conv1 + skip only)
+        fuse_in = j > 0 and blk.downsample is None
+        fuse_out = j + 1 < len(blocks) and blocks[j + 1].downsample is None
+        x = blk(x, fuse_in=fuse_in, fuse_out=fuse_out)
+    return x
 
 
 _RESNETS = {"resnet50": (3, 4, 6, 3), "resnet101": (3, 4, 23, 3)}
@@ -206,7 +243,7 @@ class _Body(nn.Module):
             for i in range(1, self._last + 1):
                 name = f"layer{i}"
                 # stem and layer1 never train (BackboneBase): no autograd graph through them
-                x = getattr(self, name)(x)
+                x = run_stage(getattr(self, name), x)
                 if name in self.return_layers:
                     out[self.return_layers[name]] = x
         return out

@@ -41,6 +41,7 @@ from .utils import MLP, _get_activation_fn, gen_encoder_output_proposals, gen_si
 
 _OWN_ATTENTION = os.environ.get("DATR_OWN_ATTENTION", "1") != "0"
 _FUSED_ATTENTION = os.environ.get("DATR_FUSED_ATTENTION", "1") != "0"   # 0: batched GEMMs around the softmax kernel
+_MEMORY_GRAD_CHAIN = os.environ.get("DATR_MEMORY_GRAD_CHAIN", "1") != "0"  # 0: autograd sums the decoder's memory gradients
 
 
 def _fused_attention_on():
@@ -224,26 +225,27 @@ class DeformableTransformerDecoderLayer(nn.Module):
                                                                   mask_bits=self_attn_mask_bits)))
 
     def forward_ca(self, tgt, tgt_query_pos, tgt_reference_points, memory, memory_key_padding_mask,
-                   memory_level_start_index, memory_spatial_shapes):
+                   memory_level_start_index, memory_spatial_shapes, memory_grad_chain=None):
         if _fusable(self, self.dropout1):
             return ln(self.norm1, self.cross_attn(self.with_pos_embed(tgt, tgt_query_pos), tgt_reference_points, memory,
                                               memory_spatial_shapes, memory_level_start_index,
-                                              memory_key_padding_mask, residual=tgt))
+                                              memory_key_padding_mask, residual=tgt, value_grad_chain=memory_grad_chain))
         attn = self.cross_attn(self.with_pos_embed(tgt, tgt_query_pos), tgt_reference_points, memory,
-                               memory_spatial_shapes, memory_level_start_index, memory_key_padding_mask)
+                               memory_spatial_shapes, memory_level_start_index, memory_key_padding_mask,
+                               value_grad_chain=memory_grad_chain)
         return ln(self.norm1, tgt + self.dropout1(attn))
 
     def forward(self, tgt, tgt_query_pos=None, tgt_query_sine_embed=None, tgt_key_padding_mask=None,
                 tgt_reference_points=None, memory=None, memory_key_padding_mask=None, memory_level_start_index=None,
                 memory_spatial_shapes=None, memory_pos=None, self_attn_mask=None, cross_attn_mask=None,
-                self_attn_mask_bits=None):
+                self_attn_mask_bits=None, memory_grad_chain=None):
         """Batch-first: tgt/query_pos [N,nq,C], reference points [N,nq,L,4], memory [N,S,C]."""
         for step in self.module_seq:
             if step == "sa":
                 tgt = self.forward_sa(tgt, tgt_query_pos, self_attn_mask, self_attn_mask_bits)
             elif step == "ca":
                 tgt = self.forward_ca(tgt, tgt_query_pos, tgt_reference_points, memory, memory_key_padding_mask,
-                                      memory_level_start_index, memory_spatial_shapes)
+                                      memory_level_start_index, memory_spatial_shapes, memory_grad_chain)
             elif step == "ffn":
                 tgt = self.forward_ffn(tgt)
             else:
@@ -295,6 +297,14 @@ class TransformerDecoder(nn.Module):
         if (_fused_attention_on() and tgt.is_cuda and tgt.dtype == torch.float32
                 and (tgt_mask is None or tgt_mask.dtype == torch.bool)):
             mask_bits = attention.pack_mask(tgt_mask, tgt.shape[1], tgt.device, transposed=torch.is_grad_enabled())
+        # every layer projects the same memory (cross-attention values): their input gradients are summed along a chain
+        # inside the input-gradient GEMMs instead of five accumulation passes over [N, S, C] (linear.GradChain)
+        chain = None
+        if (_MEMORY_GRAD_CHAIN and len(self.layers) > 1 and memory.is_cuda and memory.requires_grad and torch.is_grad_enabled()
+                and dl.get_mode() == "tf32" and memory.dtype == torch.float32
+                and all(getattr(l, "module_seq", ()).count("ca") == 1 and dl.eligible(memory, l.cross_attn.value_proj.weight)
+                        for l in self.layers)):
+            chain = dl.GradChain(len(self.layers))
         for lid, layer in enumerate(self.layers):
             if self.training and self.decoder_query_perturber is not None and lid != 0:
                 ref = self.decoder_query_perturber(ref)
@@ -303,7 +313,7 @@ class TransformerDecoder(nn.Module):
             out = layer(tgt=out, tgt_query_pos=query_pos, tgt_reference_points=ref_in, memory=memory,
                         memory_key_padding_mask=memory_key_padding_mask, memory_level_start_index=level_start_index,
                         memory_spatial_shapes=spatial_shapes, memory_pos=pos, self_attn_mask=tgt_mask,
-                        self_attn_mask_bits=mask_bits)
+                        self_attn_mask_bits=mask_bits, memory_grad_chain=chain)
             if self.bbox_embed is not None:
                 new_ref = (self.bbox_embed[lid](out) + inverse_sigmoid(ref)).sigmoid()
                 ref = new_ref if (self.rm_detach and "dec" in self.rm_detach) else new_ref.detach()

@@ -24,6 +24,9 @@ import os
 _FUSED = os.environ.get("DATR_MSDA_FUSED", "1") != "0"
 
 
+_SKIP_CARRIER = os.environ.get("DATR_MSDA_SKIP_CARRIER", "1") != "0"
+
+
 def set_fused(on: bool) -> None:
     global _FUSED
     _FUSED = bool(on)
@@ -101,18 +104,32 @@ class MSDeformAttn(nn.Module):
             nn.init.constant_(proj.bias.data, 0.0)
 
     def forward(self, query, reference_points, input_flatten, input_spatial_shapes,
-                input_level_start_index, input_padding_mask=None, residual=None):
+                input_level_start_index, input_padding_mask=None, residual=None, value_grad_chain=None):
         """query [N,Lq,C]; reference_points [N,Lq,L,2] (centres) or [N,Lq,L,4] (cx,cy,w,h boxes), in [0,1];
         input_flatten [N,S,C]; input_spatial_shapes [L,2]=(H,W); input_level_start_index [L];
         input_padding_mask [N,S] bool, True on padding.  Returns [N,Lq,C].
-        `residual` (extension, optional [N,Lq,C]) is added to the result inside the output projection's epilogue."""
+        `residual` (extension, optional [N,Lq,C]) is added to the result inside the output projection's epilogue.
+        `value_grad_chain` (extension, optional linear.GradChain): the gradient of input_flatten through the value
+        projection is summed across the modules sharing the chain (the decoder layers' cross-attention over one memory)."""
         N, Lq, _ = query.shape
         S = input_flatten.shape[1]
         M, L, P = self.n_heads, self.n_levels, self.n_points
         _check_levels(input_spatial_shapes, S)      # reference :92
 
         # value.masked_fill(mask[..., None], 0) of the reference (:96-97) is applied in place on the fresh projection
-        value = dl.linear(input_flatten, self.value_proj.weight, self.value_proj.bias, zero_rows=input_padding_mask)
+        # `residual is input_flatten` (encoder self-attention: the skip connection around the module starts at the tensor
+        # the value projection reads): the output projection hands the skip gradient to the value projection's
+        # input-gradient GEMM (linear.GradCarrier) instead of leaving autograd a separate accumulation pass
+        carrier = None
+        if (residual is not None and residual is input_flatten and input_flatten.requires_grad and torch.is_grad_enabled()
+                and dl.get_mode() == "tf32" and dl.eligible(input_flatten, self.value_proj.weight)
+                and dl.eligible(input_flatten, self.output_proj.weight) and _SKIP_CARRIER):
+            carrier = dl.GradCarrier()
+        vkw = dict(skip_in=carrier) if carrier is not None else {}
+        if value_grad_chain is not None:        # extension: linear.GradChain shared by the modules reading input_flatten
+            vkw["chain"] = value_grad_chain
+        okw = dict(skip_out=carrier) if carrier is not None else {}
+        value = dl.linear(input_flatten, self.value_proj.weight, self.value_proj.bias, zero_rows=input_padding_mask, **vkw)
         value = value.view(N, S, M, self.d_model // M)
 
         ref_dim = reference_points.shape[-1]
@@ -125,14 +142,14 @@ class MSDeformAttn(nn.Module):
                                torch.cat((self.sampling_offsets.bias, self.attention_weights.bias), 0))
             sampled = MSDeformAttnMergedFunction.apply(value, input_spatial_shapes, input_level_start_index, merged,
                                                        reference_points.contiguous(), M, L, P, _VALUE_STORAGE)
-            return dl.linear(sampled, self.output_proj.weight, self.output_proj.bias, residual=residual)
+            return dl.linear(sampled, self.output_proj.weight, self.output_proj.bias, residual=residual, **okw)
 
         offsets = dl.linear(query, self.sampling_offsets.weight, self.sampling_offsets.bias).view(N, Lq, M, L, P, 2)
         logits = dl.linear(query, self.attention_weights.weight, self.attention_weights.bias).view(N, Lq, M, L * P)
         if _FUSED and MSDA.fused_supported(value, offsets, reference_points):
             sampled = MSDeformAttnFusedFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                                       offsets, logits, reference_points.contiguous())
-            return dl.linear(sampled, self.output_proj.weight, self.output_proj.bias, residual=residual)
+            return dl.linear(sampled, self.output_proj.weight, self.output_proj.bias, residual=residual, **okw)
 
         weights = F.softmax(logits, -1).view(N, Lq, M, L, P)
         if ref_dim == 2:      # offsets are in pixels of each level: normalise by (W_l, H_l)
@@ -151,4 +168,4 @@ class MSDeformAttn(nn.Module):
             return out if residual is None else out + residual
         sampled = MSDeformAttnFunction.apply(value, input_spatial_shapes, input_level_start_index,
                                              locations, weights, self.im2col_step)
-        return dl.linear(sampled, self.output_proj.weight, self.output_proj.bias, residual=residual)
+        return dl.linear(sampled, self.output_proj.weight, self.output_proj.bias, residual=residual, **okw)

@@ -26,7 +26,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward", "datr_msda_fused_backward", "datr_last_error", "datr_abi_version",
            "datr_msda_backward_hs", "datr_msda_fused_backward_hs", "datr_msda_pack_value_pairs", "datr_msda_fused_forward_pairs", "datr_msda_set_backward_stages", "datr_msda_get_backward_stages",
-           "datr_launch_count", "datr_linear_tf32", "datr_linear_tf32_bt", "datr_linear_bf16", "datr_linear_wgrad_bf16", "datr_linear_last_error", "datr_linear_launch_count",
+           "datr_launch_count", "datr_linear_tf32", "datr_linear_tf32_bt", "datr_linear_tf32_bt_masked", "datr_linear_bf16", "datr_linear_wgrad_bf16", "datr_linear_last_error", "datr_linear_launch_count",
            "datr_layernorm256_forward", "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count",
            "datr_colsum", "datr_relu_bwd_colsum", "datr_colsum_last_error", "datr_colsum_launch_count",
            "datr_conv3x3_nhwc_tf32", "datr_conv3x3_wgrad_nhwc_tf32", "datr_conv_last_error", "datr_conv_launch_count",
@@ -133,6 +133,8 @@ def lib() -> ctypes.CDLL:
         L.datr_linear_tf32.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
         L.datr_linear_tf32_bt.restype = i
         L.datr_linear_tf32_bt.argtypes = [vp, vp, vp, vp, vp, i, i, i, i, vp]
+        L.datr_linear_tf32_bt_masked.restype = i
+        L.datr_linear_tf32_bt_masked.argtypes = [vp, vp, vp, vp, vp, i, i, i, vp]
         L.datr_linear_bf16.restype = i
         L.datr_linear_bf16.argtypes = [vp, vp, vp, vp, i, vp, i, i, i, i, i, vp]
         L.datr_linear_wgrad_bf16.restype = i

@@ -12,8 +12,9 @@ training step: every trainable parameter's .grad is a view into one contiguous b
 Works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests).
 
 Two ways of getting the gradients into the buffer:
-  * gather=False: every .grad IS its slice of the buffer during the backward; autograd then runs one tiny `grad += new`
-    kernel per gradient arrival (1 200 of them in a DINO step: 640 parameters, the transformer's used by two passes);
+  * gather=False: every .grad IS its slice of the buffer during the backward; eagerly, autograd runs one tiny
+    `grad += new` kernel per gradient arrival (640 parameters in a DINO step); under CUDA graphs the captured backward of
+    each segment adds its gradients into the slices itself with multi-tensor launches (graphs._TrainingGraph);
   * gather=True: .grad is None during the backward, so autograd simply keeps the first gradient tensor of a
     parameter (no kernel) and adds in place only for a second arrival; collect() then moves everything into the buffer
     with ONE multi-tensor copy and re-points .grad at the slices for the optimizer.
@@ -56,6 +57,12 @@ class FlatGradients:
             p.grad = self.views[-1]
             off += p.numel()
         self.group = process_group
+        if not gather and dev.type == "cuda":
+            # CUDA-graph segments captured from now on add their parameter gradients into these views inside the captured
+            # backward (datr_b200.graphs._TrainingGraph) instead of one eager `grad += new` kernel per parameter
+            from . import graphs
+            if graphs.ACTIVE is not None:
+                graphs.ACTIVE.set_grad_sinks(self)
 
     @property
     def world_size(self):

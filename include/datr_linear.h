@@ -64,6 +64,13 @@ uint64_t datr_linear_wgrad_launch_count(void);
 int datr_linear_tf32_bt(const float* x, const float* w_t, const float* bias, const float* residual, float* y,
                         int M, int N, int K, int relu, void* stream);
 
+/* y = (x w_t + residual) where mask > 0, else 0; mask [M, N] fp32, residual [M, N] optional.  Replaces, in the backward of
+ * a ResNet bottleneck (reference models/dino/backbone.py:62-72 is torchvision's Bottleneck: out = relu(bn3(conv3(..)) +
+ * identity)), three passes autograd runs separately: the input gradient of conv1, its sum with the gradient of the identity
+ * branch, and the ReLU backward of the previous block's output. */
+int datr_linear_tf32_bt_masked(const float* x, const float* w_t, const float* residual, const float* mask, float* y,
+                               int M, int N, int K, void* stream);
+
 int datr_linear_bf16(const void* x, const void* w, const float* bias, const void* residual, int residual_bf16, void* y,
                      int y_bf16, int M, int N, int K, int relu, void* stream);
 int datr_linear_wgrad_bf16(const void* dz, const void* x, float* dw, float* db, int M, int N, int K, void* stream);

@@ -302,3 +302,70 @@ def test_transposed_weight_linear_matches_the_plain_kernel_and_fp64(M, N, K, rel
     want = want * (r.double() > 0) if relu == 3 else (want + r.double() if res else want)
     assert rel(got, want) < REL_TF32
     assert rel(got, plain) < 1e-6
+
+
+@pytest.mark.parametrize("M,N,K,res", [(66800, 512, 128, True), (3001, 1024, 256, True), (130, 256, 64, False), (4200, 2048, 512, True),
+                                       (257, 64, 32, True)])
+def test_masked_transposed_weight_linear(M, N, K, res):
+    """datr_linear_tf32_bt_masked: (x w_t + residual) where mask > 0 -- input gradient of conv1 + gradient of the skip
+    connection + ReLU backward of the previous bottleneck in one kernel.  Against fp64, and bit-equal to the unmasked kernel
+    followed by the mask (same accumulator, same additions)."""
+    from datr_b200.linear import _launch_bt, _launch_bt_masked
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).cuda()
+    w_t = (torch.randn(K, N, generator=g) / K ** 0.5).cuda()
+    r = torch.randn(M, N, generator=g).cuda() if res else None
+    mask = torch.randn(M, N, generator=g).clamp_min(0).cuda()            # a ReLU output: zeros and positives
+    got = _launch_bt_masked(x, w_t, r, mask)
+    want = x.double() @ w_t.double()
+    if res:
+        want = want + r.double()
+    want = want * (mask > 0)
+    assert rel(got, want) < REL_TF32
+    plain = _launch_bt(x, w_t, None, r, 0) * (mask > 0)
+    assert torch.equal(got, plain)
+
+
+def test_resnet_stage_backward_fusion_matches_autograd():
+    """run_stage(): skip gradient handed through the GradCarrier + ReLU mask in the next block's input-gradient GEMM
+    against the same stage with autograd's separate accumulation / threshold passes: identical kernels and operands for
+    everything else, so outputs are equal and gradients agree to fp32 summation order."""
+    from datr_b200 import linear as dl
+    from datr_b200.models.dino import backbone as bb
+    torch.manual_seed(0)
+    down = torch.nn.Sequential(torch.nn.Conv2d(128, 256, 1, stride=2, bias=False), bb.FrozenBatchNorm2d(256))
+    stage = torch.nn.Sequential(bb.Bottleneck(128, 64, stride=2, downsample=down), bb.Bottleneck(256, 64), bb.Bottleneck(256, 64),
+                                bb.Bottleneck(256, 64)).cuda()
+    for m in stage.modules():
+        if isinstance(m, bb.FrozenBatchNorm2d):
+            m.weight.uniform_(0.5, 1.5); m.bias.normal_(0, 0.3); m.running_mean.normal_(0, 0.3); m.running_var.uniform_(0.5, 2.0)
+    stage = stage.to(memory_format=torch.channels_last)
+    x = torch.randn(2, 128, 38, 50, device="cuda").contiguous(memory_format=torch.channels_last)
+    g = torch.randn(2, 256, 19, 25, device="cuda").contiguous(memory_format=torch.channels_last)
+
+    def run(fused):
+        bb._FUSED_BWD = fused
+        dl.set_mode("tf32")
+        try:
+            xa = x.clone().requires_grad_(True)
+            stage.zero_grad()
+            y = bb.run_stage(stage, xa)
+            y.backward(g)
+        finally:
+            dl.set_mode("fp32")
+        return [y.detach().clone(), xa.grad.clone()] + [p.grad.clone() for p in stage.parameters()]
+
+    keep = bb._FUSED_BWD
+    try:
+        from datr_b200 import native
+        n0 = native.linear_launch_count()
+        got = run(True)
+        n_fused = native.linear_launch_count() - n0
+        want = run(False)
+    finally:
+        bb._FUSED_BWD = keep
+    assert torch.equal(got[0], want[0])
+    for a, b in zip(got[1:], want[1:]):
+        assert rel(a, b.double()) < 1e-5
+    # eager evidence that the fused path ran: same number of GEMM launches (the masked entry point replaces the plain one)
+    assert n_fused > 0

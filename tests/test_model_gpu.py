@@ -213,6 +213,113 @@ def test_channels_last_and_graph_replay_match_eager(small, cpu_noise):
         assert float((got[k] - want[k]).abs().max()) / den < 5e-3, k
 
 
+def test_graph_replay_adds_parameter_gradients_into_the_flat_buffer(small, cpu_noise):
+    """With a FlatGradients buffer registered, the captured backward of every segment adds its parameter gradients into
+    the buffer itself (graphs._TrainingGraph: multi-tensor launches inside the graph, nothing handed to AccumulateGrad).
+    Same gradients as the eager model on every replay; dropping the views is reported, not silently ignored."""
+    import copy
+    from datr_b200 import graphs
+    from datr_b200.parallel import FlatGradients
+    model, crit, _ = small
+    tg = mcase.targets(device="cuda")
+    images = [i.cuda() for i in mcase.images()]
+    want_loss, want = _train_losses_and_grads(model, crit, tg, images)
+    fast = copy.deepcopy(model).to(memory_format=torch.channels_last)
+    sg = graphs.StepGraphs()
+    graphs.ACTIVE = sg
+
+    def step():
+        sg.begin_step()
+        fast.train(); crit.train()
+        fast.global_proto = None
+        torch.manual_seed(7)
+        total = mcase.total_loss(crit(fast(images, tg), tg), crit.weight_dict)
+        total.backward()
+        return float(total.detach())
+
+    try:
+        flat = FlatGradients(fast)              # registers its views with the active StepGraphs
+        assert len(sg.grad_sinks) == len(flat.params)
+        for it in range(3):                     # capture, replay, replay
+            flat.zero()
+            got_loss = step()
+            assert flat.check_views()
+            assert abs(got_loss - want_loss) < 1e-4 * abs(want_loss)
+            for k, p in fast.named_parameters():
+                if k in want:
+                    den = max(float(want[k].abs().max()), 1e-6)
+                    assert float((p.grad - want[k]).abs().max()) / den < 5e-3, (it, k)
+                elif p.requires_grad:
+                    assert float(p.grad.abs().max()) == 0.0, (it, k)
+        sunk = sum(g.n_sunk for g, _ in sg.cache.values() if isinstance(g, graphs._TrainingGraph))
+        assert sunk > len(want) // 2, (sunk, len(want))      # the rest belongs to the eager pieces between the segments
+        flat.zero()
+        for p in fast.parameters():
+            p.grad = None
+        with pytest.raises(RuntimeError, match="FlatGradients"):
+            step()
+    finally:
+        graphs.ACTIVE = None
+
+
+def test_tensor_core_mode_backward_fusions_match_plain_autograd(small, cpu_noise, monkeypatch):
+    """The benchmarked configuration -- tensor-core mode, NHWC, CUDA-graph replay with the parameter gradients added inside
+    the captured backward, small weight gradients on the parallel branch of the graph, skip-connection gradients handed
+    through linear.GradCarrier (ResNet bottlenecks, encoder self-attention), the decoder's memory gradients summed along a
+    linear.GradChain -- against the SAME model in the same mode run eagerly with every one of these switched off.  Same
+    kernels and operands in both runs, so the forward is identical and the gradients differ by summation order only."""
+    import copy
+    from datr_b200 import graphs, linear as dl
+    from datr_b200.models.dino import backbone as bb, deformable_transformer as dt
+    from datr_b200.models.dino.ops.modules import ms_deform_attn as mmod
+    from datr_b200.parallel import FlatGradients
+    model, crit, _ = small
+    tg = mcase.targets(device="cuda")
+    images = [i.cuda() for i in mcase.images()]
+    fast = copy.deepcopy(model).to(memory_format=torch.channels_last)
+    dl.set_mode("tf32")
+    try:
+        for mod, name in ((bb, "_FUSED_BWD"), (mmod, "_SKIP_CARRIER"), (dt, "_MEMORY_GRAD_CHAIN")):
+            monkeypatch.setattr(mod, name, False)
+        want_loss, want = _train_losses_and_grads(fast, crit, tg, images)
+        for p in fast.parameters():
+            p.grad = None
+        for mod, name in ((bb, "_FUSED_BWD"), (mmod, "_SKIP_CARRIER"), (dt, "_MEMORY_GRAD_CHAIN")):
+            monkeypatch.setattr(mod, name, True)
+        # the eager step with the fusions on (no graphs, no parallel branch): carriers and chain alone
+        mid_loss, mid = _train_losses_and_grads(fast, crit, tg, images)
+        assert abs(mid_loss - want_loss) <= 1e-6 * abs(want_loss)
+        for k in want:
+            den = max(float(want[k].abs().max()), 1e-6)
+            assert float((mid[k] - want[k]).abs().max()) / den < 1e-3, k
+        for p in fast.parameters():
+            p.grad = None
+        sg = graphs.StepGraphs()
+        graphs.ACTIVE = sg
+        try:
+            flat = FlatGradients(fast)
+            for it in range(3):
+                flat.zero()
+                sg.begin_step()
+                fast.train(); crit.train()
+                fast.global_proto = None
+                torch.manual_seed(7)
+                total = mcase.total_loss(crit(fast(images, tg), tg), crit.weight_dict)
+                total.backward()
+                assert abs(float(total.detach()) - want_loss) < 1e-5 * abs(want_loss)
+                for k, p in fast.named_parameters():
+                    if k in want:
+                        den = max(float(want[k].abs().max()), 1e-6)
+                        assert float((p.grad - want[k]).abs().max()) / den < 1e-3, (it, k)
+            tgs = [g for g, _ in sg.cache.values() if isinstance(g, graphs._TrainingGraph)]
+            assert sum(g.n_sunk for g in tgs) > len(want) // 2
+            assert sum(g.side_launches for g in tgs) > 0, "no weight gradient took the parallel branch"
+        finally:
+            graphs.ACTIVE = None
+    finally:
+        dl.set_mode("fp32")
+
+
 @pytest.mark.parametrize("flag", [False, True], ids=["burn_in", "self_training"])
 def test_joint_encoder_decoder_passes_match_the_two_pass_structure(small, cpu_noise, flag, monkeypatch):
     """DINO.forward runs the encoder and the decoder ONCE on the source + target halves (zero de-noising slots for the

@@ -70,11 +70,16 @@ def index_flips(a, b):
     return diff, tot
 
 
-def run_parity_pass(model, crit, samples, targets, seed=7):
-    """One training forward + criterion + backward with recorded index work.  Returns dict of python values."""
+def run_parity_pass(model, crit, samples, targets, seed=7, keep_grad_views=False):
+    """One training forward + criterion + backward with recorded index work.  Returns dict of python values.
+    `keep_grad_views`: the .grad tensors are views of a FlatGradients buffer the captured backward graphs add into
+    (datr_b200.graphs) -- they are zeroed in place instead of being dropped."""
     model.train(); crit.train()
     for p in model.parameters():
-        p.grad = None
+        if keep_grad_views and p.grad is not None:
+            p.grad.zero_()
+        else:
+            p.grad = None
     torch.manual_seed(seed)
     out = model(samples, targets)
     # the two-stage top-k (deformable_transformer.py:342) gathers one proposal box per selected token, and every
@@ -304,14 +309,13 @@ def main():
             wl.model.global_proto = None
             samples = NestedTensor(wl.images.copy_(images), wl.mask.copy_(mask))
             wl.grads.zero()
-            r = run_parity_pass(wl.model, wl.criterion, samples, targets)
-            for p in wl.model.parameters():                    # run_parity_pass detached .grad from the flat buffer
-                p.grad = None
+            r = run_parity_pass(wl.model, wl.criterion, samples, targets, keep_grad_views=True)
             ours[mode] = r
             compare(f"ours_{mode}_vs_reference_fp32", r, ref_runs["fp32"], report)
         _dn.SYNC_FREE = True
         if mode == "tf32" and not a.skip_timing:
-            wl.grads = __import__("datr_b200.parallel", fromlist=["FlatGradients"]).FlatGradients(wl.model, late=lambda n: n.startswith("backbone"))
+            if not wl.grads.check_views():
+                wl.grads = __import__("datr_b200.parallel", fromlist=["FlatGradients"]).FlatGradients(wl.model, late=lambda n: n.startswith("backbone"))
             wl.model._on_backbone_output_grad = wl.grads.reduce_early
             _groups = __import__("datr_b200.parallel", fromlist=["param_groups"]).param_groups(wl.model, 1e-4, 1e-5)
             if getattr(wl, "flat_opt", False):

@@ -15,6 +15,7 @@
 #   launches     ncu launch list (gpu__time_duration.sum) of the msda workload and of the hand-written kernels of the dino step
 #   ncu_msda     ncu --set full of the MSDeformAttn kernels at the config-2 encoder / decoder calls
 #   probes       the standalone probes under tools/probes (built here, run there)
+#   toggles      default bench with / without the in-graph gradient sinks and the side-branch weight gradients
 set -u
 TAG=${1:?tag}; shift
 mkdir -p gpurun_out
@@ -63,6 +64,14 @@ for stage in "$@"; do
     probes)
       for p in gemm_2cta_probe msda_tile_probes tmem_ld_layout_probe; do
         [ -x build/$p ] && { timeout 180 build/$p > gpurun_out/${TAG}_$p.txt 2>&1; echo "$p rc=$?"; tail -4 gpurun_out/${TAG}_$p.txt; }
+      done ;;
+    toggles)
+      # A/B of the graph-side switches on the default workload (short runs, no CPU baseline, no eager leg)
+      # TOGGLES="name:ENV=v,ENV2=v name2:..." overrides the list
+      for cfg in ${TOGGLES:-new: noside:DATR_WGRAD_SIDE_ROWS=0 base:DATR_WGRAD_SIDE_ROWS=0,DATR_GRAPH_SINKS=0}; do
+        nm=${cfg%%:*}; envs=${cfg#*:}; envs=${envs//,/ }
+        env $envs timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-eager > gpurun_out/${TAG}_toggle_${nm}.json 2> gpurun_out/${TAG}_toggle_${nm}.err
+        echo "$nm rc=$? $(python -c "import json,sys; d=json.load(open('gpurun_out/${TAG}_toggle_${nm}.json')); print(round(d['ms_per_step'],3),'ms', round(d['e2e']['ms_per_step'],3),'ms e2e, loss',d.get('loss'))" 2>&1 | tail -1)"
       done ;;
     *) echo "unknown stage $stage"; exit 2 ;;
   esac
