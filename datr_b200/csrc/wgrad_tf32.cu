@@ -328,29 +328,52 @@ int zero_outputs(float* dw, float* db, int N, int K, cudaStream_t stream) {
 
 extern "C" {
 
-int datr_linear_wgrad_tf32(const float* dz, const float* x, float* dw, float* db, int M, int N, int K, void* stream_) {
+static int wgrad_tf32(const float* dz, const float* x, float* dw, float* db, int M, int N, int K, void* stream_, bool accumulate) {
   if (!dz || !x || !dw) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "null pointer argument%s");
   if (M <= 0 || N <= 0 || K <= 0) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "all dimensions must be positive%s");
   if (N % 4 != 0 || K % 4 != 0) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "N and K must be multiples of 4%s");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al16(dz) || !al16(x) || !al16(dw)) return wfail(DATR_LINEAR_ERR_ALIGNMENT, "buffers must be 16-byte aligned%s");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (int rc = zero_outputs(dw, db, N, K, stream)) return rc;
+  if (!accumulate)
+    if (int rc = zero_outputs(dw, db, N, K, stream)) return rc;
   CUtensorMap mdz, mx;
   if (int rc = make_map(&mdz, dz, M, N)) return rc;
   if (int rc = make_map(&mx, x, M, K)) return rc;
   return K > 128 ? launch<256, 4>(mdz, mx, dw, db, M, N, K, stream) : launch<128, 6>(mdz, mx, dw, db, M, N, K, stream);
 }
 
+int datr_linear_wgrad_tf32(const float* dz, const float* x, float* dw, float* db, int M, int N, int K, void* stream_) {
+  return wgrad_tf32(dz, x, dw, db, M, N, K, stream_, false);
+}
+
+// dw += dz^T x, db += column sums of dz: the same kernel without the zero fill -- its partial tiles are reduced into dw / db
+// with atomics anyway, so a gradient buffer that already holds earlier contributions (the step's flat .grad buffer) takes the
+// weight gradient directly: no temporary, no zero fill, no `grad += new` pass.
+int datr_linear_wgrad_tf32_acc(const float* dz, const float* x, float* dw, float* db, int M, int N, int K, void* stream_) {
+  return wgrad_tf32(dz, x, dw, db, M, N, K, stream_, true);
+}
+
 // bf16 operands (dz [M, N], x [M, K] as bf16), fp32 accumulation, dw [N, K] / db [N] fp32.
+static int wgrad_bf16(const void* dz, const void* x, float* dw, float* db, int M, int N, int K, void* stream_, bool accumulate);
+
 int datr_linear_wgrad_bf16(const void* dz, const void* x, float* dw, float* db, int M, int N, int K, void* stream_) {
+  return wgrad_bf16(dz, x, dw, db, M, N, K, stream_, false);
+}
+
+int datr_linear_wgrad_bf16_acc(const void* dz, const void* x, float* dw, float* db, int M, int N, int K, void* stream_) {
+  return wgrad_bf16(dz, x, dw, db, M, N, K, stream_, true);
+}
+
+static int wgrad_bf16(const void* dz, const void* x, float* dw, float* db, int M, int N, int K, void* stream_, bool accumulate) {
   if (!dz || !x || !dw) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "null pointer argument%s");
   if (M <= 0 || N <= 0 || K <= 0) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "all dimensions must be positive%s");
   if (N % 8 != 0 || K % 8 != 0) return wfail(DATR_LINEAR_ERR_BAD_ARGUMENT, "N and K must be multiples of 8 for bf16 operands%s");
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (!al16(dz) || !al16(x) || !al16(dw)) return wfail(DATR_LINEAR_ERR_ALIGNMENT, "buffers must be 16-byte aligned%s");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (int rc = zero_outputs(dw, db, N, K, stream)) return rc;
+  if (!accumulate)
+    if (int rc = zero_outputs(dw, db, N, K, stream)) return rc;
   CUtensorMap mdz, mx;
   if (int rc = make_map_bf16(&mdz, dz, M, N)) return rc;
   if (int rc = make_map_bf16(&mx, x, M, K)) return rc;

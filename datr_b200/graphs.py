@@ -135,8 +135,9 @@ class _TrainingGraph:
     """Forward and backward CUDA graphs of one module -- the capture protocol of torch.cuda.make_graphed_callables (side-
     stream warm-up, forward capture, backward capture of torch.autograd.grad into static gradient tensors sharing one
     memory pool, replay from a torch.autograd.Function) with one difference: parameters listed in `sinks`
-    (id(parameter) -> persistent gradient buffer) get their gradient ADDED INTO that buffer inside the captured backward,
-    by multi-tensor launches, and the autograd node returns None for them.  torch's version hands the static gradient of
+    (id(parameter) -> persistent gradient buffer) get their gradient ADDED INTO that buffer inside the captured backward --
+    by the weight-gradient kernel itself where a Linear owns the parameter (linear.GradSinks), by multi-tensor launches at
+    the end of the capture for the rest -- and the autograd node returns None for them.  torch's version hands the static gradient of
     every parameter to AccumulateGrad, i.e. one eager `grad += new` kernel per parameter per replay (640 per DINO step)."""
 
     def __init__(self, module, sample_args, warmup_iters, sinks):
@@ -176,11 +177,12 @@ class _TrainingGraph:
             branch = dl.SideWgrad(torch.cuda.Stream(), dl.SIDE_WGRAD_MAX_ROWS) if dl.SIDE_WGRAD_MAX_ROWS > 0 else None
             with torch.cuda.graph(bwd, pool=pool):
                 dl._SIDE = branch        # small weight-gradient launches become a parallel branch of this graph
+                direct = dl._SINKS = dl.GradSinks(sinks) if sinks else None     # Linears reduce dW / db straight into the sinks
                 try:
                     grads = torch.autograd.grad(outs_req, req, tuple(g for g in static_grad_outputs if g is not None),
                                                 only_inputs=True, allow_unused=True)
                 finally:
-                    dl._SIDE = None
+                    dl._SIDE = dl._SINKS = None
                 if branch is not None and branch.used:
                     torch.cuda.current_stream().wait_stream(branch.stream)
                     self.side_launches = branch.used
@@ -199,6 +201,10 @@ class _TrainingGraph:
                 if dst:
                     torch._foreach_add_(dst, src)
                 n_sunk = len(dst)
+                if direct is not None and direct.used:
+                    n_sunk += len({id(p) for p, _ in direct.used})
+                    if probe is None:
+                        probe = direct.used[0]
                 grads = tuple(kept)
                 del dst, src, kept
         it = iter(grads)

@@ -198,11 +198,81 @@ def _wgrad(g2, x2, want_db):
     return dw, db
 
 
+class GradSinks:
+    """Set as `linear._SINKS` by graphs._TrainingGraph while it captures a segment's backward: `map` is id(parameter) ->
+    persistent gradient buffer (a FlatGradients view, zeroed once per step).  A Linear whose weight (and bias) ARE such
+    parameters -- not slices, concatenations or products of them -- lets its weight-gradient kernel reduce straight into
+    the buffers (datr_linear_wgrad_*_acc) and returns no gradient to autograd: no temporary, no zero fill, no accumulation
+    pass, and nothing downstream that would have to wait for the kernel (it may run on the parallel branch)."""
+
+    def __init__(self, mapping):
+        self.map, self.used = mapping, []
+
+    def lookup(self, weight, bias, want_gb):
+        if not isinstance(weight, torch.nn.Parameter):
+            return None
+        sw = self.map.get(id(weight))
+        if sw is None or sw.shape != weight.shape or not sw.is_contiguous() or sw.data_ptr() % 16:
+            return None
+        sb = None
+        if want_gb:
+            if not isinstance(bias, torch.nn.Parameter):
+                return None
+            sb = self.map.get(id(bias))
+            if sb is None or sb.shape != bias.shape or not sb.is_contiguous() or sb.data_ptr() % 4:
+                return None
+        return sw, sb
+
+
+_SINKS = None
+
+
+def _wgrad_into(sinks, pairs, g2, x2, bf16=False):
+    """dW (+ db) of one Linear reduced directly into its gradient buffers `pairs` = (sink_w, sink_b | None)."""
+    sw, sb = pairs
+    M, N = g2.shape
+    K = x2.shape[1]
+    lib = native.lib()
+    fn = lib.datr_linear_wgrad_bf16_acc if bf16 else lib.datr_linear_wgrad_tf32_acc
+    with torch.cuda.device(g2.device):
+        rc = fn(g2.data_ptr(), x2.data_ptr(), sw.data_ptr(), sb.data_ptr() if sb is not None else None, M, N, K,
+                torch.cuda.current_stream().cuda_stream)
+    if rc != 0:
+        raise RuntimeError(f"datr_linear_wgrad_*_acc failed (code {rc}): {lib.datr_linear_wgrad_last_error().decode()}")
+
+
+def _wgrad_param(fn, g2, x2, want_db, weight, bias, bf16=False):
+    """Weight / bias gradient of a Linear: into the parameters' gradient buffers when they are registered (returns
+    (None, None): autograd gets nothing) -- then also eligible for the parallel branch --, else `fn` on the main branch."""
+    sinks = _SINKS
+    pairs = sinks.lookup(weight, bias, want_db) if sinks is not None and g2.is_cuda else None
+    if pairs is None:
+        return fn(g2, x2, want_db)
+    side = _SIDE
+    if side is not None and g2.shape[0] <= side.max_rows and torch.cuda.current_stream() != side.stream:
+        side.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side.stream):
+            _wgrad_into(sinks, pairs, g2, x2, bf16)
+        # both operands were allocated on the main branch: their memory must not be handed out again while this branch reads it
+        g2.record_stream(side.stream)
+        x2.record_stream(side.stream)
+        side.used += 1
+    else:
+        _wgrad_into(sinks, pairs, g2, x2, bf16)
+    sinks.used.append((weight, pairs[0]))
+    if pairs[1] is not None:
+        sinks.used.append((bias, pairs[1]))
+    return None, None
+
+
 class SideWgrad:
     """Set as `linear._SIDE` by graphs._TrainingGraph while it captures a segment's backward: weight-gradient launches of
-    at most `max_rows` rows go to `stream`, a parallel branch of the captured graph.  At decoder sizes (4 400 rows) a
-    weight-gradient kernel occupies a few dozen SMs and nothing downstream of the input-gradient chain waits for it; on
-    one stream it still serialises with that chain.  The capture joins the branch before it consumes the gradients."""
+    at most `max_rows` rows that reduce straight into a parameter's gradient buffer (GradSinks) go to `stream`, a parallel
+    branch of the captured graph.  At decoder sizes (4 400 rows) a weight-gradient kernel occupies a few dozen SMs and
+    nothing in the rest of the pass reads its result; on one stream it still serialises with the input-gradient chain.
+    Gradients that autograd post-processes (slices / concatenations / products of parameters, shared parameters summed by
+    the engine) stay on the main branch: the engine runs those operations there without waiting for this stream.  The
+    capture joins the branch at its end."""
 
     def __init__(self, stream, max_rows):
         self.stream, self.max_rows, self.used = stream, max_rows, 0
@@ -210,21 +280,6 @@ class SideWgrad:
 
 _SIDE = None
 SIDE_WGRAD_MAX_ROWS = int(_os.environ.get("DATR_WGRAD_SIDE_ROWS", "16384"))      # 0: every launch stays on the main branch
-
-
-def _wgrad_branch(fn, g2, x2, want_db):
-    side = _SIDE
-    if (side is None or g2.shape[0] > side.max_rows or not g2.is_cuda
-            or torch.cuda.current_stream() == side.stream):          # already on the branch (a chained layer)
-        return fn(g2, x2, want_db)
-    side.stream.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side.stream):
-        out = fn(g2, x2, want_db)
-    # both operands were allocated on the main branch: their memory must not be handed out again while this branch reads it
-    g2.record_stream(side.stream)
-    x2.record_stream(side.stream)
-    side.used += 1
-    return out
 
 
 def _zero_rows(t2, mask):
@@ -243,6 +298,7 @@ class _LinearTF32(torch.autograd.Function):
         ctx.skip_out, ctx.skip_in = skip_out if residual is not None else None, skip_in
         ctx.mask_input_grad, ctx.grad_premasked = bool(mask_input_grad), bool(grad_premasked)
         ctx.chain = chain               # GradChain: x's gradient is accumulated across the layers sharing the chain
+        ctx.params = (weight, bias)     # the objects themselves: their registered gradient buffers are looked up by identity
         K = weight.shape[1]
         x2 = _c(x.reshape(-1, K))
         w = _c(weight)
@@ -261,7 +317,8 @@ class _LinearTF32(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         side = _SIDE
-        if ctx.chain is None or side is None or not ctx.needs_input_grad[0] or not gy.is_cuda:
+        if (ctx.chain is None or side is None or not ctx.needs_input_grad[0] or not gy.is_cuda or _SINKS is None
+                or _SINKS.lookup(ctx.params[0], ctx.params[1], ctx.has_bias and ctx.needs_input_grad[2]) is None):
             return _LinearTF32._backward(ctx, gy)
         # nothing in the rest of this backward pass waits for a chained layer: its whole backward joins the parallel branch
         main = torch.cuda.current_stream()
@@ -330,7 +387,7 @@ class _LinearTF32(torch.autograd.Function):
                 else:
                     ch.g, gx = gx.view(-1, K), None
         if fused:
-            gw, gb = _wgrad_branch(_wgrad, g2, x2, want_gb)
+            gw, gb = _wgrad_param(_wgrad, g2, x2, want_gb, *ctx.params)
         else:
             if want_gb and gb is None:
                 gb = _colsum(g2)[1]
@@ -355,6 +412,7 @@ class _FFNTF32(torch.autograd.Function):
         h = _launch(x2, w1c, _c(b1), None, 1)
         y = _launch(h, w2c, _c(b2), x2, 0)
         ctx.xshape = x.shape
+        ctx.params = (w1, b1, w2, b2)
         ctx.save_for_backward(x2, w1c, w2c, h)
         return y.view(x.shape)
 
@@ -363,9 +421,10 @@ class _FFNTF32(torch.autograd.Function):
     def backward(ctx, gy):
         x2, w1, w2, h = ctx.saved_tensors
         g2 = _c(gy.reshape(-1, w2.shape[0]))
-        gw2, gb2 = _wgrad_branch(_wgrad, g2, h, True)
+        w1p, b1p, w2p, b2p = ctx.params
+        gw2, gb2 = _wgrad_param(_wgrad, g2, h, True, w2p, b2p)
         dz1 = _launch_bt(g2, w2, None, h, 3)
-        gw1, gb1 = _wgrad_branch(_wgrad, dz1, x2, True)
+        gw1, gb1 = _wgrad_param(_wgrad, dz1, x2, True, w1p, b1p)
         gx = _launch_bt(dz1, w1, None, g2, 0).view(ctx.xshape)
         return gx, gw1, gb1, gw2, gb2
 
@@ -421,6 +480,7 @@ class _FFNBF16(torch.autograd.Function):
         h = _launch_bf16(xb, w1b, _c(b1), None, 1, True)
         y = _launch_bf16(h, w2b, _c(b2), x2, 0, False)
         ctx.xshape = x.shape
+        ctx.params = (w1, b1, w2, b2)
         ctx.save_for_backward(xb, w1b, w2b, h)
         return y.view(x.shape)
 
@@ -430,9 +490,10 @@ class _FFNBF16(torch.autograd.Function):
         xb, w1b, w2b, h = ctx.saved_tensors
         g2 = _c(gy.reshape(-1, w2b.shape[0]))
         gb = g2.to(torch.bfloat16)
-        gw2, gb2 = _wgrad_bf16(gb, h, True)
+        w1p, b1p, w2p, b2p = ctx.params
+        gw2, gb2 = _wgrad_param(_wgrad_bf16, gb, h, True, w2p, b2p, bf16=True)
         dz1 = _launch_bf16(gb, w2b.t().contiguous(), None, h, 3, True, residual_bf16=True)
-        gw1, gb1 = _wgrad_bf16(dz1, xb, True)
+        gw1, gb1 = _wgrad_param(_wgrad_bf16, dz1, xb, True, w1p, b1p, bf16=True)
         gx = _launch_bf16(dz1, w1b.t().contiguous(), None, g2, 0, False).view(ctx.xshape)
         return gx, gw1, gb1, gw2, gb2
 

@@ -30,7 +30,7 @@ EXPORTS = ("datr_msda_forward", "datr_msda_backward", "datr_msda_fused_forward",
            "datr_layernorm256_forward", "datr_layernorm256_backward", "datr_layernorm_last_error", "datr_layernorm_launch_count",
            "datr_colsum", "datr_relu_bwd_colsum", "datr_colsum_last_error", "datr_colsum_launch_count",
            "datr_conv3x3_nhwc_tf32", "datr_conv3x3_wgrad_nhwc_tf32", "datr_conv_last_error", "datr_conv_launch_count",
-           "datr_linear_wgrad_tf32", "datr_linear_wgrad_last_error", "datr_linear_wgrad_launch_count",
+           "datr_linear_wgrad_tf32", "datr_linear_wgrad_tf32_acc", "datr_linear_wgrad_bf16_acc", "datr_linear_wgrad_last_error", "datr_linear_wgrad_launch_count",
            "datr_zero_masked_rows", "datr_rowmask_last_error", "datr_rowmask_launch_count",
            "datr_attn_softmax_forward", "datr_attn_softmax_backward", "datr_attn_last_error", "datr_attn_launch_count",
            "datr_attn_mask_words", "datr_attn_pack_mask", "datr_attn_fused_forward", "datr_attn_fused_backward", "datr_attn_fused_last_error",
@@ -161,6 +161,9 @@ def lib() -> ctypes.CDLL:
         L.datr_conv_launch_count.restype = ctypes.c_uint64
         L.datr_linear_wgrad_tf32.restype = i
         L.datr_linear_wgrad_tf32.argtypes = [vp, vp, vp, vp, i, i, i, vp]
+        for fn in (L.datr_linear_wgrad_tf32_acc, L.datr_linear_wgrad_bf16_acc):
+            fn.restype = i
+            fn.argtypes = [vp, vp, vp, vp, i, i, i, vp]
         L.datr_linear_wgrad_last_error.restype = ctypes.c_char_p
         L.datr_linear_wgrad_launch_count.restype = ctypes.c_uint64
         L.datr_zero_masked_rows.restype = i

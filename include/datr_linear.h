@@ -49,6 +49,9 @@ int datr_linear_tf32(const float* x, const float* w, const float* bias, const fl
  * (summation order, hence the last bits, vary from run to run).  N % 4 == 0, K % 4 == 0.
  */
 int datr_linear_wgrad_tf32(const float* dz, const float* x, float* dw, float* db, int M, int N, int K, void* stream);
+/* dw += dz^T x, db += column sums of dz: no zero fill -- the reductions land in a buffer that already holds gradient
+ * (what autograd's AccumulateGrad does with `param.grad += new` after `grad_output.t().mm(input)`, in one kernel). */
+int datr_linear_wgrad_tf32_acc(const float* dz, const float* x, float* dw, float* db, int M, int N, int K, void* stream);
 const char* datr_linear_wgrad_last_error(void);
 uint64_t datr_linear_wgrad_launch_count(void);
 
@@ -74,6 +77,7 @@ int datr_linear_tf32_bt_masked(const float* x, const float* w_t, const float* re
 int datr_linear_bf16(const void* x, const void* w, const float* bias, const void* residual, int residual_bf16, void* y,
                      int y_bf16, int M, int N, int K, int relu, void* stream);
 int datr_linear_wgrad_bf16(const void* dz, const void* x, float* dw, float* db, int M, int N, int K, void* stream);
+int datr_linear_wgrad_bf16_acc(const void* dz, const void* x, float* dw, float* db, int M, int N, int K, void* stream);
 
 const char* datr_linear_last_error(void);
 

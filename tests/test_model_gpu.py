@@ -267,7 +267,9 @@ def test_tensor_core_mode_backward_fusions_match_plain_autograd(small, cpu_noise
     the captured backward, small weight gradients on the parallel branch of the graph, skip-connection gradients handed
     through linear.GradCarrier (ResNet bottlenecks, encoder self-attention), the decoder's memory gradients summed along a
     linear.GradChain -- against the SAME model in the same mode run eagerly with every one of these switched off.  Same
-    kernels and operands in both runs, so the forward is identical and the gradients differ by summation order only."""
+    kernels and operands in both runs, so the forward is identical and the gradients differ by summation order only -- which
+    TF32 operand rounding amplifies (a one-ulp difference in a gradient that is a GEMM operand can round the other way:
+    2^-11 of that element), hence the 5e-3 bar of the other graph-replay test; a lost term or a race is an O(1) error."""
     import copy
     from datr_b200 import graphs, linear as dl
     from datr_b200.models.dino import backbone as bb, deformable_transformer as dt
@@ -291,7 +293,7 @@ def test_tensor_core_mode_backward_fusions_match_plain_autograd(small, cpu_noise
         assert abs(mid_loss - want_loss) <= 1e-6 * abs(want_loss)
         for k in want:
             den = max(float(want[k].abs().max()), 1e-6)
-            assert float((mid[k] - want[k]).abs().max()) / den < 1e-3, k
+            assert float((mid[k] - want[k]).abs().max()) / den < 5e-3, k
         for p in fast.parameters():
             p.grad = None
         sg = graphs.StepGraphs()
@@ -310,7 +312,7 @@ def test_tensor_core_mode_backward_fusions_match_plain_autograd(small, cpu_noise
                 for k, p in fast.named_parameters():
                     if k in want:
                         den = max(float(want[k].abs().max()), 1e-6)
-                        assert float((p.grad - want[k]).abs().max()) / den < 1e-3, (it, k)
+                        assert float((p.grad - want[k]).abs().max()) / den < 5e-3, (it, k)
             tgs = [g for g, _ in sg.cache.values() if isinstance(g, graphs._TrainingGraph)]
             assert sum(g.n_sunk for g in tgs) > len(want) // 2
             assert sum(g.side_launches for g in tgs) > 0, "no weight gradient took the parallel branch"

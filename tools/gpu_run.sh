@@ -12,6 +12,7 @@
 #   reference[:4scale|5scale[:init|seeded]]   tools/bench_reference_gpu.py: the reference model on this GPU + full-size parity
 #   micro_msda | micro_linear | micro_conv    the per-kernel micro-benchmarks against the reference CUDA op / cuBLAS / cuDNN
 #   kernels      torch.profiler kernel table + idle-gap report of the graph-replayed step
+#   timeline     per-segment device timeline of the graph-replayed step (tools/timeline_report.py)
 #   launches     ncu launch list (gpu__time_duration.sum) of the msda workload and of the hand-written kernels of the dino step
 #   ncu_msda     ncu --set full of the MSDeformAttn kernels at the config-2 encoder / decoder calls
 #   probes       the standalone probes under tools/probes (built here, run there)
@@ -49,6 +50,9 @@ for stage in "$@"; do
       timeout 600 python tools/profile_dino.py > /dev/null 2>&1; cp gpurun_out/dino_step_kernels.txt gpurun_out/${TAG}_dino_step_kernels_graphs.txt
       timeout 600 python tools/gap_report.py > /dev/null 2>&1; cp gpurun_out/dino_step_gaps.txt gpurun_out/${TAG}_dino_step_gaps.txt
       head -40 gpurun_out/${TAG}_dino_step_kernels_graphs.txt | cut -c1-180 ;;
+    timeline)
+      timeout 600 python tools/timeline_report.py > gpurun_out/${TAG}_timeline.log 2>&1; echo "rc=$?"
+      cp gpurun_out/dino_step_timeline.txt gpurun_out/${TAG}_dino_step_timeline.txt; head -40 gpurun_out/${TAG}_dino_step_timeline.txt | cut -c1-170 ;;
     launches)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches_msda.csv \
         python bench.py --workload msda --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_under_ncu_msda.log 2>&1
