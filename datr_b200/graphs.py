@@ -50,10 +50,13 @@ class StepGraphs:
         # parameter gradients into these buffers itself (one multi-tensor launch inside the graph) and hands autograd
         # nothing, instead of one eager `grad += new` kernel per parameter after every replay (DATR_GRAPH_SINKS=0: off)
         self.grad_sinks = {}
+        self.side_segments = os.environ.get("DATR_SIDE_SEGMENTS", "1") != "0"
+        self._side_stream, self._side_pending = None, False
         self.sink_grads = os.environ.get("DATR_GRAPH_SINKS", "1") != "0"
 
     def begin_step(self):
         self.calls.clear()
+        self.join_side()
 
     def set_grad_sinks(self, flat):
         """Register the gradient buffers of `flat` (datr_b200.parallel.FlatGradients, gather=False: every .grad is a
@@ -73,14 +76,23 @@ class StepGraphs:
         for p, v in zip(flat.params, flat.views):
             self.grad_sinks[id(p)] = v
 
-    def call(self, name, owner, fn, *args):
+    def call(self, name, owner, fn, *args, side=False):
         """Run `fn(*args)` (args: any pytree of tensors and hashable constants; `owner`: the nn.Module whose
-        parameters fn uses, or None) as a graph segment; returns fn's output pytree."""
+        parameters fn uses, or None) as a graph segment; returns fn's output pytree.
+        `side`: replay the segment on a second stream, beside what the caller enqueues next; its results are valid on the
+        caller's stream after join_side().  Autograd runs the segment's backward on that stream too -- beside the backward of
+        whatever the caller ran in between -- and orders it against producers and consumers of its gradients itself."""
         if name in self.skip:
             return fn(*args)
-        return _call_segment(self, name, owner, fn, args)
+        return _call_segment(self, name, owner, fn, args, side and self.side_segments)
 
-    def run(self, name, make_module, args, key_extra=(), want_module=False, owner=None):
+    def join_side(self):
+        """Make the results of every `side=True` segment of this step visible to the current stream."""
+        if self._side_pending:
+            torch.cuda.current_stream().wait_stream(self._side_stream)
+            self._side_pending = False
+
+    def run(self, name, make_module, args, key_extra=(), want_module=False, owner=None, side=False):
         """Run segment `name` on tensor arguments `args` through its graph (capturing it on first use).  `owner`
         (optional) is the module the segment belongs to: two models that run the same segment on the same shapes (student
         and EMA teacher) get separate graphs."""
@@ -118,7 +130,15 @@ class StepGraphs:
             self.captures += 1
         graphed, per_pair = entry
         self.replayed_native_launches += per_pair
-        out = graphed(*args)
+        if side and grad:
+            if self._side_stream is None:
+                self._side_stream = torch.cuda.Stream()
+            self._side_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side_stream):
+                out = graphed(*args)
+            self._side_pending = True
+        else:
+            out = graphed(*args)
         if self.alias_inputs and grad:
             for o in (out if isinstance(out, (tuple, list)) else (out,)):
                 if isinstance(o, torch.Tensor) and o.is_cuda:
@@ -305,7 +325,7 @@ class FnSegment(nn.Module):
         return tuple(l for l in flat if isinstance(l, torch.Tensor))
 
 
-def _call_segment(sg: "StepGraphs", name, owner, fn, args):
+def _call_segment(sg: "StepGraphs", name, owner, fn, args, side=False):
     from torch.utils import _pytree as pytree
     leaves, spec = pytree.tree_flatten(args)
     consts = tuple((i, l) for i, l in enumerate(leaves) if not isinstance(l, torch.Tensor))
@@ -317,7 +337,7 @@ def _call_segment(sg: "StepGraphs", name, owner, fn, args):
         return holder["m"]
 
     key_extra = (repr(spec), repr(consts))
-    out_tensors, module = sg.run(name, make, tensors, key_extra=key_extra, want_module=True, owner=owner)
+    out_tensors, module = sg.run(name, make, tensors, key_extra=key_extra, want_module=True, owner=owner, side=side)
     if not isinstance(out_tensors, tuple):
         out_tensors = (out_tensors,)
     it = iter(out_tensors)

@@ -349,6 +349,13 @@ class DINO(nn.Module):
         # the eager de-noising query construction, and a parameter must not be shared between a live eager graph and a
         # segment being captured.)
         hs[0] = hs[0] + self.label_enc.weight[0, 0] * 0.0
+        da = {}
+        if self.training and graphs.ACTIVE is not None and srcs_all[0].is_cuda:
+            # image-level discriminator (dense 3x3 convolutions that depend on the projected feature maps only) as a
+            # segment on a second stream: forward beside the prediction heads / the matcher, and -- autograd runs a
+            # node's backward on the stream of its forward, latest nodes first -- its backward beside the heads' and the
+            # decoder's backward, whose short kernels leave most SMs idle.  Joined before forward() returns.
+            da["backbone_DA"] = graphs.ACTIVE.call("d_img", self.D_img, self._image_discriminator, tuple(srcs_all), side=True)
         outputs_class, interm_class = self._class_logits(hs, hs_enc)
         if graphs.ACTIVE is not None and hs[0].is_cuda:
             out = graphs.ACTIVE.call("heads", self.bbox_embed, self._outputs_from, tuple(hs), tuple(reference),
@@ -363,10 +370,7 @@ class DINO(nn.Module):
             prefetch(getattr(self, "_prefetch_matcher", None), out, targets)
 
         # ---- domain adaptation -----------------------------------------------------------------
-        da = {}
-        if graphs.ACTIVE is not None and srcs_all[0].is_cuda:
-            da["backbone_DA"] = graphs.ACTIVE.call("d_img", self.D_img, self._image_discriminator, tuple(srcs_all))
-        else:
+        if "backbone_DA" not in da:
             da["backbone_DA"] = self._image_discriminator(tuple(srcs_all))
 
         pad = dn_meta["pad_size"] if dn_meta is not None else 0
@@ -395,6 +399,8 @@ class DINO(nn.Module):
             if hs_enc_t is not None:
                 self._interm(out, self.transformer.enc_out_class_embed(hs_enc_t[-1]), ref_enc_t, init_box_proposal_t,
                              suffix="_target")
+        if graphs.ACTIVE is not None:
+            graphs.ACTIVE.join_side()       # the discriminator's outputs are valid on the caller's stream from here on
         return out
 
     @torch.jit.unused
