@@ -57,7 +57,7 @@ for stage in "$@"; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/${TAG}_launches_msda.csv \
         python bench.py --workload msda --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_bench_under_ncu_msda.log 2>&1
       DATR_GRAPHS=0 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none \
-        -k "regex:msda_|linear_tf32|wgrad_tf32|layernorm256|softmax_|conv3x3|colsum|zero_masked|ema_update" --launch-skip 1500 -c 2500 --csv \
+        -k "regex:msda_|linear_tf32|wgrad_tf32|layernorm256|softmax_|conv3x3|colsum|zero_masked|ema_update|attn_fwd|attn_bwd|adamw_step|lsa_kernel|gn_fwd|gn_bwd|sine_embed|pos_embed|bn_relu_maxpool" --launch-skip 1500 -c 2500 --csv \
         --log-file gpurun_out/${TAG}_launches_dino_handwritten.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-eager > gpurun_out/${TAG}_bench_under_ncu_dino.log 2>&1
       python tools/launch_list_summary.py gpurun_out/${TAG}_launches_msda.csv gpurun_out/${TAG}_msda_workload_launches.txt "ncu launch list of: python bench.py --workload msda --steps 2 --warmup 3"
       python tools/launch_list_summary.py gpurun_out/${TAG}_launches_dino_handwritten.csv gpurun_out/${TAG}_dino_step_handwritten_launches.txt "ncu launch list (hand-written kernels, eager) of: python bench.py --steps 1 --warmup 3"
