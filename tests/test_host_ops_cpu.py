@@ -57,3 +57,75 @@ def test_layer_norm_and_attention_dispatch_on_cpu():
     q = torch.randn(1, 2, 5, 8)
     assert not attention.applicable(q, None, 0.0)                       # CPU tensors keep the SDPA path
     assert not attention.applicable(q, torch.zeros(5, 5), 0.0)
+
+
+def test_backward_fusion_flags_need_the_tensor_core_path():
+    """skip / mask / chain flags change what the backward returns to autograd: on the plain torch path they must not be
+    silently ignored."""
+    x = torch.randn(4, 32); w = torch.randn(16, 32)
+    for kw in (dict(skip_in=dl.GradCarrier()), dict(skip_out=dl.GradCarrier(), residual=torch.randn(4, 16)),
+               dict(mask_input_grad=True), dict(grad_premasked=True), dict(chain=dl.GradChain(2))):
+        with pytest.raises(ValueError):
+            dl.linear(x, w, None, **kw)
+
+
+def test_grad_sinks_take_parameters_only():
+    """linear.GradSinks.lookup: a weight-gradient kernel may reduce into a registered buffer only if the Linear's weight (and
+    bias) ARE the registered parameters -- slices / products of parameters are post-processed by autograd and keep the
+    ordinary path; shape, density and alignment of the buffer are checked."""
+    lin = torch.nn.Linear(32, 16)
+    flat = torch.zeros(16 * 32 + 16 + 4)
+    vw, vb = flat[:512].view(16, 32), flat[512:528]
+    sinks = dl.GradSinks({id(lin.weight): vw, id(lin.bias): vb})
+    sw, sb = sinks.lookup(lin.weight, lin.bias, True)
+    assert sw.data_ptr() == vw.data_ptr() and sb.data_ptr() == vb.data_ptr()
+    assert sinks.lookup(lin.weight, lin.bias, False)[1] is None            # no bias gradient wanted
+    assert sinks.lookup(lin.weight[:8], lin.bias[:8], True) is None        # a slice is not the parameter
+    assert sinks.lookup(lin.weight * 2.0, lin.bias, True) is None          # nor is a BN-folded product
+    assert sinks.lookup(lin.weight, None, True) is None
+    other = torch.nn.Linear(32, 16)
+    assert sinks.lookup(other.weight, other.bias, True) is None            # not registered
+    assert dl.GradSinks({id(lin.weight): flat[1:513].view(16, 32)}).lookup(lin.weight, None, False) is None   # misaligned
+    assert dl.GradSinks({id(lin.weight): flat[:512].view(32, 16)}).lookup(lin.weight, None, False) is None    # other shape
+
+
+def test_step_graphs_drop_training_captures_when_the_gradient_buffer_moves():
+    """graphs.StepGraphs.set_grad_sinks: captures made against an earlier FlatGradients buffer would add into memory nobody
+    reads; registering a new buffer for the same parameters forgets them (they are captured again on next use)."""
+    from datr_b200 import graphs
+    from datr_b200.parallel import FlatGradients
+    net = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
+    sg = graphs.StepGraphs()
+    a = FlatGradients(net)
+    sg.set_grad_sinks(a)
+    assert len(sg.grad_sinks) == 4 and all(sg.grad_sinks[id(p)].data_ptr() == p.grad.data_ptr() for p in net.parameters())
+    sg.cache[("enc", 0, True, None, ())] = ("training graph", 3)
+    sg.cache[("enc", 0, False, None, ())] = ("inference graph", 3)
+    sg.per_segment[("enc", 0)] = 2
+    sg.set_grad_sinks(a)                                   # same buffer: nothing to forget
+    assert len(sg.cache) == 2
+    b = FlatGradients(net)                                 # new buffer for the same parameters
+    sg.set_grad_sinks(b)
+    assert list(sg.cache) == [("enc", 0, False, None, ())] and sg.per_segment[("enc", 0)] == 1
+    assert all(sg.grad_sinks[id(p)].data_ptr() == p.grad.data_ptr() for p in net.parameters())
+    sg.set_grad_sinks(FlatGradients(net, gather=True))     # gather mode has no persistent views: ignored
+    assert all(sg.grad_sinks[id(p)].data_ptr() == v.data_ptr() for p, v in zip(b.params, b.views))
+
+
+def test_resnet_stage_runner_is_the_sequential_on_the_plain_path():
+    """backbone.run_stage only re-routes gradients on the tensor-core path; elsewhere it is stage(x) -- same output, same
+    gradients."""
+    from datr_b200.models.dino import backbone as bb
+    torch.manual_seed(0)
+    down = torch.nn.Sequential(torch.nn.Conv2d(16, 32, 1, stride=2, bias=False), bb.FrozenBatchNorm2d(32))
+    stage = torch.nn.Sequential(bb.Bottleneck(16, 8, stride=2, downsample=down), bb.Bottleneck(32, 8), bb.Bottleneck(32, 8))
+    x = torch.randn(2, 16, 12, 10)
+    outs = []
+    for fn in (lambda t: bb.run_stage(stage, t), stage):
+        xa = x.clone().requires_grad_(True)
+        stage.zero_grad()
+        y = fn(xa)
+        y.square().sum().backward()
+        outs.append([y.detach(), xa.grad] + [p.grad.clone() for p in stage.parameters()])
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
