@@ -88,19 +88,23 @@ def gpu_baseline_record():
     """The reference model itself on a B200 of this pool (tools/bench_reference_gpu.py; committed measurement)."""
     out = {}
     for tag in ("4scale", "5scale"):
-        p = os.path.join(ROOT, "profiles", f"r02bb_reference_gpu_{tag}_init.json")
+        # newest committed measurement first (r02bq: timing-only run at the end of round 2, 4 scales)
+        cands = [os.path.join(ROOT, "profiles", f"r02bq_reference_gpu_{tag}_timing.json"),
+                 os.path.join(ROOT, "profiles", f"r02bb_reference_gpu_{tag}_init.json")]
+        p = next((c for c in cands if os.path.exists(c)), cands[-1])
         if os.path.exists(p):
             try:
                 d = json.load(open(p))
                 out[tag] = {k: {"ms_per_step": v.get("ms_per_step"), "images_per_s": v.get("images_per_s")}
                             for k, v in d.get("reference_step", {}).items() if "ms_per_step" in v}
                 out[tag]["ours_same_run"] = d.get("ours_step")
+                out[tag]["file"] = os.path.relpath(p, ROOT)
             except Exception:
                 pass
     if out:
         out["what"] = ("UNMODIFIED reference DINO (baseline/_ref) + its own MSDeformAttn CUDA extension rebuilt for sm_100a "
                        "(oracle/_ref), eager engine.py step on one B200 of this pool, identical synthetic batch; measured by "
-                       "tools/bench_reference_gpu.py in an earlier gpurun call (profiles/r02bb_reference_gpu_*_init.json), "
+                       "tools/bench_reference_gpu.py in an earlier gpurun call (the `file` of each entry), "
                        "NOT in this run; --gpu-baseline re-measures it live")
     return out or None
 
