@@ -1,11 +1,16 @@
 """CUDA graphs for the static segments of the DINO training step.
 
-The step is launch-bound on the host (tools/segment_times.py: ~10 k kernel launches, forward 47 ms of pure enqueue
-time).  The ResNet body, the deformable encoder and the decoder are pure tensor functions with static shapes for a
-fixed image size / number of de-noising queries, so each is captured ONCE -- forward and backward -- with
-torch.cuda.make_graphed_callables and replayed afterwards: no Python, no per-kernel launch cost.  The pieces in between
-(de-noising query construction, two-stage top-k, heads, prototypes, criterion with the scipy Hungarian matcher)
-stay eager because they depend on the targets or synchronise with the host.
+Launched kernel by kernel the step is bound by the host (tools/segment_times.py: ~10 k launches, 47 ms of pure enqueue time
+for the forward alone).  The ResNet body, the input projections, the level flattening, the deformable encoder, the two-stage
+query selection, the decoder, the prediction heads, the image-level discriminator and the criterion's losses are pure tensor
+functions with static shapes for a fixed image size / number of de-noising queries / number of boxes, so each is captured ONCE
+-- forward and backward, following the protocol of torch.cuda.make_graphed_callables (_TrainingGraph below) -- and replayed
+afterwards: no Python, no per-kernel launch cost.  What stays eager in between depends on the targets (de-noising query
+construction, the matcher's cost matrices and the GPU Hungarian solver, prototype bookkeeping).
+
+What the captured backward does beyond torch's version: parameter gradients go INTO the step's flat gradient
+buffer inside the graph (`set_grad_sinks`), small weight-gradient GEMMs fork onto a parallel branch, and a segment can be
+replayed on a second stream beside its neighbours (`call(..., side=True)` / `join_side()`).
 
 Usage (what bench_dino.DinoStep does):
     graphs.ACTIVE = graphs.StepGraphs()      # opt in
