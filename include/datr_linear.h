@@ -50,7 +50,9 @@ int datr_linear_tf32(const float* x, const float* w, const float* bias, const fl
  */
 int datr_linear_wgrad_tf32(const float* dz, const float* x, float* dw, float* db, int M, int N, int K, void* stream);
 /* dw += dz^T x, db += column sums of dz: no zero fill -- the reductions land in a buffer that already holds gradient
- * (what autograd's AccumulateGrad does with `param.grad += new` after `grad_output.t().mm(input)`, in one kernel). */
+ * (what autograd's AccumulateGrad does with `param.grad += new` after `grad_output.t().mm(input)` during the reference's
+ * `optimizer.zero_grad(); losses.backward()`, engine.py:98-99 -- here in the weight-gradient kernel itself; dw / db are the
+ * parameter's slices of the step's flat gradient buffer, zeroed once per step by the caller). */
 int datr_linear_wgrad_tf32_acc(const float* dz, const float* x, float* dw, float* db, int M, int N, int K, void* stream);
 const char* datr_linear_wgrad_last_error(void);
 uint64_t datr_linear_wgrad_launch_count(void);
