@@ -75,6 +75,14 @@ def test_bad_arguments_return_error_codes_without_touching_the_gpu():
     assert lib.datr_linear_bf16(p, p, None, None, 0, p, 0, 8, 64, 96, 0, None) == -1 and b"64" in lib.datr_linear_last_error()
     assert lib.datr_linear_bf16(p, p, None, p, 0, p, 1, 8, 256, 64, 0, None) == -1                               # bf16 output + fp32 residual
     assert lib.datr_linear_wgrad_bf16(None, p, p, None, 8, 64, 64, None) == -1
+    # backward-pass entry points of DESIGN.md 4.15
+    assert lib.datr_linear_tf32_bt_masked(p, p, None, None, p, 128, 64, 32, None) == -1 and b"mask" in lib.datr_linear_last_error()
+    assert lib.datr_linear_tf32_bt_masked(None, p, None, p, p, 128, 64, 32, None) == -1
+    assert lib.datr_linear_tf32_bt_masked(p, p, None, p, p, 128, 64, 33, None) == -1 and b"32" in lib.datr_linear_last_error()
+    assert lib.datr_linear_tf32_bt(p, p, None, None, p, 128, 64, 32, 4, None) == -1            # relu 4 is the masked entry point's
+    assert lib.datr_linear_wgrad_tf32_acc(None, p, p, None, 8, 64, 64, None) == -1
+    assert lib.datr_linear_wgrad_tf32_acc(p, p, p, None, 8, 62, 64, None) == -1 and b"multiples of 4" in lib.datr_linear_wgrad_last_error()
+    assert lib.datr_linear_wgrad_bf16_acc(p, p, p, None, 8, 60, 64, None) == -1 and b"multiples of 8" in lib.datr_linear_wgrad_last_error()
     assert lib.datr_sine_embed(p, p, 4, 3, p, None) == -1
     assert lib.datr_adamw_step(None, None, 1, None, 0.9, 0.999, 1e-8, 0.1, 0.03, None) == -1
     assert lib.datr_adamw_step(p, p, 1, None, 0.9, 0.999, 1e-8, 0.0, 0.03, None) == -1                           # bias correction must be > 0
