@@ -14,12 +14,13 @@ Works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU test
 Two ways of getting the gradients into the buffer:
   * gather=False: every .grad IS its slice of the buffer during the backward; eagerly, autograd runs one tiny
     `grad += new` kernel per gradient arrival (640 parameters in a DINO step); under CUDA graphs the captured backward of
-    each segment adds its gradients into the slices itself with multi-tensor launches (graphs._TrainingGraph);
+    each segment puts its gradients into the slices itself -- the weight-gradient kernels of parameter-owning Linears reduce
+    straight into them, the rest is added with multi-tensor launches (graphs._TrainingGraph, linear.GradSinks);
   * gather=True: .grad is None during the backward, so autograd simply keeps the first gradient tensor of a
     parameter (no kernel) and adds in place only for a second arrival; collect() then moves everything into the buffer
     with ONE multi-tensor copy and re-points .grad at the slices for the optimizer.
-Measured on the B200 DINO step both take the same time (68.0 vs 67.9 ms: with CUDA graphs the per-parameter
-accumulation is a small part of the ~5 000 short kernels of a step), so the simpler gather=False stays the default."""
+Measured on the B200 DINO step in round 1 both took the same time (68.0 vs 67.9 ms); gather=False is the default and what
+the in-graph accumulation builds on (the views must stay in place between steps: zero(), not `p.grad = None`)."""
 from __future__ import annotations
 
 import torch
