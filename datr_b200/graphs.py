@@ -12,6 +12,10 @@ What the captured backward does beyond torch's version: paramet
 buffer inside the graph (`set_grad_sinks`), small weight-gradient GEMMs fork onto a parallel branch, and a segment can be
 replayed on a second stream beside its neighbours (`call(..., side=True)` / `join_side()`).
 
+Precondition of the first (capturing) call, as for torch's own make_graphed_callables: no autograd graph of an EARLIER eager
+pass over the same parameters may still be alive (a kept loss tensor is enough) -- its AccumulateGrad nodes belong to the
+default stream, and the capture fails loudly with cudaErrorStreamCaptureImplicit rather than make that stream wait.
+
 Usage (what bench_dino.DinoStep does):
     graphs.ACTIVE = graphs.StepGraphs()      # opt in
     ...each step:  graphs.ACTIVE.begin_step(); loss = criterion(model(...)); loss.backward()

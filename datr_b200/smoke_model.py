@@ -67,3 +67,47 @@ def run():
     assert err < 2e-2, err
     print(f"[smoke] tensor-core mode ok: loss={loss_tc.item():.4f}, hand-written kernel launches={c1[3] - c0[3]} "
           f"(linear {c1[0] - c0[0]}, weight gradient {c1[1] - c0[1]}, attention {c1[2] - c0[2]}), bf16 FFN rel err {err:.1e}")
+
+    # and as the benchmark replays it (datr_b200.graphs): every static segment as a CUDA graph, parameter gradients put
+    # into the flat buffer inside the captured backward, small weight gradients on the graph's parallel branch, the image
+    # discriminator on a second stream.  First step captures, second replays.
+    from datr_b200 import graphs
+    # the eager steps' autograd graphs must be gone before the first capture: their AccumulateGrad nodes belong to the default
+    # stream, and a capture must not make that stream wait (torch's own make_graphed_callables has the same precondition)
+    del out, losses, loss, loss_tc, y, ref, x, w1, b1, w2, b2, g
+    import gc
+    gc.collect()
+    fast = model.to(memory_format=torch.channels_last)
+    sg = graphs.StepGraphs()
+    graphs.ACTIVE = sg
+    dl.set_mode("tf32")
+    try:
+        flat = FlatGradients(fast)
+        timgs = torch.zeros(4, 3, 160, 200, device="cuda")
+        from datr_b200.util.misc import NestedTensor
+        mask = torch.ones(4, 160, 200, dtype=torch.bool, device="cuda")
+        for i, im in enumerate(imgs):
+            timgs[i, :, :im.shape[1], :im.shape[2]] = im
+            mask[i, :im.shape[1], :im.shape[2]] = False
+        samples = NestedTensor(timgs.contiguous(memory_format=torch.channels_last), mask)
+        for it in range(2):
+            sg.begin_step()
+            flat.zero()
+            torch.manual_seed(0)
+            out = fast(samples, targets)
+            losses = criterion(out, targets)
+            loss_g = losses["_weighted_total"] if "_weighted_total" in losses else \
+                sum(losses[k] * criterion.weight_dict[k] for k in losses if k in criterion.weight_dict)
+            loss_g.backward()
+        torch.cuda.synchronize()
+    finally:
+        graphs.ACTIVE = None
+        dl.set_mode("fp32")
+    tgs = [g for g, _ in sg.cache.values() if isinstance(g, graphs._TrainingGraph)]
+    assert torch.isfinite(loss_g).item() and torch.isfinite(flat.flat).all().item()
+    assert float(flat.flat.abs().max()) > 0 and flat.check_views()
+    assert sg.captures >= 5 and sum(g.n_sunk for g in tgs) > 0, (sg.captures, sum(g.n_sunk for g in tgs))
+    print(f"[smoke] graph replay ok: loss={float(loss_g.detach()):.4f}, {sg.captures} segments, "
+          f"{sum(g.n_sunk for g in tgs)} parameter gradients accumulated inside the captured backward, "
+          f"{sum(g.side_launches for g in tgs)} launches on the parallel branch")
+
