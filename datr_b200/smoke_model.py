@@ -1,5 +1,6 @@
 """Second half of __graft_entry__.smoke(): one tiny DINO training step on cuda:0 (forward, losses, backward) with
-the CUDA MSDeformAttn kernels, checked for finiteness and for launch counts."""
+the CUDA MSDeformAttn kernels, checked for finiteness and for launch counts; the same step in the benchmarked
+tensor-core mode (+ clip / AdamW); and the step replayed as CUDA-graph segments the way bench.py runs it."""
 import torch
 
 
